@@ -1,0 +1,78 @@
+"""
+Pins the CPU oracle (oracle/fw_oracle.c + oracle/oracle.py) against the
+fixtures generated from the LIVE reference (tests/golden/make_golden.py).
+
+Bar: bit-exact for u, every state variable, activation-time maps, point
+samplers and the stencil weights (same operation order, same libm);
+ECG traces within 1e-12 relative (the reference's prange reduction order is
+unspecified).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.cases import make_cases, max_rel_err
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CASES = make_cases()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    oracle.build()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_matches_reference(case):
+    g = np.load(GOLDEN / (case["name"] + ".npz"))
+    out = oracle.simulate(case, return_model=True)
+    ecg_keys = {f"tracker{i}" for i, t in enumerate(case.get("trackers", []))
+                if t["kind"] == "ecg"}
+    assert np.array_equal(out["_weights"], g["weights"]), "stencil weights differ"
+    for k in g.files:
+        if k in ("checksum", "weights"):
+            continue
+        if k in ecg_keys:
+            assert max_rel_err(out[k], g[k]) <= 1e-12, k
+        else:
+            assert out[k].shape == g[k].shape, k
+            assert np.array_equal(out[k], g[k]), f"{k}: {max_rel_err(out[k], g[k]):.3e}"
+
+
+def test_golden_inputs_unchanged():
+    """The case definitions still produce the inputs the fixtures were made from."""
+    from tests.golden.make_golden import input_checksum
+    for case in CASES:
+        g = np.load(GOLDEN / (case["name"] + ".npz"))
+        assert str(g["checksum"]) == input_checksum(case), case["name"]
+
+
+def test_reference_fingerprints():
+    """SURVEY.md App. C fingerprints of the README quick start."""
+    g = np.load(GOLDEN / "c1_ap2d_readme.npz")
+    assert float(g["u"].sum()) == 5997.748456816207
+    assert float(g["v"].sum()) == 794.2711218120692
+    assert float(g["u"].max()) == 0.9899530914614856
+    assert float(g["t"]) == 9.999999999999831
+    assert np.allclose(g["weights"][50, 50], [0.16, 0.16, 0.36, 0.16, 0.16])
+    assert np.allclose(g["weights"][1, 1], [0, 0, 0.36, 0.32, 0.32])
+
+
+def test_quirks():
+    """SURVEY.md App. A.4 quirks present in the fixtures (and so in the oracle)."""
+    g = np.load(GOLDEN / "tp06_2d_iso.npz")
+    assert np.all(g["cai"] == 0.00007), "TP06 cai must stay frozen"
+    g = np.load(GOLDEN / "c3_ms3d_iso_focal.npz")
+    act = g["tracker0"]
+    assert act[0, 0, 0] == -1 and act[12, 12, 12] == 0.0
+    # current stim fires duration/dt + 1 times: (t0=0.5, dur=0.5, dt=0.01) -> 51
+    t, n = 0.0, 0
+    for _ in range(600):
+        if t >= 0.5:
+            n += 1
+            if t >= 0.5 + 0.5:
+                break
+        t += 0.01
+    assert n == 51
