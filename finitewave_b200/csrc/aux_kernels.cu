@@ -1,0 +1,373 @@
+// aux_kernels.cu -- index structures, layout conversions, stimuli, tracker helpers.
+#include "aux_kernels.cuh"
+
+namespace fwb {
+
+// ---------------------------------------------------------------------------
+// chunk bits + exclusive prefix popcount (replaces the int64 myo_indexes list of
+// finitewave/core/tissue/cardiac_tissue.py:54-63)
+// ---------------------------------------------------------------------------
+__global__ void chunk_bits_kernel(const uint8_t *mask, int64_t n_nodes, uint32_t *bits,
+                                  int64_t n_chunks)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const int64_t n = gw * 32 + lane;
+    const bool on = n < n_nodes && mask[n] != 0;
+    const uint32_t b = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[gw] = b;
+}
+
+constexpr int SCAN_ITEMS = 4096;   // chunks per scan block (1024 threads x 4)
+
+// pass 1: per-block popcount totals
+__global__ void __launch_bounds__(1024) scan_totals_kernel(const uint32_t *bits, int64_t n_chunks,
+                                                           unsigned long long *block_tot)
+{
+    __shared__ unsigned long long sh[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS;
+    unsigned long long v = 0;
+    for (int q = 0; q < 4; ++q) {
+        const int64_t i = base + q * 1024 + threadIdx.x;
+        if (i < n_chunks) v += __popc(bits[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sh[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) block_tot[blockIdx.x] = v;
+    }
+}
+
+// pass 2: exclusive scan of the block totals (single thread block, serial over
+// at most a few thousand entries per thread-strided segment)
+__global__ void scan_blocks_kernel(unsigned long long *block_tot, int n_blocks,
+                                   unsigned long long *total)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < n_blocks; ++i) {
+            const unsigned long long v = block_tot[i];
+            block_tot[i] = run;
+            run += v;
+        }
+        *total = run;
+    }
+}
+
+// pass 3: exclusive scan inside each block + block offset
+__global__ void __launch_bounds__(1024) scan_final_kernel(const uint32_t *bits, int64_t n_chunks,
+                                                          const unsigned long long *block_off,
+                                                          uint32_t *base_out)
+{
+    __shared__ unsigned int warp_tot[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS;
+    // thread handles 4 consecutive chunks
+    const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+    unsigned int p[4], sum = 0;
+    for (int q = 0; q < 4; ++q) {
+        p[q] = (i0 + q < n_chunks) ? __popc(bits[i0 + q]) : 0;
+        sum += p[q];
+    }
+    // inclusive warp scan of per-thread sums
+    unsigned int inc = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = warp_tot[lane];
+        unsigned int winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;   // exclusive
+    }
+    __syncthreads();
+    unsigned long long run = block_off[blockIdx.x] + warp_tot[warp] + (inc - sum);
+    for (int q = 0; q < 4; ++q) {
+        if (i0 + q < n_chunks) base_out[i0 + q] = (uint32_t)run;
+        run += p[q];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dense <-> compact
+// ---------------------------------------------------------------------------
+__global__ void gather_kernel(const double *dense, double *compact, int64_t n_chunks,
+                              const uint32_t *bits, const uint32_t *base)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const uint32_t b = bits[gw];
+    if ((b >> lane) & 1u)
+        compact[(int64_t)base[gw] + __popc(b & ((1u << lane) - 1u))] = dense[gw * 32 + lane];
+}
+
+__global__ void scatter_kernel(const double *compact, double *dense, double fill,
+                               int64_t n_nodes, int64_t n_chunks, const uint32_t *bits,
+                               const uint32_t *base)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const uint32_t b = bits[gw];
+    const int64_t n = gw * 32 + lane;
+    if (n >= n_nodes) return;
+    dense[n] = ((b >> lane) & 1u)
+                   ? compact[(int64_t)base[gw] + __popc(b & ((1u << lane) - 1u))]
+                   : fill;
+}
+
+__global__ void weights_pack_kernel(const double *aos, double *soa, int K, int64_t ld,
+                                    int64_t n_chunks, const uint32_t *bits, const uint32_t *base)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const uint32_t b = bits[gw];
+    if (!((b >> lane) & 1u)) return;
+    const int64_t c = (int64_t)base[gw] + __popc(b & ((1u << lane) - 1u));
+    const int64_t n = gw * 32 + lane;
+    for (int k = 0; k < K; ++k) soa[(int64_t)k * ld + c] = aos[n * K + k];
+}
+
+__global__ void weights_unpack_kernel(const double *soa, double *aos, int K, int64_t ld,
+                                      int64_t n_nodes, int64_t n_chunks, const uint32_t *bits,
+                                      const uint32_t *base)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const uint32_t b = bits[gw];
+    const int64_t n = gw * 32 + lane;
+    if (n >= n_nodes) return;
+    const bool on = (b >> lane) & 1u;
+    const int64_t c = (int64_t)base[gw] + __popc(b & ((1u << lane) - 1u));
+    // nodes the solver does not update show the reference's untouched row: all zero
+    // except the +1 on the centre slot (isotropic_stencil_2d.py:66-67 and twins)
+    const int centre = K == 5 ? 2 : K == 7 ? 3 : 4;
+    for (int k = 0; k < K; ++k)
+        aos[n * K + k] = on ? soa[(int64_t)k * ld + c] : (k == centre ? 1.0 : 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// stimuli (cpuwave{2D,3D}/stimulation/*.py `stimulate`), ROI sized
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void stim_apply(double *u, int64_t n, int mode, double value,
+                                           double dt_value, int has_u_max, double u_max)
+{
+    if (mode == FWB_STIM_CURRENT) {
+        double v = u[n] + dt_value;                 // u += dt * curr_value
+        if (has_u_max && v > u_max) v = u_max;      // np.where(u > u_max, u_max, u)
+        u[n] = v;
+    } else {
+        u[n] = value;
+    }
+}
+
+__global__ void stim_box_kernel(double *u, const uint8_t *tissue, StimBox b, int mode,
+                                double value, double dt_value, int has_u_max, double u_max)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= b.count) return;
+    const int64_t l = q % b.e2, r = (q / b.e2) % b.e1, p = q / (b.e2 * b.e1);
+    const int64_t n = (b.o0 + p) * b.s0 + (b.o1 + r) * b.s1 + (b.o2 + l);
+    if (tissue[n] != 1) return;
+    stim_apply(u, n, mode, value, dt_value, has_u_max, u_max);
+}
+
+__global__ void stim_nodes_kernel(double *u, const int64_t *nodes, int64_t count, int mode,
+                                  double value, double dt_value, int has_u_max, double u_max)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    stim_apply(u, nodes[q], mode, value, dt_value, has_u_max, u_max);
+}
+
+// ---------------------------------------------------------------------------
+// tracker helpers
+// ---------------------------------------------------------------------------
+// extra ActivationTime trackers beyond the fused one
+__global__ void act_kernel(double *act_t, const double *u, int64_t n_nodes, double thr, double t)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    if (act_t[n] < 0 && u[n] > thr) act_t[n] = t;
+}
+
+// deterministic sum of the per-block ECG partials: one block per lead
+__global__ void __launch_bounds__(256) ecg_finalize_kernel(const double *partial, int64_t n_blocks,
+                                                           int n_leads, double *out)
+{
+    __shared__ double sh[256];
+    const int lead = blockIdx.x;
+    double v = 0.0;
+    for (int64_t b = threadIdx.x; b < n_blocks; b += 256) v += partial[b * n_leads + lead];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[lead] = sh[0];
+}
+
+// point samplers: item = (var, flat node, compact index)
+__global__ void point_gather_kernel(const int64_t *items, const double *fill, int n_items,
+                                    const double *u, const double *state, int64_t ld, double *out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_items) return;
+    const int64_t var = items[3 * q], n = items[3 * q + 1], c = items[3 * q + 2];
+    double v;
+    if (var == 0) v = u[n];
+    else v = (c >= 0) ? state[(var - 1) * ld + c] : fill[q];
+    out[q] = v;
+}
+
+static inline unsigned warp_blocks(int64_t n_chunks, int threads)
+{
+    return (unsigned)((n_chunks * 32 + threads - 1) / threads);
+}
+
+int launch_stim_box(double *u, const uint8_t *tissue, const StimBox &b, int mode, double value,
+                    double dt_value, int has_u_max, double u_max, cudaStream_t s)
+{
+    if (b.count <= 0) return 0;
+    stim_box_kernel<<<(unsigned)((b.count + 255) / 256), 256, 0, s>>>(u, tissue, b, mode, value,
+                                                                        dt_value, has_u_max, u_max);
+    FWB_KERNEL_CHECK("stim_box_kernel");
+    return 0;
+}
+
+int launch_stim_nodes(double *u, const int64_t *nodes, int64_t count, int mode, double value,
+                      double dt_value, int has_u_max, double u_max, cudaStream_t s)
+{
+    if (count <= 0) return 0;
+    stim_nodes_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(u, nodes, count, mode, value,
+                                                                        dt_value, has_u_max, u_max);
+    FWB_KERNEL_CHECK("stim_nodes_kernel");
+    return 0;
+}
+
+int launch_act(double *act_t, const double *u, int64_t n_nodes, double thr, double t,
+               cudaStream_t s)
+{
+    if (n_nodes <= 0) return 0;
+    act_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(act_t, u, n_nodes, thr, t);
+    FWB_KERNEL_CHECK("act_kernel");
+    return 0;
+}
+
+int launch_ecg_finalize(const double *partial, int64_t n_blocks, int n_leads, double *out,
+                        cudaStream_t s)
+{
+    if (n_leads <= 0) return 0;
+    ecg_finalize_kernel<<<n_leads, 256, 0, s>>>(partial, n_blocks, n_leads, out);
+    FWB_KERNEL_CHECK("ecg_finalize_kernel");
+    return 0;
+}
+
+int launch_point_gather(const int64_t *items, const double *fill, int n_items, const double *u,
+                        const double *state, int64_t ld, double *out, cudaStream_t s)
+{
+    if (n_items <= 0) return 0;
+    point_gather_kernel<<<(n_items + 63) / 64, 64, 0, s>>>(items, fill, n_items, u, state, ld, out);
+    FWB_KERNEL_CHECK("point_gather_kernel");
+    return 0;
+}
+
+}  // namespace fwb
+
+using namespace fwb;
+
+extern "C" int fwb_build_chunks(const uint8_t *update_mask, int64_t n_nodes,
+                                uint32_t *chunk_bits, uint32_t *chunk_base,
+                                int64_t *n_myo, fwb_stream_t stream)
+{
+    if (!update_mask || !chunk_bits || !chunk_base || n_nodes <= 0) {
+        set_error("fwb_build_chunks: bad argument");
+        return FWB_E_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    chunk_bits_kernel<<<warp_blocks(n_chunks, 256), 256, 0, s>>>(update_mask, n_nodes, chunk_bits,
+                                                                  n_chunks);
+    FWB_KERNEL_CHECK("chunk_bits_kernel");
+    const int n_sb = (int)((n_chunks + SCAN_ITEMS - 1) / SCAN_ITEMS);
+    unsigned long long *tot = nullptr;
+    FWB_CUDA(cudaMallocAsync((void **)&tot, sizeof(unsigned long long) * (n_sb + 1), s));
+    scan_totals_kernel<<<n_sb, 1024, 0, s>>>(chunk_bits, n_chunks, tot);
+    FWB_KERNEL_CHECK("scan_totals_kernel");
+    scan_blocks_kernel<<<1, 32, 0, s>>>(tot, n_sb, tot + n_sb);
+    FWB_KERNEL_CHECK("scan_blocks_kernel");
+    scan_final_kernel<<<n_sb, 1024, 0, s>>>(chunk_bits, n_chunks, tot, chunk_base);
+    FWB_KERNEL_CHECK("scan_final_kernel");
+    unsigned long long total = 0;
+    FWB_CUDA(cudaMemcpyAsync(&total, tot + n_sb, sizeof(total), cudaMemcpyDeviceToHost, s));
+    FWB_CUDA(cudaStreamSynchronize(s));
+    FWB_CUDA(cudaFreeAsync(tot, s));
+    if (total > 0xffffffffULL) {
+        set_error("fwb_build_chunks: more than 2^32 updated nodes on one device");
+        return FWB_E_UNSUPPORTED;
+    }
+    if (n_myo) *n_myo = (int64_t)total;
+    return 0;
+}
+
+extern "C" int fwb_gather_compact(const double *dense, double *compact, int64_t n_nodes,
+                                  const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                                  fwb_stream_t stream)
+{
+    if (!dense || !compact || !chunk_bits || !chunk_base) { set_error("fwb_gather_compact: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    gather_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        dense, compact, n_chunks, chunk_bits, chunk_base);
+    FWB_KERNEL_CHECK("gather_kernel");
+    return 0;
+}
+
+extern "C" int fwb_scatter_compact(const double *compact, double *dense, double fill,
+                                   int64_t n_nodes, const uint32_t *chunk_bits,
+                                   const uint32_t *chunk_base, fwb_stream_t stream)
+{
+    if (!dense || !compact || !chunk_bits || !chunk_base) { set_error("fwb_scatter_compact: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    scatter_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        compact, dense, fill, n_nodes, n_chunks, chunk_bits, chunk_base);
+    FWB_KERNEL_CHECK("scatter_kernel");
+    return 0;
+}
+
+extern "C" int fwb_weights_pack(const double *dense_aos, double *compact_soa, int K, int64_t ld,
+                                int64_t n_nodes, const uint32_t *chunk_bits,
+                                const uint32_t *chunk_base, fwb_stream_t stream)
+{
+    if (!dense_aos || !compact_soa || K <= 0) { set_error("fwb_weights_pack: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    weights_pack_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        dense_aos, compact_soa, K, ld, n_chunks, chunk_bits, chunk_base);
+    FWB_KERNEL_CHECK("weights_pack_kernel");
+    return 0;
+}
+
+extern "C" int fwb_weights_unpack(const double *compact_soa, double *dense_aos, int K, int64_t ld,
+                                  int64_t n_nodes, const uint32_t *chunk_bits,
+                                  const uint32_t *chunk_base, fwb_stream_t stream)
+{
+    if (!dense_aos || !compact_soa || K <= 0) { set_error("fwb_weights_unpack: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    weights_unpack_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        compact_soa, dense_aos, K, ld, n_nodes, n_chunks, chunk_bits, chunk_base);
+    FWB_KERNEL_CHECK("weights_unpack_kernel");
+    return 0;
+}

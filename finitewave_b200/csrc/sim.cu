@@ -1,0 +1,461 @@
+// sim.cu -- C ABI of the step backend: FwbSim and the per-step runner.
+//
+// fwb_sim_run reproduces, per step, the order of CardiacModel.run's loop body
+// (finitewave/core/model/cardiac_model.py:164-189):
+//   1. stimuli whose time has come (stim_sequence.py:65-77, stim.py:52-56)
+//   2. fused diffusion + ionic step (one kernel)
+//   3. native trackers whose gate passes (tracker.py:70-84) -- fused in (2)
+//      for the first ActivationTime / ECG tracker, tiny extra launches otherwise
+//   4. t += dt (fp64, as the reference's Python float), step += 1, swap(u, u_new)
+// Host hooks (commands, state savers, user trackers) are the caller's business:
+// it asks for exactly as many steps as may run before the next hook is due.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "step_kernel.cuh"
+
+namespace fwb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+extern const ModelEntry g_entry_aliev_panfilov, g_entry_barkley, g_entry_mitchell_schaeffer,
+    g_entry_fenton_karma, g_entry_luo_rudy91, g_entry_tp06, g_entry_nomodel;
+
+const ModelEntry *model_entry(int model)
+{
+    switch (model) {
+    case FWB_MODEL_ALIEV_PANFILOV: return &g_entry_aliev_panfilov;
+    case FWB_MODEL_BARKLEY: return &g_entry_barkley;
+    case FWB_MODEL_MITCHELL_SCHAEFFER: return &g_entry_mitchell_schaeffer;
+    case FWB_MODEL_FENTON_KARMA: return &g_entry_fenton_karma;
+    case FWB_MODEL_LUO_RUDY91: return &g_entry_luo_rudy91;
+    case FWB_MODEL_TP06: return &g_entry_tp06;
+    case FWB_N_MODELS: return &g_entry_nomodel;
+    default: return nullptr;
+    }
+}
+
+struct Stim {
+    int kind;            // 0 box, 1 node list
+    int mode;
+    double t, duration, value, u_max;
+    int has_u_max;
+    bool passed;
+    StimBox box;
+    const int64_t *nodes;
+    int64_t n_nodes;
+    std::vector<double> values;   // FWB_STIM_VOLTAGE_LIST
+    int64_t fired;
+};
+
+enum { TR_ACT = 0, TR_ECG = 1, TR_POINT = 2 };
+struct Tracker {
+    int kind;
+    double start, end;
+    int64_t every;
+    int64_t samples;
+    // act
+    double *act_t;
+    double thr;
+    // ecg
+    const double *coords;
+    int n_leads;
+    double dr;
+    // point
+    const int64_t *items;
+    const double *fill;
+    int n_items;
+    // ecg / point output
+    double *out;
+    int64_t capacity;
+};
+
+}  // namespace fwb
+
+using namespace fwb;
+
+struct FwbSim {
+    int dim, model, stencil;
+    int64_t shape[3];
+    Grid g;
+    const ModelEntry *entry;
+    const uint8_t *tissue;
+    int64_t n_myo;
+    double *buf[2];
+    int cur;                   // buf[cur] is u
+    const double *weights;
+    double *state;
+    double dt;
+    double t;
+    int64_t step;
+    cudaStream_t stream;
+    alignas(16) unsigned char consts[CONSTS_BYTES];
+    std::vector<Stim> stims;
+    std::vector<Tracker> trackers;
+    double *ecg_partial;
+    int64_t ecg_partial_cap;
+    int64_t launches;
+};
+
+extern "C" const char *fwb_last_error(void) { return g_err; }
+extern "C" int fwb_version(void) { return FWB_VERSION; }
+
+extern "C" int fwb_model_n_state(int model)
+{
+    const ModelEntry *e = (model >= 0 && model < FWB_N_MODELS) ? model_entry(model) : nullptr;
+    return e ? e->n_state : FWB_E_ARG;
+}
+extern "C" int fwb_model_n_params(int model)
+{
+    const ModelEntry *e = (model >= 0 && model < FWB_N_MODELS) ? model_entry(model) : nullptr;
+    return e ? e->n_params : FWB_E_ARG;
+}
+extern "C" uint32_t fwb_model_read_mask(int model)
+{
+    const ModelEntry *e = (model >= 0 && model < FWB_N_MODELS) ? model_entry(model) : nullptr;
+    return e ? e->read_mask : 0;
+}
+extern "C" uint32_t fwb_model_write_mask(int model)
+{
+    const ModelEntry *e = (model >= 0 && model < FWB_N_MODELS) ? model_entry(model) : nullptr;
+    return e ? e->write_mask : 0;
+}
+extern "C" int fwb_stencil_k(int dim, int stencil)
+{
+    if (dim == 2) return stencil == FWB_STENCIL_ISO ? 5 : stencil == FWB_STENCIL_ANISO ? 9 : FWB_E_ARG;
+    if (dim == 3) return stencil == FWB_STENCIL_ISO ? 7 : stencil == FWB_STENCIL_ANISO ? 19 : FWB_E_ARG;
+    return FWB_E_ARG;
+}
+
+extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int model, int stencil,
+                              const uint8_t *tissue, const uint32_t *chunk_bits,
+                              const uint32_t *chunk_base, int64_t n_myo, int64_t ld,
+                              double *u, double *u_new, const double *weights, double *state,
+                              const double *params, int n_params, double dt, fwb_stream_t stream)
+{
+    if (!out || !shape || (dim != 2 && dim != 3) || !chunk_bits || !chunk_base || !u || !u_new ||
+        !weights || !tissue) {
+        set_error("fwb_sim_create: bad argument");
+        return FWB_E_ARG;
+    }
+    const ModelEntry *e = (model >= 0 && model < FWB_N_MODELS) ? model_entry(model) : nullptr;
+    if (!e) { set_error("fwb_sim_create: unknown model %d", model); return FWB_E_ARG; }
+    if (fwb_stencil_k(dim, stencil) < 0) { set_error("fwb_sim_create: unknown stencil %d", stencil); return FWB_E_ARG; }
+    if (n_params != e->n_params || (n_params > 0 && !params)) {
+        set_error("fwb_sim_create: model %d takes %d parameters, got %d", model, e->n_params, n_params);
+        return FWB_E_ARG;
+    }
+    if (e->n_state > 0 && !state) { set_error("fwb_sim_create: state is NULL"); return FWB_E_ARG; }
+    if (ld < n_myo) { set_error("fwb_sim_create: ld < n_myo"); return FWB_E_ARG; }
+    for (int d = 0; d < dim; ++d)
+        if (shape[d] < 3) { set_error("fwb_sim_create: every axis needs >= 3 nodes"); return FWB_E_ARG; }
+    FwbSim *s = new FwbSim();
+    s->dim = dim; s->model = model; s->stencil = stencil;
+    for (int d = 0; d < 3; ++d) s->shape[d] = d < dim ? shape[d] : 1;
+    s->g = make_grid(dim, shape, chunk_bits, chunk_base, ld);
+    s->entry = e; s->tissue = tissue; s->n_myo = n_myo;
+    s->buf[0] = u; s->buf[1] = u_new; s->cur = 0;
+    s->weights = weights; s->state = state;
+    s->dt = dt; s->t = 0.0; s->step = 0;
+    s->stream = (cudaStream_t)stream;
+    memset(s->consts, 0, sizeof(s->consts));
+    e->derive(params, dt, s->consts);
+    s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0;
+    *out = s;
+    return 0;
+}
+
+extern "C" int fwb_sim_destroy(FwbSim *s)
+{
+    if (!s) return 0;
+    if (s->ecg_partial) cudaFree(s->ecg_partial);
+    delete s;
+    return 0;
+}
+
+extern "C" int fwb_sim_set_time(FwbSim *s, double t, int64_t step)
+{
+    if (!s) return FWB_E_ARG;
+    s->t = t; s->step = step;
+    return 0;
+}
+extern "C" int fwb_sim_get_time(const FwbSim *s, double *t, int64_t *step)
+{
+    if (!s) return FWB_E_ARG;
+    if (t) *t = s->t;
+    if (step) *step = s->step;
+    return 0;
+}
+extern "C" int fwb_sim_current_buffer(const FwbSim *s) { return s ? s->cur : FWB_E_ARG; }
+extern "C" int fwb_sim_set_weights(FwbSim *s, const double *w)
+{
+    if (!s || !w) return FWB_E_ARG;
+    s->weights = w;
+    return 0;
+}
+extern "C" int fwb_sim_set_params(FwbSim *s, const double *params, int n_params, double dt)
+{
+    if (!s || n_params != s->entry->n_params) { set_error("fwb_sim_set_params: bad argument"); return FWB_E_ARG; }
+    s->dt = dt;
+    s->entry->derive(params, dt, s->consts);
+    return 0;
+}
+
+extern "C" int fwb_sim_clear_stims(FwbSim *s)
+{
+    if (!s) return FWB_E_ARG;
+    s->stims.clear();
+    return 0;
+}
+
+static int check_mode(int mode)
+{
+    if (mode != FWB_STIM_VOLTAGE && mode != FWB_STIM_CURRENT && mode != FWB_STIM_VOLTAGE_LIST) {
+        set_error("unknown stimulus mode %d", mode);
+        return FWB_E_ARG;
+    }
+    return 0;
+}
+
+extern "C" int fwb_sim_add_stim_box(FwbSim *s, int mode, double t, double duration, double value,
+                                    int has_u_max, double u_max, const int64_t *box)
+{
+    if (!s || !box) { set_error("fwb_sim_add_stim_box: bad argument"); return FWB_E_ARG; }
+    if (check_mode(mode) || mode == FWB_STIM_VOLTAGE_LIST) { set_error("fwb_sim_add_stim_box: bad mode"); return FWB_E_ARG; }
+    Stim st{};
+    st.kind = 0; st.mode = mode; st.t = t; st.duration = duration; st.value = value;
+    st.has_u_max = has_u_max; st.u_max = u_max; st.passed = false; st.fired = 0;
+    int64_t lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    // (plane,row,line) <- (x,y,z) in 3D, (row,line) <- (x,y) in 2D
+    const int first = 3 - s->dim;
+    for (int d = 0; d < s->dim; ++d) {
+        int64_t a = box[2 * d], b = box[2 * d + 1];
+        const int64_t n = s->shape[d];
+        if (a < 0) a = 0;
+        if (b > n) b = n;
+        if (b < a) b = a;
+        lo[first + d] = a; hi[first + d] = b;
+    }
+    st.box.o0 = lo[0]; st.box.o1 = lo[1]; st.box.o2 = lo[2];
+    st.box.e1 = hi[1] - lo[1]; st.box.e2 = hi[2] - lo[2];
+    st.box.s0 = s->g.s_plane; st.box.s1 = s->g.s_row;
+    st.box.count = (hi[0] - lo[0]) * st.box.e1 * st.box.e2;
+    s->stims.push_back(st);
+    return (int)s->stims.size() - 1;
+}
+
+extern "C" int fwb_sim_add_stim_nodes(FwbSim *s, int mode, double t, double duration, double value,
+                                      int has_u_max, double u_max, const int64_t *nodes,
+                                      int64_t n_nodes, const double *values, int64_t n_values)
+{
+    if (!s || (n_nodes > 0 && !nodes) || check_mode(mode)) { set_error("fwb_sim_add_stim_nodes: bad argument"); return FWB_E_ARG; }
+    Stim st{};
+    st.kind = 1; st.mode = mode; st.t = t; st.duration = duration; st.value = value;
+    st.has_u_max = has_u_max; st.u_max = u_max; st.passed = false; st.fired = 0;
+    st.nodes = nodes; st.n_nodes = n_nodes;
+    if (mode == FWB_STIM_VOLTAGE_LIST) {
+        if (!values || n_values <= 0) { set_error("fwb_sim_add_stim_nodes: VOLTAGE_LIST needs values"); return FWB_E_ARG; }
+        st.values.assign(values, values + n_values);
+    }
+    s->stims.push_back(st);
+    return (int)s->stims.size() - 1;
+}
+
+extern "C" int fwb_sim_stim_passed(const FwbSim *s, int id)
+{
+    if (!s || id < 0 || id >= (int)s->stims.size()) return FWB_E_ARG;
+    return s->stims[id].passed ? 1 : 0;
+}
+extern "C" int fwb_sim_set_stim_passed(FwbSim *s, int id, int passed)
+{
+    if (!s || id < 0 || id >= (int)s->stims.size()) return FWB_E_ARG;
+    s->stims[id].passed = passed != 0;
+    return 0;
+}
+
+extern "C" int fwb_sim_clear_trackers(FwbSim *s)
+{
+    if (!s) return FWB_E_ARG;
+    s->trackers.clear();
+    return 0;
+}
+
+extern "C" int fwb_sim_add_tracker_act(FwbSim *s, double *act_t, double threshold,
+                                       double start_time, double end_time, int64_t every)
+{
+    if (!s || !act_t || every <= 0) { set_error("fwb_sim_add_tracker_act: bad argument"); return FWB_E_ARG; }
+    Tracker tr{};
+    tr.kind = TR_ACT; tr.start = start_time; tr.end = end_time; tr.every = every;
+    tr.act_t = act_t; tr.thr = threshold;
+    s->trackers.push_back(tr);
+    return (int)s->trackers.size() - 1;
+}
+
+extern "C" int fwb_sim_add_tracker_ecg(FwbSim *s, const double *coords, int n_leads, double dr,
+                                       double start_time, double end_time, int64_t every,
+                                       double *out, int64_t capacity)
+{
+    if (!s || !coords || n_leads <= 0 || !out || every <= 0) { set_error("fwb_sim_add_tracker_ecg: bad argument"); return FWB_E_ARG; }
+    for (const Tracker &o : s->trackers)
+        if (o.kind == TR_ECG) { set_error("only one native ECG tracker per simulation"); return FWB_E_UNSUPPORTED; }
+    Tracker tr{};
+    tr.kind = TR_ECG; tr.start = start_time; tr.end = end_time; tr.every = every;
+    tr.coords = coords; tr.n_leads = n_leads; tr.dr = dr; tr.out = out; tr.capacity = capacity;
+    const int64_t need = s->g.n_blocks * n_leads;
+    if (need > s->ecg_partial_cap) {
+        if (s->ecg_partial) cudaFree(s->ecg_partial);
+        FWB_CUDA(cudaMalloc((void **)&s->ecg_partial, sizeof(double) * need));
+        s->ecg_partial_cap = need;
+    }
+    s->trackers.push_back(tr);
+    return (int)s->trackers.size() - 1;
+}
+
+extern "C" int fwb_sim_add_tracker_point(FwbSim *s, const int64_t *items, const double *fill,
+                                         int n_items, double start_time, double end_time,
+                                         int64_t every, double *out, int64_t capacity)
+{
+    if (!s || !items || !fill || n_items <= 0 || !out || every <= 0) { set_error("fwb_sim_add_tracker_point: bad argument"); return FWB_E_ARG; }
+    Tracker tr{};
+    tr.kind = TR_POINT; tr.start = start_time; tr.end = end_time; tr.every = every;
+    tr.items = items; tr.fill = fill; tr.n_items = n_items; tr.out = out; tr.capacity = capacity;
+    s->trackers.push_back(tr);
+    return (int)s->trackers.size() - 1;
+}
+
+extern "C" int64_t fwb_sim_tracker_samples(const FwbSim *s, int id)
+{
+    if (!s || id < 0 || id >= (int)s->trackers.size()) return FWB_E_ARG;
+    return s->trackers[id].samples;
+}
+
+extern "C" int64_t fwb_sim_launch_count(const FwbSim *s) { return s ? s->launches : FWB_E_ARG; }
+
+static inline bool gate(const Tracker &tr, double t, int64_t step)
+{
+    // Tracker.track (core/tracker/tracker.py:70-84)
+    if (tr.start > t || t > tr.end) return false;
+    return step % tr.every == 0;
+}
+
+extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
+{
+    if (!s || n_steps < 0) { set_error("fwb_sim_run: bad argument"); return FWB_E_ARG; }
+    cudaStream_t st = s->stream;
+    for (int64_t it = 0; it < n_steps; ++it) {
+        double *u = s->buf[s->cur];
+        double *u_new = s->buf[s->cur ^ 1];
+        const double t = s->t;
+
+        // 1. stimuli (StimSequence.stimulate_next)
+        for (Stim &sm : s->stims) {
+            if (t >= sm.t && !sm.passed) {
+                double value = sm.value;
+                int mode = sm.mode;
+                if (mode == FWB_STIM_VOLTAGE_LIST) {
+                    if (sm.fired >= (int64_t)sm.values.size()) {
+                        set_error("StimVoltageListMatrix: voltage list exhausted");
+                        return FWB_E_STATE;
+                    }
+                    value = sm.values[sm.fired];
+                    mode = FWB_STIM_VOLTAGE;
+                }
+                const double dt_value = s->dt * sm.value;
+                int rc = sm.kind == 0
+                    ? launch_stim_box(u, s->tissue, sm.box, mode, value, dt_value, sm.has_u_max, sm.u_max, st)
+                    : launch_stim_nodes(u, sm.nodes, sm.n_nodes, mode, value, dt_value, sm.has_u_max, sm.u_max, st);
+                if (rc) return rc;
+                s->launches++;
+                sm.fired++;
+                sm.passed = t >= sm.t + sm.duration;   // Stim.update_status
+            }
+        }
+
+        // 2+3. fused step, with the trackers whose gate passes
+        StepCommon k;
+        memset(&k, 0, sizeof(k));
+        k.g = s->g; k.u = u; k.u_new = u_new; k.w = s->weights; k.state = s->state;
+        k.t = t;
+        bool track = false;
+        Tracker *ecg = nullptr;
+        bool act_fused = false;
+        for (Tracker &tr : s->trackers) {
+            if (!gate(tr, t, s->step)) continue;
+            if (tr.kind == TR_ACT && !act_fused) {
+                k.act_t = tr.act_t; k.act_thr = tr.thr; k.do_act = 1;
+                act_fused = true; track = true; tr.samples++;
+            } else if (tr.kind == TR_ECG) {
+                if (tr.samples >= tr.capacity) { set_error("ECG tracker output buffer full"); return FWB_E_STATE; }
+                k.do_ecg = 1; k.n_leads = tr.n_leads; k.ecg_coords = tr.coords; k.dr = tr.dr;
+                k.ecg_partial = s->ecg_partial;
+                ecg = &tr; track = true;
+            }
+        }
+        int rc = s->entry->launch(s->dim, s->stencil, track, k, s->consts, st);
+        if (rc) return rc;
+        s->launches++;
+        if (ecg) {
+            rc = launch_ecg_finalize(s->ecg_partial, s->g.n_blocks, ecg->n_leads,
+                                     ecg->out + ecg->samples * ecg->n_leads, st);
+            if (rc) return rc;
+            s->launches++;
+            ecg->samples++;
+        }
+        bool first_act = true;
+        for (Tracker &tr : s->trackers) {
+            if (!gate(tr, t, s->step)) continue;
+            if (tr.kind == TR_ACT) {
+                if (first_act) { first_act = false; continue; }   // fused above
+                rc = launch_act(tr.act_t, u, s->g.n_nodes, tr.thr, t, st);
+                if (rc) return rc;
+                s->launches++; tr.samples++;
+            } else if (tr.kind == TR_POINT) {
+                if (tr.samples >= tr.capacity) { set_error("point tracker output buffer full"); return FWB_E_STATE; }
+                rc = launch_point_gather(tr.items, tr.fill, tr.n_items, u, s->state, s->g.ld,
+                                         tr.out + tr.samples * tr.n_items, st);
+                if (rc) return rc;
+                s->launches++; tr.samples++;
+            }
+        }
+
+        // 4. advance
+        s->t += s->dt;
+        s->step += 1;
+        s->cur ^= 1;
+    }
+    return 0;
+}
+
+extern "C" int fwb_diffuse(int dim, int stencil, const int64_t *shape,
+                           const uint32_t *chunk_bits, const uint32_t *chunk_base, int64_t ld,
+                           const double *u, double *u_new, const double *weights,
+                           fwb_stream_t stream)
+{
+    if (!shape || !chunk_bits || !chunk_base || !u || !u_new || !weights ||
+        fwb_stencil_k(dim, stencil) < 0) {
+        set_error("fwb_diffuse: bad argument");
+        return FWB_E_ARG;
+    }
+    StepCommon k;
+    memset(&k, 0, sizeof(k));
+    k.g = make_grid(dim, shape, chunk_bits, chunk_base, ld);
+    k.u = u; k.u_new = u_new; k.w = weights; k.state = nullptr;
+    NoModel::Consts c{0.0};
+    return model_entry(FWB_N_MODELS)->launch(dim, stencil, false, k, &c, (cudaStream_t)stream);
+}

@@ -1,0 +1,247 @@
+"""
+engine.py -- device residency of one simulation (single GPU).
+
+PyTorch is used only to own device / pinned-host buffers and to provide the
+stream; every computation is a call into libfinitewave_b200.so.
+
+Device layout: u, u_new, act_t dense; weights and state
+compact SoA in myocyte order; 1 bit + 1/8 byte of index structure per node.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, shape_arr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.FwbError("finitewave_b200 needs a CUDA device (sm_100a); "
+                            "there is no CPU fallback.")
+
+
+def pinned_empty(shape, dtype=torch.float64):
+    return torch.empty(tuple(int(s) for s in shape), dtype=dtype, pin_memory=True)
+
+
+class Engine:
+    """Device side of one CardiacModel instance."""
+
+    def __init__(self, shape, device=None):
+        require_cuda()
+        self.L = lib()
+        self.device = torch.device(device if device is not None
+                                   else f"cuda:{torch.cuda.current_device()}")
+        self.shape = tuple(int(s) for s in shape)
+        self.dim = len(self.shape)
+        self.n_nodes = int(np.prod(self.shape))
+        self.n_chunks = (self.n_nodes + 31) // 32
+        self.sim = ctypes.c_void_p(0)
+        self.tissue = None       # uint8 dense, mesh == 1
+        self.update = None       # uint8 dense, mesh == 1 & special == 0
+        self.chunk_bits = None
+        self.chunk_base = None
+        self.n_myo = 0
+        self.ld = 0
+        self.weights = None      # [K, ld]
+        self.K = 0
+        self.stencil = None
+        self.state = None        # [S, ld]
+        self.ubuf = [None, None]
+        self.staging = None
+        self._keep = []          # tensors borrowed by the C side (stims, trackers)
+
+    # ---- tissue ---------------------------------------------------------
+    def set_tissue(self, mesh, special_boundaries=None):
+        """mesh: host ndarray or device tensor with values 0/1/2."""
+        dev = self.device
+        if isinstance(mesh, torch.Tensor):
+            m = mesh.to(dev)
+        else:
+            m = torch.from_numpy(np.ascontiguousarray(mesh)).to(dev)
+        tissue = (m == 1)
+        # the solver never updates the outer ring (CardiacTissue.add_boundaries)
+        interior = torch.zeros(self.shape, dtype=torch.bool, device=dev)
+        interior[tuple(slice(1, -1) for _ in self.shape)] = True
+        tissue = tissue & interior
+        update = tissue
+        if special_boundaries is not None:
+            sb = special_boundaries
+            sb = sb.to(dev) if isinstance(sb, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(sb)).to(dev)
+            update = tissue & (sb == 0)
+        self.tissue = tissue.to(torch.uint8).contiguous()
+        self.update = update.to(torch.uint8).contiguous()
+        self.chunk_bits = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
+        self.chunk_base = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
+        n_myo = ctypes.c_int64(0)
+        check(self.L.fwb_build_chunks(_ptr(self.update), self.n_nodes, _ptr(self.chunk_bits),
+                                      _ptr(self.chunk_base), ctypes.byref(n_myo), _stream()),
+              "fwb_build_chunks")
+        self.n_myo = int(n_myo.value)
+        self.ld = max(32, (self.n_myo + 31) // 32 * 32)
+
+    # ---- weights --------------------------------------------------------
+    def compute_weights(self, stencil, conductivity, fibers, D_al, D_ac, D_model, dt, dr):
+        dev = self.device
+        self.stencil = stencil
+        self.K = self.L.fwb_stencil_k(self.dim, stencil)
+        self.weights = torch.empty((self.K, self.ld), dtype=torch.float64, device=dev)
+        cond_t, cond_s = None, 1.0
+        if isinstance(conductivity, torch.Tensor):
+            cond_t = conductivity.to(dev, torch.float64).contiguous()
+        elif np.ndim(conductivity) == 0:
+            cond_s = float(conductivity)
+        else:
+            cond_t = torch.from_numpy(np.ascontiguousarray(
+                conductivity * np.ones(self.shape), dtype=np.float64)).to(dev)
+        fib_t = None
+        if fibers is not None:
+            fib_t = (fibers.to(dev, torch.float64).contiguous() if isinstance(fibers, torch.Tensor)
+                     else torch.from_numpy(np.ascontiguousarray(fibers, dtype=np.float64)).to(dev))
+            if tuple(fib_t.shape) != (*self.shape, self.dim):
+                raise ValueError(f"fibers must have shape {(*self.shape, self.dim)}")
+        dr2 = dr ** 2
+        check(self.L.fwb_compute_weights(
+            self.dim, stencil, shape_arr(self.shape), _ptr(self.tissue), _ptr(cond_t), cond_s,
+            _ptr(fib_t), float(D_al), float(D_ac), float(D_model), float(dt), float(dr2),
+            _ptr(self.chunk_bits), _ptr(self.chunk_base), self.ld, _ptr(self.weights),
+            _stream()), "fwb_compute_weights")
+        torch.cuda.current_stream().synchronize()   # cond_t / fib_t may be freed now
+        if self.sim:
+            check(self.L.fwb_sim_set_weights(self.sim, _ptr(self.weights)), "fwb_sim_set_weights")
+
+    def set_weights_dense(self, w):
+        """User-supplied (*shape, K) weights (custom Stencil)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        K = w.shape[-1]
+        expect = {2: (5, 9), 3: (7, 19)}[self.dim]
+        if w.shape[:-1] != self.shape or K not in expect:
+            raise ValueError(f"weights must have shape (*{self.shape}, K) with K in {expect}")
+        self.K = K
+        self.stencil = _lib.STENCIL_ISO if K in (5, 7) else _lib.STENCIL_ANISO
+        d = torch.from_numpy(w).to(self.device)
+        self.weights = torch.empty((K, self.ld), dtype=torch.float64, device=self.device)
+        check(self.L.fwb_weights_pack(_ptr(d), _ptr(self.weights), K, self.ld, self.n_nodes,
+                                      _ptr(self.chunk_bits), _ptr(self.chunk_base), _stream()),
+              "fwb_weights_pack")
+        torch.cuda.current_stream().synchronize()
+        if self.sim:
+            check(self.L.fwb_sim_set_weights(self.sim, _ptr(self.weights)), "fwb_sim_set_weights")
+
+    def weights_dense(self):
+        out = torch.empty((*self.shape, self.K), dtype=torch.float64, device=self.device)
+        check(self.L.fwb_weights_unpack(_ptr(self.weights), _ptr(out), self.K, self.ld,
+                                        self.n_nodes, _ptr(self.chunk_bits),
+                                        _ptr(self.chunk_base), _stream()), "fwb_weights_unpack")
+        return out.cpu().numpy()
+
+    # ---- buffers --------------------------------------------------------
+    def allocate(self, n_state):
+        dev = self.device
+        self.n_state = n_state
+        self.ubuf = [torch.empty(self.shape, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.state = torch.zeros((max(n_state, 1), self.ld), dtype=torch.float64, device=dev)
+        self.staging = torch.empty(self.shape, dtype=torch.float64, device=dev)
+
+    def upload_dense(self, which, host):
+        """which: 0/1 = the two u buffers (creation order)."""
+        self.ubuf[which].copy_(_as_tensor(host), non_blocking=True)
+
+    def download_dense(self, which, host_out):
+        _as_tensor(host_out).copy_(self.ubuf[which], non_blocking=True)
+
+    def upload_state(self, slot, host):
+        self.staging.copy_(_as_tensor(host), non_blocking=True)
+        check(self.L.fwb_gather_compact(_ptr(self.staging), _ptr(self.state[slot]), self.n_nodes,
+                                        _ptr(self.chunk_bits), _ptr(self.chunk_base), _stream()),
+              "fwb_gather_compact")
+
+    def download_state(self, slot, host_out, fill):
+        check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(self.staging), float(fill),
+                                         self.n_nodes, _ptr(self.chunk_bits),
+                                         _ptr(self.chunk_base), _stream()), "fwb_scatter_compact")
+        _as_tensor(host_out).copy_(self.staging, non_blocking=True)
+        # staging is reused by the next call on the same stream: ordering is by stream
+
+    def fill_state(self, slot, value):
+        self.state[slot].fill_(float(value))
+
+    # ---- simulation object ---------------------------------------------
+    def create_sim(self, model_id, params, dt):
+        self.destroy_sim()
+        p = (ctypes.c_double * len(params))(*[float(x) for x in params])
+        sim = ctypes.c_void_p(0)
+        check(self.L.fwb_sim_create(
+            ctypes.byref(sim), self.dim, shape_arr(self.shape), model_id, self.stencil,
+            _ptr(self.tissue), _ptr(self.chunk_bits), _ptr(self.chunk_base), self.n_myo, self.ld,
+            _ptr(self.ubuf[0]), _ptr(self.ubuf[1]), _ptr(self.weights), _ptr(self.state),
+            p, len(params), float(dt), _stream()), "fwb_sim_create")
+        self.sim = sim
+        self._keep = []
+
+    def destroy_sim(self):
+        if self.sim:
+            self.L.fwb_sim_destroy(self.sim)
+            self.sim = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.destroy_sim()
+        except Exception:
+            pass
+
+    def current(self):
+        return self.L.fwb_sim_current_buffer(self.sim)
+
+    def set_time(self, t, step):
+        check(self.L.fwb_sim_set_time(self.sim, float(t), int(step)), "fwb_sim_set_time")
+
+    def get_time(self):
+        t, s = ctypes.c_double(0), ctypes.c_int64(0)
+        check(self.L.fwb_sim_get_time(self.sim, ctypes.byref(t), ctypes.byref(s)))
+        return t.value, s.value
+
+    def run(self, n_steps):
+        check(self.L.fwb_sim_run(self.sim, int(n_steps)), "fwb_sim_run")
+
+    def launch_count(self):
+        return int(self.L.fwb_sim_launch_count(self.sim))
+
+    def keep(self, t):
+        self._keep.append(t)
+        return t
+
+    def synchronize(self):
+        torch.cuda.current_stream().synchronize()
+
+    def compact_index(self, flat):
+        """compact index of flat node ids (host ints); -1 where not updated."""
+        bits = self.chunk_bits.cpu().numpy().view(np.uint32)
+        base = self.chunk_base.cpu().numpy().view(np.uint32)
+        flat = np.asarray(flat, dtype=np.int64)
+        ch, lane = flat // 32, flat % 32
+        b = bits[ch]
+        on = (b >> lane.astype(np.uint32)) & 1
+        below = b & ((np.uint32(1) << lane.astype(np.uint32)) - np.uint32(1))
+        pop = np.array([bin(int(x)).count("1") for x in below], dtype=np.int64)
+        return np.where(on == 1, base[ch].astype(np.int64) + pop, -1)
+
+
+def _as_tensor(a):
+    if isinstance(a, torch.Tensor):
+        return a
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags.c_contiguous:
+        raise ValueError("host arrays must be C-contiguous float64")
+    return torch.from_numpy(a)

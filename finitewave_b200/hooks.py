@@ -1,0 +1,130 @@
+"""
+Host hooks of the time loop: commands and state save / load.
+
+These are not compute components; the device runner only has to honour them
+("Commands", "State save/load").  Names, attributes and
+firing rules follow the reference so user scripts run unchanged:
+  Command / CommandSequence   finitewave/core/command/{command,command_sequence}.py
+  StateSaver / StateSaverCollection / StateLoader
+                              finitewave/core/state/{state_saver,state_loader}.py
+The model synchronises ``model.__dict__[var]`` with the device around every hook
+(model.CardiacModel.run), so ``execute(model)`` / ``save()`` see plain numpy arrays.
+"""
+from pathlib import Path
+
+import numpy as np
+
+
+class Command:
+    """User callback fired once, after the step on which ``model.t >= time``."""
+
+    def __init__(self, time=None):
+        self.t = time
+        self.passed = False
+
+    def execute(self, model):
+        raise NotImplementedError
+
+    def update_status(self, model):
+        self.passed = model.t >= self.t
+        return self.passed
+
+
+class CommandSequence:
+    def __init__(self):
+        self.sequence = []
+        self.model = None
+
+    def initialize(self, model):
+        self.model = model
+        for command in self.sequence:
+            command.passed = False
+
+    def add_command(self, command):
+        self.sequence.append(command)
+
+    def remove_commands(self):
+        self.sequence = []
+
+    def execute_next(self):
+        for command in self.sequence:
+            if not command.passed and command.update_status(self.model):
+                command.execute(self.model)
+
+
+class StateSaver:
+    """Writes every ``model.state_vars`` array to ``<path>/<var>.npy`` once, at
+    ``time`` (or at ``t_max`` when ``time < 0``)."""
+
+    def __init__(self, path=".", time=-1):
+        self.path = path
+        self.passed = False
+        self.model = None
+        self.time = time
+
+    def initialize(self, model):
+        self.model = model
+        self.passed = self.path == ""
+
+    def due(self):
+        if self.passed:
+            return False
+        if self.time < 0:
+            return self.model.t >= self.model.t_max
+        return self.model.t >= self.time
+
+    def save(self):
+        if not self.due():
+            return
+        Path(self.path).mkdir(parents=True, exist_ok=True)
+        for var in self.model.state_vars:
+            self._save_variable(Path(self.path).joinpath(var + ".npy"),
+                                self.model.__dict__[var])
+        self.passed = True
+
+    def _save_variable(self, var_path, var):
+        np.save(var_path, var)
+
+
+class StateSaverCollection(StateSaver):
+    def __init__(self):
+        super().__init__()
+        self.savers = []
+
+    def initialize(self, model):
+        self.model = model
+        for saver in self.savers:
+            saver.initialize(model)
+
+    def due(self):
+        return any(s.due() for s in self.savers)
+
+    def save(self):
+        for saver in self.savers:
+            saver.save()
+
+
+class StateLoader:
+    """Reads ``<path>/<var>.npy`` into ``model.<var>`` once at the start of run()."""
+
+    def __init__(self, path=""):
+        self.path = path
+        self.passed = True
+        self.model = None
+
+    def initialize(self, model):
+        self.model = model
+        self.passed = self.path == ""
+        if not Path(self.path).exists():
+            raise FileNotFoundError(f"Unable to load state from {self.path}. "
+                                    "Directory does not exist.")
+
+    def load(self):
+        if self.passed:
+            return
+        for var in self.model.state_vars:
+            setattr(self.model, var, self._load_variable(Path(self.path).joinpath(var + ".npy")))
+        self.passed = True
+
+    def _load_variable(self, var_path):
+        return np.load(var_path)

@@ -1,0 +1,536 @@
+"""
+CardiacModel and the six on-path models, 2D and 3D.
+
+Public surface = the reference's (finitewave/core/model/cardiac_model.py:9-239 and
+finitewave/cpuwave{2D,3D}/model/{aliev_panfilov,barkley,mitchell_schaeffer,fenton_karma,
+luo_rudy91,tp06}_{2,3}d.py): attribute-style configuration (``dt, dr, t_max, prog_bar,
+npfloat, D_model``, every model parameter and ``init_*``), ``cardiac_tissue /
+stim_sequence / tracker_sequence / command_sequence / state_loader / state_saver /
+stencil``, ``u``, ``u_new``, each state variable, ``weights``, ``t``, ``step``,
+``initialize()``, ``compute_weights()``, ``run(initialize=True, num_of_theads=None)``,
+``check_termination()``, ``select_stencil()``, ``clone()``.
+
+What differs is where the time loop runs: ``run()`` keeps the reference's step
+order but executes stimulus -> diffusion -> ionic -> native
+trackers -> ``t += dt`` on the GPU, as one fused kernel per step, for as many steps
+as may pass before the next *host hook* (a Command whose time has come, a
+StateSaver that fires, a user-defined Tracker whose gate passes, a user-defined
+Stim that is due, or termination).  Around every host hook the ``state_vars``
+arrays in ``model.__dict__`` are synchronised with the device, so hooks see and
+may mutate plain numpy arrays exactly as with the reference.
+"""
+import copy
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine, pinned_empty
+from .stencil import (AsymmetricStencil2D, AsymmetricStencil3D, DeviceWeights,
+                      IsotropicStencil2D, IsotropicStencil3D)
+
+
+class CardiacModel:
+    # subclasses fill these
+    _MODEL = None          # key of _lib.MODEL_IDS
+    _PARAMS = ()           # parameter attribute names in the ionic kernel's argument order
+    _STATE = ()            # state attribute names in device slot order
+    _INIT_U_NEW = False    # LR91/TP06 also initialise u_new (luo_rudy91_2d.py:117, tp06_2d.py:182)
+    _DIM = None
+
+    def __init__(self):
+        self.meta = {}
+        self.cardiac_tissue = None
+        self.stim_sequence = None
+        self.tracker_sequence = None
+        self.command_sequence = None
+        self.state_loader = None
+        self.state_saver = None
+        self.stencil = None
+        self.diffusion_kernel = None
+        self.ionic_kernel = None
+        self.u = np.ndarray
+        self.u_new = np.ndarray
+        self.weights = np.ndarray
+        self.dt = 0.
+        self.dr = 0.
+        self.t_max = 0.
+        self.t = 0
+        self.step = 0
+        self.D_model = 1.
+        self.prog_bar = True
+        self.npfloat = np.float64
+        self.state_vars = []
+        self._engine = None
+        self._engine_key = None
+        self.gpu_launches = 0       # kernels launched by the last run()
+
+    # ------------------------------------------------------------------ engine
+    def _engine_for(self, tissue):
+        shape = tuple(tissue.mesh.shape)
+        if self._engine is None or self._engine.shape != shape:
+            self._engine = Engine(shape)
+        return self._engine
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engine",):
+                new.__dict__[k] = None
+            elif isinstance(v, DeviceWeights):
+                new.__dict__[k] = np.asarray(v).copy()
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    # ------------------------------------------------------------------ setup
+    def _alloc_host(self, shape, value):
+        a = pinned_empty(shape).numpy()
+        a[...] = value
+        return a
+
+    def initialize(self):
+        """CardiacModel.initialize (cardiac_model.py:91-117) + the subclass part that
+        fills u and the state arrays with their init_* constants."""
+        if np.dtype(self.npfloat) != np.float64:
+            raise NotImplementedError("finitewave_b200 computes in float64 only")
+        mesh = self.cardiac_tissue.mesh
+        shape = mesh.shape
+        self.u = self._alloc_host(shape, 0.0)
+        self.u_new = self._alloc_host(shape, 0.0)
+        self.step = 0
+        self.t = 0
+
+        self.compute_weights()
+        self.diffusion_kernel = self.stencil.select_diffusion_kernel()
+
+        for seq in (self.stim_sequence, self.tracker_sequence, self.command_sequence,
+                    self.state_loader, self.state_saver):
+            if seq:
+                seq.initialize(self)
+
+        self.u[...] = self.init_u
+        if self._INIT_U_NEW:
+            self.u_new[...] = self.init_u
+        for name in self._STATE:
+            self.__dict__[name] = self._alloc_host(shape, getattr(self, "init_" + name))
+        self._uploaded = False
+
+    def compute_weights(self):
+        """cardiac_model.py:119-128; may be called again by a Command after the mesh
+        changed (Tutorials/SpiralWaves2D.ipynb UpdateMesh)."""
+        tissue = self.cardiac_tissue
+        tissue.compute_myo_indexes()
+        if self.stencil is None:
+            self.stencil = self.select_stencil(tissue)
+        eng = self._engine_for(tissue)
+        old = (eng.n_myo, eng.ld)
+        eng.set_tissue(tissue.mesh, tissue.special_boundaries)
+        w = self.stencil.compute_weights(self, tissue)
+        if not isinstance(w, DeviceWeights):
+            eng.set_weights_dense(np.asarray(w))
+            w = DeviceWeights(eng)
+        self.weights = w
+        if eng.sim and (eng.n_myo, eng.ld) != old:
+            # the node set changed under a live simulation: rebuild device state
+            self._mesh_changed = True
+
+    def select_stencil(self, cardiac_tissue):
+        iso, aniso = ((IsotropicStencil2D, AsymmetricStencil2D) if self._DIM == 2
+                      else (IsotropicStencil3D, AsymmetricStencil3D))
+        return iso() if cardiac_tissue.fibers is None else aniso()
+
+    # ------------------------------------------------------------------ kernels
+    def run_diffusion_kernel(self):
+        """u_new = W u on the host-visible arrays (reference cardiac_model.py:205-211)."""
+        self.diffusion_kernel(self.u_new, self.u, self.weights, self.cardiac_tissue.myo_indexes)
+
+    def run_ionic_kernel(self):
+        raise NotImplementedError(
+            "finitewave_b200 fuses diffusion and the ionic update into one device kernel; "
+            "use run() (or Engine.run) instead of calling the two halves separately.")
+
+    # ------------------------------------------------------------------ device sync
+    def _param_vector(self):
+        return [float(getattr(self, p)) for p in self._PARAMS]
+
+    def _upload(self):
+        """Push u, u_new and every state array from model.__dict__ to the device
+        (creating / re-creating the device simulation when needed)."""
+        eng = self._engine
+        recreate = (eng.state is None or getattr(self, "_mesh_changed", False)
+                    or eng.state.shape != (max(len(self._STATE), 1), eng.ld))
+        if recreate:
+            if eng.sim and getattr(self, "_live", None):
+                self._collect_native()          # keep what the trackers sampled so far
+            eng.allocate(len(self._STATE))
+            self._mesh_changed = False
+            eng.destroy_sim()
+        if not eng.sim:
+            eng.create_sim(_lib.MODEL_IDS[self._MODEL], self._param_vector(), self.dt)
+            if getattr(self, "_live", None):
+                self._register_native()
+        else:
+            p = self._param_vector()
+            arr = (ctypes.c_double * len(p))(*p)
+            _lib.check(eng.L.fwb_sim_set_params(eng.sim, arr, len(p), float(self.dt)),
+                       "fwb_sim_set_params")
+        cur = eng.current()
+        eng.upload_dense(cur, self._host_array("u"))
+        eng.upload_dense(cur ^ 1, self._host_array("u_new"))
+        for slot, name in enumerate(self._STATE):
+            eng.upload_state(slot, self._host_array(name))
+        eng.synchronize()
+
+    def _register_native(self):
+        """(Re-)register the built-in stimuli and trackers with the device runner."""
+        eng, live = self._engine, self._live
+        _lib.check(eng.L.fwb_sim_clear_stims(eng.sim))
+        _lib.check(eng.L.fwb_sim_clear_trackers(eng.sim))
+        eng._keep = []
+        if live["native_stims"]:
+            for st in live["stims"]:
+                sid = st._register(eng, self)
+                _lib.check(eng.L.fwb_sim_set_stim_passed(eng.sim, sid, int(bool(st.passed))))
+        remaining = max(0, live["iters"] - live["done"])
+        for tr in live["native_tr"]:
+            tr._register(eng, self, remaining // max(1, int(tr.step)) + 2)
+
+    def _collect_native(self):
+        eng, live = self._engine, self._live
+        eng.synchronize()
+        for tr in live["native_tr"]:
+            tr._collect(eng)
+        if live["native_stims"]:
+            for i, st in enumerate(live["stims"]):
+                st.passed = bool(eng.L.fwb_sim_stim_passed(eng.sim, i))
+
+    def _host_array(self, name):
+        a = self.__dict__[name]
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != self._engine.shape:
+            raise ValueError(f"model.{name} has shape {a.shape}, expected {self._engine.shape}")
+        return a
+
+    def _download(self, swapped_view=False):
+        """Copy u, u_new and every state array from the device into the numpy arrays
+        of model.__dict__.  swapped_view: expose the pre-swap assignment of the two
+        potential buffers (what a tracker sees mid-step)."""
+        eng = self._engine
+        cur = eng.current()
+        if swapped_view:
+            cur ^= 1
+        for name, which in (("u", cur), ("u_new", cur ^ 1)):
+            host = self.__dict__[name]
+            if not (isinstance(host, np.ndarray) and host.dtype == np.float64
+                    and host.flags.c_contiguous and host.shape == eng.shape):
+                host = np.empty(eng.shape, dtype=np.float64)
+                self.__dict__[name] = host
+            eng.download_dense(which, host)
+        for slot, name in enumerate(self._STATE):
+            host = self.__dict__[name]
+            if not (isinstance(host, np.ndarray) and host.dtype == np.float64
+                    and host.flags.c_contiguous and host.shape == eng.shape):
+                host = np.empty(eng.shape, dtype=np.float64)
+                self.__dict__[name] = host
+            eng.download_state(slot, host, getattr(self, "init_" + name))
+        eng.synchronize()
+
+    # ------------------------------------------------------------------ the loop
+    def check_termination(self):
+        max_iters = int(np.ceil(self.t_max / self.dt))
+        return (self.t > self.t_max) or (self.step > max_iters)
+
+    def run(self, initialize=True, num_of_theads=None):
+        """Runs the simulation (reference: cardiac_model.py:130-189).  `num_of_theads`
+        is accepted for signature compatibility; the work runs on the GPU."""
+        if initialize:
+            self.initialize()
+        if self.t_max < self.t:
+            raise ValueError("t_max must be greater than current t.")
+        if self.state_loader:
+            self.state_loader.load()
+
+        iters = int(np.ceil((self.t_max - self.t) / self.dt))
+        eng = self._engine
+
+        stims = self.stim_sequence.sequence if self.stim_sequence else []
+        native_stims = bool(self.stim_sequence) and self.stim_sequence.all_native()
+        trackers = self.tracker_sequence.sequence if self.tracker_sequence else []
+        native_tr = [tr for tr in trackers if getattr(tr, "_native", False)]
+        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)]
+        commands = self.command_sequence.sequence if self.command_sequence else []
+        self._live = dict(stims=stims, native_stims=native_stims, native_tr=native_tr,
+                          iters=iters, done=0)
+        self._upload()
+        if eng.sim and not eng._keep and (native_tr or (native_stims and stims)):
+            self._register_native()
+        elif eng.sim:
+            self._register_native()
+        launches0 = eng.launch_count()
+        eng.set_time(self.t, self.step)
+
+        bar = None
+        if self.prog_bar:
+            from tqdm import tqdm
+            bar = tqdm(total=iters, desc=f"Running {self.__class__.__name__}")
+        chunk_cap = max(1, iters // 100) if self.prog_bar else max(1, iters)
+
+        done = 0
+        host_view_valid = True      # model.__dict__ arrays == device content
+        finished = False
+        while done < iters and not finished:
+            # ---- plan: how many steps until the next host hook --------------------
+            t_sim, step_sim, n = self.t, self.step, 0
+            hook_stim = hook_tracker = False
+            while done + n < iters and n < chunk_cap:
+                due_s = (not native_stims) and any(t_sim >= s.t and not s.passed for s in stims)
+                due_t = any(tr.gate(t_sim, step_sim) for tr in host_tr)
+                if (due_s or due_t) and n > 0:
+                    break                  # run the n clean steps first
+                t_sim += self.dt
+                step_sim += 1
+                n += 1
+                if due_s or due_t:
+                    hook_stim, hook_tracker = due_s, due_t
+                    break                  # this single step carries the hook
+                if self._post_hook_due(t_sim, step_sim, commands):
+                    break
+            post_hook = n > 0 and self._post_hook_due(t_sim, step_sim, commands)
+
+            # ---- pre-step host hook: user-defined stimuli --------------------------
+            if hook_stim:
+                if not host_view_valid:
+                    self._download()
+                self.stim_sequence.stimulate_next()
+                eng.upload_dense(eng.current(), self._host_array("u"))
+                host_view_valid = False
+
+            # ---- the device steps ---------------------------------------------------
+            eng.set_time(self.t, self.step)
+            eng.run(n)
+            host_view_valid = False
+
+            # ---- mid-step host hook: user-defined trackers (pre-increment view) ------
+            if hook_tracker:
+                self._download(swapped_view=True)
+                for tr in host_tr:
+                    tr.track()
+                # restore the post-swap assignment of the two potential arrays
+                d = self.__dict__
+                d["u"], d["u_new"] = d["u_new"], d["u"]
+                host_view_valid = True
+
+            self.t, self.step = t_sim, step_sim
+            done += n
+            self._live["done"] = done
+            if bar is not None:
+                bar.update(n)
+
+            # ---- post-step host hooks: commands, state savers, termination -----------
+            if post_hook:
+                if any((not c.passed) and self.t >= c.t for c in commands):
+                    if not host_view_valid:
+                        self._download()
+                    self.command_sequence.execute_next()
+                    self._upload()           # commands may have edited anything
+                    host_view_valid = True
+                if self.state_saver and self._saver_due(self.t):
+                    if not host_view_valid:
+                        self._download()
+                        host_view_valid = True
+                    self.state_saver.save()
+                if self.check_termination():
+                    if self.state_saver:
+                        if not host_view_valid:
+                            self._download()
+                            host_view_valid = True
+                        self.state_saver.save()
+                    finished = True
+
+        if bar is not None:
+            bar.close()
+        if not host_view_valid:
+            self._download()
+        self._collect_native()
+        self.gpu_launches = eng.launch_count() - launches0
+        self._live = None
+
+    def _saver_due(self, t):
+        savers = getattr(self.state_saver, "savers", None)
+        savers = savers if savers is not None and len(savers) else [self.state_saver]
+        for sv in savers:
+            if sv.passed:
+                continue
+            if sv.time < 0 and t >= self.t_max:
+                return True
+            if sv.time >= 0 and t >= sv.time:
+                return True
+        return False
+
+    def _post_hook_due(self, t, step, commands):
+        if any((not c.passed) and t >= c.t for c in commands):
+            return True
+        if self.state_saver and self._saver_due(t):
+            return True
+        max_iters = int(np.ceil(self.t_max / self.dt))
+        return (t > self.t_max) or (step > max_iters)
+
+
+# ---------------------------------------------------------------------------
+# The six models.  Defaults and attribute names are the reference's.
+# ---------------------------------------------------------------------------
+class AlievPanfilov2D(CardiacModel):
+    """aliev_panfilov_2d.py:13-131"""
+    _MODEL, _DIM = "aliev_panfilov", 2
+    _PARAMS = ("a", "k", "eap", "mu_1", "mu_2")
+    _STATE = ("v",)
+
+    def __init__(self):
+        super().__init__()
+        self.v = np.ndarray
+        self.D_model = 1.
+        self.state_vars = ["u", "v"]
+        self.npfloat = 'float64'
+        self.a, self.k, self.eap, self.mu_1, self.mu_2 = 0.1, 8.0, 0.01, 0.2, 0.3
+        self.init_u, self.init_v = 0.0, 0.0
+
+
+class Barkley2D(CardiacModel):
+    """barkley_2d.py:13-110"""
+    _MODEL, _DIM = "barkley", 2
+    _PARAMS = ("a", "b", "eap")
+    _STATE = ("v",)
+
+    def __init__(self):
+        super().__init__()
+        self.v = np.ndarray
+        self.D_model = 1.
+        self.state_vars = ["u", "v"]
+        self.npfloat = 'float64'
+        self.a, self.b, self.eap = 0.75, 0.02, 0.02
+        self.init_u, self.init_v = 0.0, 0
+
+
+class MitchellSchaeffer2D(CardiacModel):
+    """mitchell_schaeffer_2d.py:13-100"""
+    _MODEL, _DIM = "mitchell_schaeffer", 2
+    _PARAMS = ("tau_close", "tau_open", "tau_in", "tau_out", "u_gate")
+    _STATE = ("h",)
+
+    def __init__(self):
+        super().__init__()
+        self.h = np.ndarray
+        self.D_model = 1.
+        self.state_vars = ["u", "h"]
+        self.npfloat = 'float64'
+        self.tau_close, self.tau_open, self.tau_out, self.tau_in = 150, 120, 6, 0.3
+        self.u_gate = 0.13
+        self.init_u, self.init_h = 0.0, 1.0
+
+
+class FentonKarma2D(CardiacModel):
+    """fenton_karma_2d.py:13-141 (MLR-I parameter set)"""
+    _MODEL, _DIM = "fenton_karma", 2
+    _PARAMS = ("tau_d", "tau_o", "tau_r", "tau_si", "tau_v_m", "tau_v_p", "tau_w_m",
+               "tau_w_p", "k", "u_c", "uc_si")
+    _STATE = ("v", "w")
+
+    def __init__(self):
+        super().__init__()
+        self.v = np.ndarray
+        self.w = np.ndarray
+        self.D_model = 1.
+        self.state_vars = ["u", "v", "w"]
+        self.npfloat = 'float64'
+        self.tau_r, self.tau_o, self.tau_d, self.tau_si = 130, 12.5, 0.172, 127
+        self.tau_v_m, self.tau_v_p, self.tau_w_m, self.tau_w_p = 18.2, 10, 80, 1020
+        self.k, self.u_c, self.uc_si = 10, 0.13, 0.85
+        self.init_u, self.init_v, self.init_w = 0.0, 1.0, 1.0
+
+
+class LuoRudy912D(CardiacModel):
+    """luo_rudy91_2d.py:12-156"""
+    _MODEL, _DIM = "luo_rudy91", 2
+    _PARAMS = ("gna", "gsi", "gk", "gk1", "gkp", "gb", "ko", "ki", "nai", "nao", "cao",
+               "R", "T", "F", "PR_NaK")
+    _STATE = ("m", "h", "j", "d", "f", "x", "cai")
+    _INIT_U_NEW = True
+
+    def __init__(self):
+        super().__init__()
+        self.D_model = 0.1
+        for name in self._STATE:
+            setattr(self, name, np.ndarray)
+        self.state_vars = ["u", "m", "h", "j", "d", "f", "x", "cai"]
+        self.npfloat = 'float64'
+        self.gna, self.gsi, self.gk, self.gk1 = 23.0, 0.09, 0.282, 0.6047
+        self.gkp, self.gb = 0.0183, 0.03921
+        self.ko, self.ki, self.nai, self.nao, self.cao = 5.4, 145.0, 18.0, 140.0, 1.8
+        self.R, self.T, self.F, self.PR_NaK = 8.314, 310.0, 96.5, 0.01833
+        self.init_u = -84.5
+        self.init_m, self.init_h, self.init_j = 0.0017, 0.9832, 0.995484
+        self.init_d, self.init_f, self.init_x, self.init_cai = 0.000003, 1.0, 0.0057, 0.0002
+
+
+class TP062D(CardiacModel):
+    """tp06_2d.py:13-240 (the reference does not pre-declare the state attributes,
+    so e.g. MultiVariable trackers on TP06 states fail at initialize there; here
+    they are declared after the first initialize() as well)"""
+    _MODEL, _DIM = "tp06", 2
+    _PARAMS = ("ko", "cao", "nao", "Vc", "Vsr", "Vss", "Bufc", "Kbufc", "Bufsr", "Kbufsr",
+               "Bufss", "Kbufss", "Vmaxup", "Kup", "Vrel", "k1_", "k2_", "k3", "k4", "EC",
+               "maxsr", "minsr", "Vleak", "Vxfer", "R", "F", "T", "RTONF", "CAPACITANCE",
+               "gkr", "pKNa", "gk1", "gna", "gbna", "KmK", "KmNa", "knak", "gcal", "gbca",
+               "knaca", "KmNai", "KmCa", "ksat", "n_", "gpca", "KpCa", "gpk", "gto", "gks")
+    _STATE = ("cai", "casr", "cass", "nai", "Ki", "m", "h", "j", "xr1", "xr2", "xs", "r",
+              "s", "d", "f", "f2", "fcass", "rr", "oo")
+    _INIT_U_NEW = True
+
+    def __init__(self):
+        super().__init__()
+        self.D_model = 0.154
+        self.state_vars = ["u", "cai", "casr", "cass", "nai", "Ki", "m", "h", "j", "xr1",
+                           "xr2", "xs", "r", "s", "d", "f", "f2", "fcass", "rr", "oo"]
+        self.npfloat = 'float64'
+        self.ko, self.cao, self.nao = 5.4, 2.0, 140.0
+        self.Vc, self.Vsr, self.Vss = 0.016404, 0.001094, 0.00005468
+        self.Bufc, self.Kbufc, self.Bufsr, self.Kbufsr = 0.2, 0.001, 10., 0.3
+        self.Bufss, self.Kbufss = 0.4, 0.00025
+        self.Vmaxup, self.Kup, self.Vrel = 0.006375, 0.00025, 0.102
+        self.k1_, self.k2_, self.k3, self.k4 = 0.15, 0.045, 0.060, 0.005
+        self.EC, self.maxsr, self.minsr = 1.5, 2.5, 1.
+        self.Vleak, self.Vxfer = 0.00036, 0.0038
+        self.R, self.F, self.T, self.RTONF = 8314.472, 96485.3415, 310.0, 26.71376
+        self.CAPACITANCE = 0.185
+        self.gkr, self.gks, self.gk1, self.gto, self.gna = 0.153, 0.392, 5.405, 0.294, 14.838
+        self.gbna, self.gcal, self.gbca, self.gpca = 0.00029, 0.00003980, 0.000592, 0.1238
+        self.KpCa, self.gpk, self.pKNa = 0.0005, 0.0146, 0.03
+        self.KmK, self.KmNa, self.knak, self.knaca = 1.0, 40.0, 2.724, 1000
+        self.KmNai, self.KmCa, self.ksat, self.n_ = 87.5, 1.38, 0.1, 0.35
+        self.init_u = -84.5
+        self.init_cai, self.init_casr, self.init_cass = 0.00007, 1.3, 0.00007
+        self.init_nai, self.init_Ki = 7.67, 138.3
+        self.init_m, self.init_h, self.init_j = 0., 0.75, 0.75
+        self.init_xr1, self.init_xr2, self.init_xs = 0., 1., 0.
+        self.init_r, self.init_s = 0., 1.
+        self.init_d, self.init_f, self.init_f2, self.init_fcass = 0., 1., 1., 1.
+        self.init_rr, self.init_oo = 1., 0.
+
+
+def _as_3d(cls2d, name):
+    return type(name, (cls2d,), {"_DIM": 3, "__doc__": f"3D twin of {cls2d.__name__} "
+                                 "(the reference's 3D classes only re-index the same point functions)"})
+
+
+AlievPanfilov3D = _as_3d(AlievPanfilov2D, "AlievPanfilov3D")
+Barkley3D = _as_3d(Barkley2D, "Barkley3D")
+MitchellSchaeffer3D = _as_3d(MitchellSchaeffer2D, "MitchellSchaeffer3D")
+FentonKarma3D = _as_3d(FentonKarma2D, "FentonKarma3D")
+LuoRudy913D = _as_3d(LuoRudy912D, "LuoRudy913D")
+TP063D = _as_3d(TP062D, "TP063D")

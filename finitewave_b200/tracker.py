@@ -1,0 +1,320 @@
+"""
+Trackers.  Same names / attributes / gate as the reference
+(finitewave/core/tracker/tracker.py:7-101, tracker_sequence.py;
+ActivationTime  cpuwave2D/tracker/activation_time_2d_tracker.py:7-75,
+ECG             cpuwave2D/tracker/ecg_2d_tracker.py:9-152, cpuwave3D/tracker/ecg_3d_tracker.py:9-140,
+point samplers  cpuwave2D/tracker/{action_potential,multi_variable,variable}_2d_tracker.py).
+
+Native trackers (``_native = True``) are evaluated on the device inside the step
+runner -- activation time and ECG are fused into the step kernel -- and only
+their small outputs come back.  Any other Tracker subclass is a host hook: the
+model downloads ``state_vars`` before calling its ``_track()``.
+"""
+import copy
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from ._lib import check
+
+
+class Tracker:
+    _native = False
+
+    def __init__(self):
+        self.model = None
+        self.file_name = "tracked_data"
+        self.path = "."
+        self.start_time = 0
+        self.end_time = np.inf
+        self.step = 1
+
+    def initialize(self, model):
+        raise NotImplementedError
+
+    def _track(self):
+        raise NotImplementedError
+
+    def gate(self, t, step):
+        """Tracker.track's condition (tracker.py:70-84)."""
+        if self.start_time > t or t > self.end_time:
+            return False
+        return step % self.step == 0
+
+    def track(self):
+        if self.gate(self.model.t, self.model.step):
+            self._track()
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def write(self):
+        np.save(Path(self.path, self.file_name).with_suffix(".npy"), self.output)
+
+    # native trackers override
+    def _register(self, engine, model, max_samples):
+        raise NotImplementedError
+
+    def _collect(self, engine):
+        pass
+
+
+class TrackerSequence:
+    def __init__(self):
+        self.sequence = []
+        self.model = None
+
+    def initialize(self, model):
+        self.model = model
+        for tracker in self.sequence:
+            tracker.initialize(model)
+
+    def add_tracker(self, tracker):
+        self.sequence.append(tracker)
+
+    def remove_trackers(self):
+        self.sequence = []
+
+    def tracker_next(self):
+        for tracker in self.sequence:
+            tracker.track()
+
+
+# ---------------------------------------------------------------------------
+class ActivationTime2DTracker(Tracker):
+    """act_t = where(act_t < 0 and u > threshold, t, act_t) on every grid node."""
+    _native = True
+
+    def __init__(self):
+        super().__init__()
+        self.act_t = np.ndarray
+        self.threshold = -40
+        self.file_name = "act_time_2d"
+        self._dev = None
+
+    def initialize(self, model):
+        self.model = model
+        self.act_t = -np.ones_like(self.model.u)
+        self._dev = None
+
+    def _track(self):   # host statement (only used if called by hand)
+        self.act_t = np.where((self.act_t < 0) & (self.model.u > self.threshold),
+                              self.model.t, self.act_t)
+
+    def _register(self, engine, model, max_samples):
+        if self._dev is None or self._dev.device != engine.device:
+            self._dev = torch.from_numpy(np.ascontiguousarray(self.act_t, dtype=np.float64)).to(
+                engine.device)
+        self._id = engine.L.fwb_sim_add_tracker_act(
+            engine.sim, ctypes.c_void_p(self._dev.data_ptr()), float(self.threshold),
+            float(self.start_time), float(self.end_time), int(self.step))
+        if self._id < 0:
+            check(self._id, "fwb_sim_add_tracker_act")
+
+    def _collect(self, engine):
+        self.act_t = self._dev.cpu().numpy()
+
+    @property
+    def output(self):
+        return self.act_t
+
+
+class ActivationTime3DTracker(ActivationTime2DTracker):
+    pass
+
+
+class ECG2DTracker(Tracker):
+    """Per lead sum over myocytes of (W u - u) / (d * dr), d = squared index
+    distance (2D: (x-i)^2 + (y-j)^2 + z^2)."""
+    _native = True
+
+    def __init__(self, measure_coords=None):
+        super().__init__()
+        self.measure_coords = measure_coords
+        self.ecg = []
+        self.file_name = "ecg.npy"
+        self.u_tr = None
+
+    def initialize(self, model):
+        self.model = model
+        self.measure_coords = np.atleast_2d(self.measure_coords)
+        if self.measure_coords.shape[1] != 3:
+            raise ValueError("measure_coords must have 3 components (x, y, z) per lead")
+        self.ecg = []
+        self._taken = 0
+
+    def _track(self):
+        raise NotImplementedError("ECG is evaluated inside the device step kernel")
+
+    def _register(self, engine, model, max_samples):
+        self._coords_dev = engine.keep(torch.from_numpy(np.ascontiguousarray(
+            self.measure_coords, dtype=np.float64)).to(engine.device))
+        self._n_leads = len(self.measure_coords)
+        self._out = engine.keep(torch.zeros((max(1, max_samples), self._n_leads),
+                                            dtype=torch.float64, device=engine.device))
+        self._id = engine.L.fwb_sim_add_tracker_ecg(
+            engine.sim, ctypes.c_void_p(self._coords_dev.data_ptr()), self._n_leads,
+            float(model.dr), float(self.start_time), float(self.end_time), int(self.step),
+            ctypes.c_void_p(self._out.data_ptr()), int(self._out.shape[0]))
+        if self._id < 0:
+            check(self._id, "fwb_sim_add_tracker_ecg")
+
+    def _collect(self, engine):
+        n = int(engine.L.fwb_sim_tracker_samples(engine.sim, self._id))
+        rows = self._out[:n].cpu().numpy()
+        self.ecg.extend(list(rows))
+
+    @property
+    def output(self):
+        return np.array(self.ecg)
+
+    def write(self):
+        Path(self.path).mkdir(parents=True, exist_ok=True)
+        np.save(Path(self.path).joinpath(self.file_name).with_suffix(".npy"), self.output)
+
+
+class ECG3DTracker(ECG2DTracker):
+    def write(self):
+        Path(self.path).mkdir(parents=True, exist_ok=True)
+        np.save(Path(self.path, self.file_name), self.output)
+
+
+# ---- point samplers ------------------------------------------------------------
+class _PointTracker(Tracker):
+    _native = True
+
+    def _vars(self):
+        raise NotImplementedError
+
+    def _append(self, rows):
+        raise NotImplementedError
+
+    def _register(self, engine, model, max_samples):
+        cells = np.atleast_2d(self.cell_ind)
+        flat = np.ravel_multi_index(tuple(cells.T), engine.shape)
+        cidx = engine.compact_index(flat)
+        names = ["u"] + [v for v in model.state_vars if v != "u"]
+        items, fill = [], []
+        for var in self._vars():
+            if var not in names:
+                raise ValueError(f"Variable '{var}' not found in model.")
+            vid = names.index(var)
+            host = model.__dict__.get(var)
+            for f, c in zip(flat, cidx):
+                items.append((vid, int(f), int(c)))
+                fill.append(float(np.asarray(host).flat[int(f)]) if isinstance(host, np.ndarray)
+                            else 0.0)
+        self._n_cells = len(flat)
+        self._items = engine.keep(torch.tensor(items, dtype=torch.int64, device=engine.device))
+        self._fill = engine.keep(torch.tensor(fill, dtype=torch.float64, device=engine.device))
+        self._out = engine.keep(torch.zeros((max(1, max_samples), len(items)),
+                                            dtype=torch.float64, device=engine.device))
+        self._id = engine.L.fwb_sim_add_tracker_point(
+            engine.sim, ctypes.c_void_p(self._items.data_ptr()),
+            ctypes.c_void_p(self._fill.data_ptr()), len(items), float(self.start_time),
+            float(self.end_time), int(self.step), ctypes.c_void_p(self._out.data_ptr()),
+            int(self._out.shape[0]))
+        if self._id < 0:
+            check(self._id, "fwb_sim_add_tracker_point")
+
+    def _collect(self, engine):
+        n = int(engine.L.fwb_sim_tracker_samples(engine.sim, self._id))
+        self._append(self._out[:n].cpu().numpy())
+
+
+class ActionPotential2DTracker(_PointTracker):
+    def __init__(self):
+        super().__init__()
+        self.act_pot = []
+        self.cell_ind = [1, 1]
+        self.file_name = "act_pot"
+
+    def initialize(self, model):
+        self.model = model
+
+    def _vars(self):
+        return ["u"]
+
+    def _append(self, rows):
+        self.act_pot.extend(list(rows))
+
+    def _track(self):
+        cell = tuple(np.atleast_2d(self.cell_ind).T)
+        self.act_pot.append(self.model.u[cell])
+
+    @property
+    def output(self):
+        return np.squeeze(self.act_pot)
+
+
+class ActionPotential3DTracker(ActionPotential2DTracker):
+    pass
+
+
+class MultiVariable2DTracker(_PointTracker):
+    def __init__(self):
+        super().__init__()
+        self.var_list = []
+        self.cell_ind = [1, 1]
+        self.dir_name = "multi_vars"
+        self.vars = {}
+
+    def initialize(self, model):
+        self.vars = {}
+        self.model = model
+        for var_ in self.var_list:
+            if var_ not in self.model.__dict__:
+                raise ValueError(f"Variable '{var_}' not found in model.")
+            self.vars[var_] = []
+
+    def _vars(self):
+        return list(self.var_list)
+
+    def _append(self, rows):
+        n = self._n_cells
+        for k, var_ in enumerate(self.var_list):
+            self.vars[var_].extend(list(rows[:, k * n:(k + 1) * n]))
+
+    def _track(self):
+        cell = tuple(np.atleast_2d(self.cell_ind).T)
+        for var_ in self.var_list:
+            self.vars[var_].append(self.model.__dict__[var_][cell])
+
+    @property
+    def output(self):
+        return {v: np.squeeze(self.vars[v]) for v in self.var_list}
+
+    def write(self):
+        out_dir = Path(self.path, self.dir_name)
+        out_dir.mkdir(parents=True, exist_ok=True)
+        for var_ in self.var_list:
+            np.save(out_dir / f"{var_}.npy", self.output[var_])
+
+
+class MultiVariable3DTracker(MultiVariable2DTracker):
+    pass
+
+
+class Variable2DTracker(MultiVariable2DTracker):
+    @property
+    def var_name(self):
+        return self.var_list[0]
+
+    @var_name.setter
+    def var_name(self, value):
+        self.var_list = [value]
+
+    @property
+    def output(self):
+        return self.vars[self.var_name]
+
+    def write(self):
+        out_dir = Path(self.path, self.dir_name)
+        out_dir.mkdir(parents=True, exist_ok=True)
+        np.save(Path(out_dir, self.var_name).with_suffix(".npy"), self.output)
+
+
+class Variable3DTracker(Variable2DTracker):
+    pass

@@ -1,0 +1,229 @@
+/*
+ * finitewave_b200.h -- C ABI of the B200-native finitewave step backend.
+ *
+ * One shared library (finitewave_b200/libfinitewave_b200.so, sm_100a only).
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (device
+ * pointers are borrowed, e.g. from torch tensors' data_ptr(); the library
+ * owns only the small FwbSim bookkeeping object and its scratch), is
+ * asynchronous on the caller-supplied cudaStream_t unless stated otherwise,
+ * never throws, and returns
+ *       0   ok
+ *     > 0   a cudaError_t
+ *     < 0   an argument error (FWB_E_*)
+ * with a human-readable message from fwb_last_error().
+ *
+ * The reference (finitewave v0.8.5) has no FFI: its seam is Python template
+ * methods plus function pointers to numba kernels.  Each entry point below
+ * names the reference interface it replaces (paths relative to the reference
+ * root, /root/reference in the build container).
+ *
+ * Device data layout:
+ *   u, u_new, act_t        dense fp64, C order over the bounding grid (*shape)
+ *   chunk_bits/chunk_base  per 32 consecutive flat nodes: bitmask of the
+ *                          nodes the solver updates (mesh == 1 and
+ *                          special_boundaries == 0) and the exclusive prefix
+ *                          count of such nodes -> "compact index" of a node =
+ *                          its position in the reference's myo_indexes array
+ *   weights                compact SoA: weights[k * ld + c], k = stencil slot
+ *                          in the reference's slot order, c = compact index
+ *   state                  compact SoA: state[s * ld + c], s in the model's
+ *                          state order (FWB_MODEL_* comments)
+ */
+#ifndef FINITEWAVE_B200_H
+#define FINITEWAVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FWB_VERSION 100
+
+/* exported symbols (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define FWB_API __attribute__((visibility("default")))
+#else
+#define FWB_API
+#endif
+
+/* error codes (< 0) */
+#define FWB_E_ARG        (-1)
+#define FWB_E_UNSUPPORTED (-2)
+#define FWB_E_STATE      (-3)
+
+/* models: state order = the reference's state_vars without "u";
+ * parameter order = the reference's ionic_kernel argument order after dt */
+#define FWB_MODEL_ALIEV_PANFILOV     0  /* state: v            params(5):  a,k,eap,mu_1,mu_2 */
+#define FWB_MODEL_BARKLEY            1  /* state: v            params(3):  a,b,eap */
+#define FWB_MODEL_MITCHELL_SCHAEFFER 2  /* state: h            params(5):  tau_close,tau_open,tau_in,tau_out,u_gate */
+#define FWB_MODEL_FENTON_KARMA       3  /* state: v,w          params(11): tau_d,tau_o,tau_r,tau_si,tau_v_m,tau_v_p,tau_w_m,tau_w_p,k,u_c,uc_si */
+#define FWB_MODEL_LUO_RUDY91         4  /* state: m,h,j,d,f,x,cai  params(15): gna,gsi,gk,gk1,gkp,gb,ko,ki,nai,nao,cao,R,T,F,PR_NaK */
+#define FWB_MODEL_TP06               5  /* state: cai,casr,cass,nai,Ki,m,h,j,xr1,xr2,xs,r,s,d,f,f2,fcass,rr,oo  params(49): tp06_2d.py:204-218 order */
+#define FWB_N_MODELS                 6
+
+/* stencils; K = 5/9 (2D) or 7/19 (3D); slot order = the reference's */
+#define FWB_STENCIL_ISO   0
+#define FWB_STENCIL_ANISO 1
+
+/* stimulus modes */
+#define FWB_STIM_VOLTAGE      0   /* u = value                 (StimVoltage*)  */
+#define FWB_STIM_CURRENT      1   /* u += dt*value [, clamp]   (StimCurrent*)  */
+#define FWB_STIM_VOLTAGE_LIST 2   /* u = values[n_fired]       (StimVoltageListMatrix3D) */
+
+typedef void *fwb_stream_t;            /* cudaStream_t */
+typedef struct FwbSim FwbSim;
+
+FWB_API const char *fwb_last_error(void);
+FWB_API int fwb_version(void);
+/* number of state arrays / parameters / stencil points */
+FWB_API int fwb_model_n_state(int model);
+FWB_API int fwb_model_n_params(int model);
+FWB_API int fwb_stencil_k(int dim, int stencil);
+/* bitmask over state slots: bit s set = slot s is read / written by the step */
+FWB_API uint32_t fwb_model_read_mask(int model);
+FWB_API uint32_t fwb_model_write_mask(int model);
+
+/* ------------------------------------------------------------------------
+ * Tissue -> device index structures.
+ * Replaces CardiacTissue.compute_myo_indexes
+ * (finitewave/core/tissue/cardiac_tissue.py:54-63): instead of an int64 index
+ * list (8 B/node) the device keeps 1 bit + 1/8 B per node.
+ *   update_mask  dense uint8, 1 where (mesh == 1) & (special_boundaries == 0);
+ *                the boundary ring must be 0 (CardiacTissue{2,3}D.add_boundaries)
+ *   chunk_bits   [n_chunks]   out, n_chunks = ceil(n_nodes / 32)
+ *   chunk_base   [n_chunks]   out, exclusive prefix popcount
+ *   n_myo        host out (synchronises the stream)
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_build_chunks(const uint8_t *update_mask, int64_t n_nodes,
+                     uint32_t *chunk_bits, uint32_t *chunk_base,
+                     int64_t *n_myo, fwb_stream_t stream);
+
+/* dense (*shape) <-> compact [ld] conversions of one array.
+ * gather:  compact[c] = dense[n]            for update nodes
+ * scatter: dense[n] = update ? compact[c] : fill   (all n < n_nodes)        */
+FWB_API int fwb_gather_compact(const double *dense, double *compact, int64_t n_nodes,
+                       const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                       fwb_stream_t stream);
+FWB_API int fwb_scatter_compact(const double *compact, double *dense, double fill,
+                        int64_t n_nodes, const uint32_t *chunk_bits,
+                        const uint32_t *chunk_base, fwb_stream_t stream);
+/* weights AoS dense (*shape, K) <-> compact SoA [K][ld] (user-supplied
+ * Stencil results in, `model.weights` out) */
+FWB_API int fwb_weights_pack(const double *dense_aos, double *compact_soa, int K, int64_t ld,
+                     int64_t n_nodes, const uint32_t *chunk_bits,
+                     const uint32_t *chunk_base, fwb_stream_t stream);
+FWB_API int fwb_weights_unpack(const double *compact_soa, double *dense_aos, int K, int64_t ld,
+                       int64_t n_nodes, const uint32_t *chunk_bits,
+                       const uint32_t *chunk_base, fwb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Stencil weights.  Replaces Stencil.compute_weights of
+ *   IsotropicStencil2D   finitewave/cpuwave2D/stencil/isotropic_stencil_2d.py:41-69,161-204
+ *   IsotropicStencil3D   finitewave/cpuwave3D/stencil/isotropic_stencil_3d.py:45-74,112-149
+ *   AsymmetricStencil2D  finitewave/cpuwave2D/stencil/asymmetric_stencil_2d.py:46-84,291-433
+ *   AsymmetricStencil3D  finitewave/cpuwave3D/stencil/asymmetric_stencil_3d.py:61-105,163-458
+ * including the D_model*dt/dr**2 scaling and the +1 on the centre slot.
+ *   shape        host, dim entries
+ *   tissue       dense uint8, 1 where mesh == 1 (fibrosis/empty = 0)
+ *   cond         dense fp64 conductivity or NULL (then cond_scalar)
+ *   fibers       dense (*shape, dim) fp64 or NULL (required for ANISO)
+ *   dr2          dr**2 as evaluated by the caller
+ *   weights      out, compact SoA [K][ld]
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
+                        const uint8_t *tissue, const double *cond, double cond_scalar,
+                        const double *fibers, double D_al, double D_ac,
+                        double D_model, double dt, double dr2,
+                        const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                        int64_t ld, double *weights, fwb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * The simulation object: the fused per-time-step path.
+ * Replaces, per step, CardiacModel.run's loop body
+ * (finitewave/core/model/cardiac_model.py:164-189):
+ *   StimSequence.stimulate_next      core/stimulation/stim_sequence.py:65-77
+ *   run_diffusion_kernel             cardiac_model.py:205-211 -> diffusion_kernel_{2d,3d}_{iso,aniso}
+ *   run_ionic_kernel                 cpuwave{2D,3D}/model/<model>_{2,3}d.py ionic_kernel_{2d,3d}
+ *   TrackerSequence.tracker_next     core/tracker/tracker_sequence.py:59-64 for the native trackers
+ *   t += dt; step += 1; swap(u, u_new)
+ * One fused kernel launch per step (plus ROI-sized stimulus launches on the
+ * steps a stimulus fires and tiny finalize/gather launches on tracker
+ * samples).
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_sim_create(FwbSim **sim, int dim, const int64_t *shape, int model, int stencil,
+                   const uint8_t *tissue,              /* dense uint8, mesh == 1 (stimulus target) */
+                   const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                   int64_t n_myo, int64_t ld,
+                   double *u, double *u_new,           /* dense; swapped every step */
+                   const double *weights,              /* compact SoA [K][ld] */
+                   double *state,                      /* compact SoA [S][ld] */
+                   const double *params, int n_params, /* host */
+                   double dt, fwb_stream_t stream);
+FWB_API int fwb_sim_destroy(FwbSim *sim);
+
+/* model.t / model.step (host scalars; t accumulates as t += dt in fp64, like
+ * the reference's Python float) */
+FWB_API int fwb_sim_set_time(FwbSim *sim, double t, int64_t step);
+FWB_API int fwb_sim_get_time(const FwbSim *sim, double *t, int64_t *step);
+/* which of the two buffers passed at creation currently is `u` (0 or 1) */
+FWB_API int fwb_sim_current_buffer(const FwbSim *sim);
+/* rebind after the caller re-uploaded / recomputed arrays (same sizes) */
+FWB_API int fwb_sim_set_weights(FwbSim *sim, const double *weights);
+FWB_API int fwb_sim_set_params(FwbSim *sim, const double *params, int n_params, double dt);
+
+/* ---- stimuli: Stim.stimulate of cpuwave{2D,3D}/stimulation/*.py ---------- */
+FWB_API int fwb_sim_clear_stims(FwbSim *sim);
+/* Stim{Voltage,Current}Coord{2D,3D}: half-open index box, only mesh == 1.
+ * box = x1,x2,y1,y2[,z1,z2]; has_u_max = 0 -> no clamp.  Returns stim id >= 0. */
+FWB_API int fwb_sim_add_stim_box(FwbSim *sim, int mode, double t, double duration, double value,
+                         int has_u_max, double u_max, const int64_t *box);
+/* Stim*Matrix*, StimCurrentArea*, StimVoltageListMatrix3D: flat node indices
+ * (device int64, already restricted to mesh == 1 by the caller).
+ * values/n_values (host) only for FWB_STIM_VOLTAGE_LIST. */
+FWB_API int fwb_sim_add_stim_nodes(FwbSim *sim, int mode, double t, double duration, double value,
+                           int has_u_max, double u_max, const int64_t *nodes, int64_t n_nodes,
+                           const double *values, int64_t n_values);
+FWB_API int fwb_sim_stim_passed(const FwbSim *sim, int stim_id);
+FWB_API int fwb_sim_set_stim_passed(FwbSim *sim, int stim_id, int passed);
+
+/* ---- native trackers ---------------------------------------------------- */
+FWB_API int fwb_sim_clear_trackers(FwbSim *sim);
+/* ActivationTime{2,3}DTracker (cpuwave2D/tracker/activation_time_2d_tracker.py:51-63),
+ * gate of core/tracker/tracker.py:70-84.  act_t dense fp64, caller-initialised to -1. */
+FWB_API int fwb_sim_add_tracker_act(FwbSim *sim, double *act_t, double threshold,
+                            double start_time, double end_time, int64_t every);
+/* ECG{2,3}DTracker (ecg_2d_tracker.py:61-79,114-152; ecg_3d_tracker.py:51-69,99-140).
+ * coords device (n_leads, 3) fp64; out device [capacity][n_leads]. */
+FWB_API int fwb_sim_add_tracker_ecg(FwbSim *sim, const double *coords, int n_leads, double dr,
+                            double start_time, double end_time, int64_t every,
+                            double *out, int64_t capacity);
+/* ActionPotential / MultiVariable / Variable trackers
+ * (action_potential_2d_tracker.py:46-54, multi_variable_2d_tracker.py:58-69).
+ * items: n_items triples (var, flat node, compact index or -1) as device int64
+ * [n_items][3]; var 0 = u, 1.. = state slot + 1; fill[n_items] device fp64 is
+ * used when compact index < 0; out device [capacity][n_items]. */
+FWB_API int fwb_sim_add_tracker_point(FwbSim *sim, const int64_t *items, const double *fill,
+                              int n_items, double start_time, double end_time,
+                              int64_t every, double *out, int64_t capacity);
+/* samples taken so far by tracker id (ids in order of registration) */
+FWB_API int64_t fwb_sim_tracker_samples(const FwbSim *sim, int tracker_id);
+
+/* run exactly n_steps time steps from the current (t, step) */
+FWB_API int fwb_sim_run(FwbSim *sim, int64_t n_steps);
+/* kernel launches issued by fwb_sim_run so far */
+FWB_API int64_t fwb_sim_launch_count(const FwbSim *sim);
+
+/* ------------------------------------------------------------------------
+ * Single unfused pieces (used for ECG-style re-application and tests).
+ * fwb_diffuse replaces diffusion_kernel_{2d,3d}_{iso,aniso}(u_new, u, w, idx).
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_diffuse(int dim, int stencil, const int64_t *shape,
+                const uint32_t *chunk_bits, const uint32_t *chunk_base, int64_t ld,
+                const double *u, double *u_new, const double *weights,
+                fwb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINITEWAVE_B200_H */

@@ -1,0 +1,111 @@
+"""
+CPU check of the CUDA kernels' per-node model math.
+
+finitewave_b200/csrc/models.cuh is a __host__ __device__ header; tests/hostcheck
+compiles it with g++ (TEST ONLY, not a product path) so the transcription --
+operation order, host-hoisted constants, read/write masks -- can be compared
+with the oracle bit for bit on random node states without a GPU.  What the GPU
+adds on top (CUDA libm vs glibc, <= 2 ulp per call) is covered by the -m gpu
+parity tests with the 1e-9 tolerance.
+"""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "tests" / "hostcheck" / "host_models.cpp"
+SO = ROOT / "tests" / "hostcheck" / "libhost_models.so"
+MODEL_IDS = {"aliev_panfilov": 0, "barkley": 1, "mitchell_schaeffer": 2, "fenton_karma": 3,
+             "luo_rudy91": 4, "tp06": 5}
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    deps = [SRC, ROOT / "finitewave_b200" / "csrc" / "models.cuh"]
+    if not SO.exists() or SO.stat().st_mtime < max(d.stat().st_mtime for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-fno-fast-math", "-fvisibility=hidden",
+                               "-I/usr/local/cuda/include", "-o", str(SO), str(SRC), "-lm"])
+    return ctypes.CDLL(str(SO))
+
+
+def _random_node_states(model, n, rng):
+    """u and state values spread over the ranges a simulation visits (both sides of
+    every branch threshold)."""
+    spec = oracle.MODELS[model]
+    if model in ("luo_rudy91", "tp06"):
+        u = rng.uniform(-95.0, 45.0, n)
+        u[: n // 8] = rng.uniform(-41.0, -39.0, n // 8)     # around the h/j branch
+    else:
+        u = rng.uniform(-0.1, 1.1, n)
+        u[: n // 8] = rng.uniform(0.12, 0.14, n // 8)       # around u_gate / u_c
+    states = []
+    for name in spec["state"]:
+        init = spec["init"][name]
+        if name in ("cai", "cass"):
+            s = rng.uniform(5e-5, 2e-3, n)
+        elif name == "casr":
+            s = rng.uniform(0.3, 4.0, n)
+        elif name in ("nai",):
+            s = rng.uniform(7.0, 11.0, n)
+        elif name in ("Ki",):
+            s = rng.uniform(130.0, 142.0, n)
+        else:
+            s = rng.uniform(0.0, 1.0, n)
+        s[0] = init
+        states.append(np.ascontiguousarray(s))
+    return np.ascontiguousarray(u), states
+
+
+@pytest.mark.parametrize("model", list(MODEL_IDS))
+@pytest.mark.parametrize("dt", [0.01, 0.005])
+def test_models_header_matches_oracle_bitwise(hostlib, model, dt):
+    rng = np.random.default_rng(11)
+    n = 20000
+    spec = oracle.MODELS[model]
+    u, st = _random_node_states(model, n, rng)
+    pvec = np.array([float(v) for v in spec["params"].values()], dtype=np.float64)
+    diff = rng.uniform(-1, 1, n) * 0.01 + u                    # a "diffusion result"
+
+    # oracle
+    un_o = diff.copy()
+    st_o = [s.copy() for s in st]
+    idx = np.arange(n, dtype=np.int64)
+    oracle.ionic(model, un_o, u, st_o, idx, dt, pvec)
+
+    # the kernels' header
+    un_h = diff.copy()
+    st_h = [s.copy() for s in st]
+    arr = (c_double_p * max(1, len(st_h)))(*[s.ctypes.data_as(c_double_p) for s in st_h])
+    rc = hostlib.fwb_host_ionic(MODEL_IDS[model], un_h.ctypes.data_as(c_double_p),
+                                u.ctypes.data_as(c_double_p), arr, ctypes.c_int64(n),
+                                ctypes.c_double(dt), pvec.ctypes.data_as(c_double_p))
+    assert rc == 0
+    assert np.array_equal(un_h, un_o), f"u_new differs: {np.max(np.abs(un_h - un_o)):.3e}"
+    for name, a, b in zip(spec["state"], st_h, st_o):
+        if model == "tp06" and name == "cai":
+            assert np.array_equal(a, st[0]), "TP06 cai must stay untouched"
+        assert np.array_equal(a, b), f"{name} differs: {np.max(np.abs(a - b)):.3e}"
+
+
+def test_param_order_matches_oracle_tables():
+    """The device parameter vectors are indexed by position: the attribute order in
+    finitewave_b200.model must be the oracle's (= the reference's kernel call order)."""
+    from finitewave_b200 import model as m
+    for cls in (m.AlievPanfilov2D, m.Barkley2D, m.MitchellSchaeffer2D, m.FentonKarma2D,
+                m.LuoRudy912D, m.TP062D):
+        spec = oracle.MODELS[cls._MODEL]
+        assert list(cls._PARAMS) == list(spec["params"]), cls.__name__
+        assert list(cls._STATE) == list(spec["state"]), cls.__name__
+        obj = cls()
+        for k, v in spec["params"].items():
+            assert float(getattr(obj, k)) == float(v), (cls.__name__, k)
+        for k, v in spec["init"].items():
+            assert float(getattr(obj, "init_" + k)) == float(v), (cls.__name__, k)
+        assert obj.D_model == spec["D_model"]
