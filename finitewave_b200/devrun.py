@@ -1,0 +1,145 @@
+"""
+DeviceSimulation -- a simulation whose tissue and state live only on the GPU.
+
+``CardiacModel.run()`` mirrors the reference's host-array contract (numpy arrays in
+``model.__dict__``), which caps the tissue size at what the host can hold.  The
+large configurations (512^3 ... 1024^3, SURVEY.md section 8d "generated on device per
+slab") use this class instead: mesh / fibres / conductivity are torch CUDA tensors
+(or numpy arrays that fit), state arrays are filled with the model's ``init_*``
+constants directly on the device, stimuli and trackers are the same objects as in
+the host API, and ``run(n_steps)`` advances the fused step kernel with the
+reference's loop order (cardiac_model.py:164-189).  Nothing ever round-trips through
+host memory except what the caller asks for (``u_host()``, ``state_host(name)``,
+tracker outputs).
+
+``model`` is an un-run CardiacModel instance: it supplies the model id, parameter
+values, ``init_*`` constants, ``dt``, ``dr``, ``D_model`` and optionally ``stencil``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine
+from .stencil import AsymmetricStencil2D
+
+
+class _Shim:
+    """What the stimulus / tracker ``_register`` hooks need from a model."""
+
+    def __init__(self, sim):
+        self._sim = sim
+        self.dt = sim.dt
+        self.dr = sim.dr
+        self.state_vars = ["u"] + list(sim.state_names)
+        self.cardiac_tissue = sim
+
+    @property
+    def mesh(self):
+        return self._sim.mesh_host()
+
+
+class DeviceSimulation:
+    def __init__(self, model, mesh, fibers=None, conductivity=1.0, device=None, stencil=None):
+        self.model = model
+        shape = tuple(int(s) for s in mesh.shape)
+        if len(shape) != model._DIM:
+            raise ValueError(f"{type(model).__name__} needs a {model._DIM}-dimensional mesh")
+        self.shape = shape
+        self.dt, self.dr = float(model.dt), float(model.dr)
+        self.state_names = list(model._STATE)
+        self.engine = eng = Engine(shape, device)
+        self._mesh = mesh
+        eng.set_tissue(mesh)
+        if stencil is None:
+            stencil = model.stencil
+        aniso = fibers is not None if stencil is None else isinstance(stencil, AsymmetricStencil2D)
+        if aniso and fibers is None:
+            raise ValueError("Fibers must be provided for anisotropic diffusion.")
+        D_al = getattr(stencil, "D_al", 1) if stencil is not None else 1
+        D_ac = getattr(stencil, "D_ac", 1 / 9) if stencil is not None else 1 / 9
+        eng.compute_weights(_lib.STENCIL_ANISO if aniso else _lib.STENCIL_ISO, conductivity,
+                            fibers if aniso else None, D_al, D_ac, model.D_model, self.dt, self.dr)
+        eng.allocate(len(self.state_names), staging=False)
+        eng.ubuf[0].fill_(float(model.init_u))
+        eng.ubuf[1].fill_(float(model.init_u) if model._INIT_U_NEW else 0.0)
+        for slot, name in enumerate(self.state_names):
+            eng.fill_state(slot, getattr(model, "init_" + name))
+        eng.create_sim(_lib.MODEL_IDS[model._MODEL], model._param_vector(), self.dt)
+        self.t, self.step = 0.0, 0
+        self.stims, self.trackers = [], []
+        self._shim = _Shim(self)
+
+    # ---- tissue views ----------------------------------------------------
+    @property
+    def n_myo(self):
+        return self.engine.n_myo
+
+    @property
+    def mesh(self):
+        return self.mesh_host()
+
+    def mesh_host(self):
+        m = self._mesh
+        return m.cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+
+    # ---- stimuli / trackers (same classes as the host API) -----------------
+    def add_stim(self, stim):
+        stim.initialize(self._shim)
+        sid = stim._register(self.engine, self._shim)
+        self.stims.append((sid, stim))
+        return stim
+
+    def add_tracker(self, tracker, max_samples):
+        if not getattr(tracker, "_native", False):
+            raise ValueError("DeviceSimulation takes native trackers only")
+        tracker.model = self._shim
+        if hasattr(tracker, "measure_coords"):
+            tracker.initialize(self._shim)
+        elif hasattr(tracker, "act_t"):
+            tracker._dev = torch.full(self.shape, -1.0, dtype=torch.float64,
+                                      device=self.engine.device)
+        tracker._register(self.engine, self._shim, int(max_samples))
+        self.trackers.append(tracker)
+        return tracker
+
+    # ---- time loop -----------------------------------------------------------
+    def run(self, n_steps):
+        eng = self.engine
+        eng.set_time(self.t, self.step)
+        eng.run(int(n_steps))
+        self.t, self.step = eng.get_time()
+
+    def synchronize(self):
+        self.engine.synchronize()
+
+    def launch_count(self):
+        return self.engine.launch_count()
+
+    # ---- results ---------------------------------------------------------------
+    def u_device(self):
+        return self.engine.ubuf[self.engine.current()]
+
+    def u_host(self):
+        return self.u_device().cpu().numpy()
+
+    def state_compact(self, name):
+        """Device view [n_myo] of one state variable in myocyte (myo_indexes) order."""
+        return self.engine.state[self.state_names.index(name), :self.engine.n_myo]
+
+    def state_host(self, name):
+        eng = self.engine
+        out = torch.empty(self.shape, dtype=torch.float64, device=eng.device)
+        _lib.check(eng.L.fwb_scatter_compact(
+            ctypes.c_void_p(eng.state[self.state_names.index(name)].data_ptr()),
+            ctypes.c_void_p(out.data_ptr()), float(getattr(self.model, "init_" + name)),
+            eng.n_nodes, ctypes.c_void_p(eng.chunk_bits.data_ptr()),
+            ctypes.c_void_p(eng.chunk_base.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "fwb_scatter_compact")
+        return out.cpu().numpy()
+
+    def collect(self):
+        self.engine.synchronize()
+        for tr in self.trackers:
+            tr._collect(self.engine)

@@ -147,12 +147,20 @@ class Engine:
         return out.cpu().numpy()
 
     # ---- buffers --------------------------------------------------------
-    def allocate(self, n_state):
+    def allocate(self, n_state, staging=True):
         dev = self.device
         self.n_state = n_state
         self.ubuf = [torch.empty(self.shape, dtype=torch.float64, device=dev) for _ in range(2)]
         self.state = torch.zeros((max(n_state, 1), self.ld), dtype=torch.float64, device=dev)
-        self.staging = torch.empty(self.shape, dtype=torch.float64, device=dev)
+        self.staging = None
+        if staging:
+            self._staging()
+
+    def _staging(self):
+        """Dense scratch for host <-> compact transfers (allocated on first use)."""
+        if self.staging is None:
+            self.staging = torch.empty(self.shape, dtype=torch.float64, device=self.device)
+        return self.staging
 
     def upload_dense(self, which, host):
         """which: 0/1 = the two u buffers (creation order)."""
@@ -162,13 +170,13 @@ class Engine:
         _as_tensor(host_out).copy_(self.ubuf[which], non_blocking=True)
 
     def upload_state(self, slot, host):
-        self.staging.copy_(_as_tensor(host), non_blocking=True)
+        self._staging().copy_(_as_tensor(host), non_blocking=True)
         check(self.L.fwb_gather_compact(_ptr(self.staging), _ptr(self.state[slot]), self.n_nodes,
                                         _ptr(self.chunk_bits), _ptr(self.chunk_base), _stream()),
               "fwb_gather_compact")
 
     def download_state(self, slot, host_out, fill):
-        check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(self.staging), float(fill),
+        check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(self._staging()), float(fill),
                                          self.n_nodes, _ptr(self.chunk_bits),
                                          _ptr(self.chunk_base), _stream()), "fwb_scatter_compact")
         _as_tensor(host_out).copy_(self.staging, non_blocking=True)
