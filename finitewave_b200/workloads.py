@@ -1,0 +1,160 @@
+"""
+Synthetic tissues of the BASELINE.json configurations, built on the device.
+
+SURVEY.md section 8d defines the inputs; the small host-side twins used for parity
+live in tests/cases.py.  Everything here returns torch tensors on ``device`` so a
+512^3 ... 1024^3 tissue never has to exist in host memory.
+
+Algorithmic bytes per myocyte node-update:
+    B = 8 (u) + 8 (u_new) + 1 (mask) + 8 K (weights) + 8 (2 S_rw + S_ro + S_wo)
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import model as _m
+from .devrun import DeviceSimulation
+from .stimulation import StimVoltageCoord2D, StimVoltageCoord3D
+from .tracker import ActivationTime3DTracker
+
+BYTES_PER_NODE = {
+    ("aliev_panfilov", 5): 73, ("aliev_panfilov", 9): 105,
+    ("fenton_karma", 9): 121, ("fenton_karma", 5): 89,
+    ("mitchell_schaeffer", 7): 89, ("mitchell_schaeffer", 19): 185,
+    ("luo_rudy91", 5): 169, ("luo_rudy91", 7): 185,
+    ("tp06", 19): 457, ("tp06", 7): 361,
+}
+
+
+def _ring_zero(mesh):
+    for ax in range(mesh.dim()):
+        mesh.select(ax, 0).zero_()
+        mesh.select(ax, mesh.shape[ax] - 1).zero_()
+    return mesh
+
+
+def fibrosis_mesh(shape, density, seed, device):
+    """mesh with 2 where uniform(0,1) <= density (rule of diffuse_2d_pattern.py:86-87)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    mesh = torch.ones(shape, dtype=torch.int8, device=device)
+    if density > 0:
+        r = torch.rand(shape, generator=g, device=device)
+        mesh[r <= density] = 2
+    return _ring_zero(mesh)
+
+
+def uniform_fibers_2d(shape, alpha, device):
+    f = torch.empty((*shape, 2), dtype=torch.float64, device=device)
+    f[..., 0] = math.cos(alpha)
+    f[..., 1] = math.sin(alpha)
+    return f
+
+
+def rotating_fibers_3d(shape, device, k0=0, nk_total=None):
+    """examples/basics/3D/slab_with_fibers_3d.py:64-70; ``k0``/``nk_total`` select a
+    z-slab [k0, k0 + shape[2]) of a taller tissue."""
+    n_i, n_j, n_k = shape
+    nk_total = nk_total or n_k
+    phi = torch.linspace(-math.pi / 3, math.pi / 2, nk_total - 2, dtype=torch.float64, device=device)
+    full = torch.zeros(nk_total, 2, dtype=torch.float64, device=device)
+    full[1:-1, 0] = torch.cos(phi)
+    full[1:-1, 1] = torch.sin(phi)
+    sl = full[k0:k0 + n_k]
+    f = torch.zeros((n_i, n_j, n_k, 3), dtype=torch.float64, device=device)
+    f[..., 0] = sl[:, 0]
+    f[..., 1] = sl[:, 1]
+    return f
+
+
+def ventricle_shell(shape, device):
+    """Half prolate-ellipsoid shell + helix fibres (-60..+60 deg across the wall),
+    the geometry of tests/cases.py::ventricle_shell evaluated plane by plane on the
+    device (examples/data/*.npy are not in the reference tree)."""
+    n_i, n_j, n_k = shape
+    mesh = torch.zeros(shape, dtype=torch.int8, device=device)
+    fib = torch.zeros((*shape, 3), dtype=torch.float64, device=device)
+    ci, cj, ck = n_i / 2, n_j / 2, 0.86 * n_k
+    jj, kk = torch.meshgrid(torch.arange(n_j, dtype=torch.float64, device=device),
+                            torch.arange(n_k, dtype=torch.float64, device=device), indexing="ij")
+    y, z = jj - cj, kk - ck
+    for i in range(n_i):
+        x = float(i) - ci
+        outer = (x / (0.39 * n_i)) ** 2 + (y / (0.39 * n_j)) ** 2 + (z / (0.82 * n_k)) ** 2
+        inner = (x / (0.31 * n_i)) ** 2 + (y / (0.31 * n_j)) ** 2 + (z / (0.74 * n_k)) ** 2
+        wall = (outer <= 1.0) & (inner > 1.0) & (kk <= ck)
+        if not bool(wall.any()):
+            continue
+        mesh[i][wall] = 1
+        si, so = torch.sqrt(inner), torch.sqrt(outer)
+        depth = torch.clamp((si - 1.0) / torch.clamp(si - so, min=1e-9), 0.0, 1.0)
+        helix = torch.deg2rad(-60.0 + 120.0 * depth)
+        r = torch.sqrt(x * x + y * y) + 1e-12
+        f = torch.stack([torch.cos(helix) * (-y / r), torch.cos(helix) * (x / r),
+                         torch.sin(helix)], dim=-1)
+        f = f / torch.linalg.norm(f, dim=-1, keepdim=True)
+        f[~wall] = 0.0
+        fib[i] = f
+    return _ring_zero(mesh), fib
+
+
+def _cfg(model, dt=0.01, dr=0.25):
+    model.dt, model.dr = dt, dr
+    model.prog_bar = False
+    return model
+
+
+def build(name, device, scale=1.0, rank=0, world=1):
+    """Returns (DeviceSimulation, info dict).  ``scale`` shrinks every axis (tests)."""
+    if name == "c2":
+        n = max(64, int(round(4096 * scale)) // 32 * 32)
+        shape = (n, n)
+        mesh = fibrosis_mesh(shape, 0.30, 2 + rank, device)
+        sim = DeviceSimulation(_cfg(_m.FentonKarma2D()), mesh,
+                               fibers=uniform_fibers_2d(shape, 0.25 * math.pi, device))
+        sim.add_stim(StimVoltageCoord2D(0, 1, 0, n, 0, 5))
+        sim.add_stim(StimVoltageCoord2D(3.0, 1, 0, n // 2, 0, n))
+        info = dict(workload=f"C2 Fenton-Karma 2D {n}x{n} aniso 9-pt, 30% random fibrosis",
+                    model="fenton_karma", K=9)
+    elif name == "c3":
+        n = max(32, int(round(512 * scale)) // 32 * 32)
+        shape = (n, n, n)
+        mesh = fibrosis_mesh(shape, 0.0, 0, device)
+        sim = DeviceSimulation(_cfg(_m.MitchellSchaeffer3D()), mesh)
+        c = n // 2
+        sim.add_stim(StimVoltageCoord3D(0, 1, c - 5, c + 5, c - 5, c + 5, c - 5, c + 5))
+        tr = ActivationTime3DTracker()
+        tr.threshold, tr.step = 0.5, 1
+        sim.add_tracker(tr, 0)
+        info = dict(workload=f"C3 Mitchell-Schaeffer 3D {n}^3 iso 7-pt, focal stimulus, "
+                             "activation-time tracker every step",
+                    model="mitchell_schaeffer", K=7, tracker_bytes=8)
+    elif name == "c4":
+        n = max(32, int(round(512 * scale)) // 32 * 32)
+        shape = (n, n, n)
+        mesh, fib = ventricle_shell(shape, device)
+        sim = DeviceSimulation(_cfg(_m.TP063D()), mesh, fibers=fib)
+        del fib
+        sim.add_stim(StimVoltageCoord3D(0, -20, 0, n, 0, n, 0, max(4, int(30 * n / 512))))
+        info = dict(workload=f"C4 TP06 3D ventricle-shaped shell in {n}^3, helix fibres, 19-pt",
+                    model="tp06", K=19)
+    elif name == "c5":
+        n = max(32, int(round(1024 * scale)) // 32 * 32)
+        nk = max(32, int(round(128 * scale)) // 32 * 32)
+        shape = (n, n, nk)
+        mesh = fibrosis_mesh(shape, 0.0, 0, device)
+        fib = rotating_fibers_3d(shape, device)
+        sim = DeviceSimulation(_cfg(_m.TP063D()), mesh, fibers=fib)
+        del fib
+        sim.add_stim(StimVoltageCoord3D(0, -20, 0, 5, 0, n, 0, nk))
+        info = dict(workload=f"C5 TP06 3D {n}x{n}x{nk} aniso 19-pt slab (one GPU's share of "
+                             "1024^3 at 8 GPUs), rotating fibres, face stimulus",
+                    model="tp06", K=19)
+    else:
+        raise ValueError(f"unknown workload {name}")
+    info["shape"] = list(sim.shape)
+    info["n_myo"] = int(sim.n_myo)
+    info["bytes_per_node"] = BYTES_PER_NODE[(info["model"], info["K"])] + info.get("tracker_bytes", 0)
+    torch.cuda.empty_cache()
+    return sim, info
