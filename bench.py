@@ -240,11 +240,8 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     peak, peak_src = measured_peak()
     device = torch.device(f"cuda:{local}")
-    if world > 1:
-        from finitewave_b200 import slab
-        sim, info = slab.build_weak(args.workload, device, rank, world, scale=args.scale)
-    else:
-        sim, info = workloads.build(args.workload, device, scale=args.scale)
+    sim, info = workloads.build(args.workload, device, scale=args.scale, rank=rank, world=world,
+                                dist=dist)
 
     with ClockSampler(local) as clk:
         ms, launches = time_device(sim, args.steps, args.warmup, dist)

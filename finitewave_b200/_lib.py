@@ -35,6 +35,10 @@ def _sig(L):
     L.fwb_model_write_mask.argtypes = [c_int]
     L.fwb_model_write_mask.restype = c_uint32
     L.fwb_build_chunks.argtypes = [p, c_int64, p, p, POINTER(c_int64), p]
+    L.fwb_worklist_capacity.argtypes = [c_int, POINTER(c_int64)]
+    L.fwb_worklist_capacity.restype = c_int64
+    L.fwb_build_worklist.argtypes = [c_int, POINTER(c_int64), p, c_int, c_int, p, c_int64,
+                                     POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), p]
     L.fwb_gather_compact.argtypes = [p, p, c_int64, p, p, p]
     L.fwb_scatter_compact.argtypes = [p, p, c_double, c_int64, p, p, p]
     L.fwb_weights_pack.argtypes = [p, p, c_int, c_int64, c_int64, p, p, p]
@@ -43,7 +47,7 @@ def _sig(L):
                                       c_double, c_double, c_double, c_double, c_double,
                                       p, p, c_int64, p, p]
     L.fwb_sim_create.argtypes = [POINTER(c_void_p), c_int, POINTER(c_int64), c_int, c_int,
-                                 p, p, p, c_int64, c_int64, p, p, p, p,
+                                 p, p, p, c_int64, c_int64, p, c_int64, p, p, p, p,
                                  POINTER(c_double), c_int, c_double, p]
     L.fwb_sim_destroy.argtypes = [p]
     L.fwb_sim_set_time.argtypes = [p, c_double, c_int64]
@@ -69,13 +73,17 @@ def _sig(L):
     L.fwb_sim_run.argtypes = [p, c_int64]
     L.fwb_sim_launch_count.argtypes = [p]
     L.fwb_sim_launch_count.restype = c_int64
-    L.fwb_diffuse.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_int64, p, p, p, p]
-    if hasattr(L, "fwb_sim_set_halo"):
-        L.fwb_sim_set_halo.argtypes = [p, c_int, c_int, p, p, p, p, p, p, p, p]
-        L.fwb_ipc_get_handle.argtypes = [p, p]
-        L.fwb_ipc_open_handle.argtypes = [p, POINTER(c_void_p)]
-        L.fwb_ipc_close_handle.argtypes = [p]
-        L.fwb_ipc_handle_size.restype = c_int
+    L.fwb_diffuse.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_int64, p, c_int64,
+                              p, p, p, p]
+    L.fwb_dev_alloc.argtypes = [POINTER(c_void_p), c_int64]
+    L.fwb_dev_free.argtypes = [p]
+    L.fwb_ipc_handle_size.restype = c_int
+    L.fwb_ipc_get_handle.argtypes = [p, p]
+    L.fwb_ipc_open_handle.argtypes = [p, POINTER(c_void_p)]
+    L.fwb_ipc_close_handle.argtypes = [p]
+    L.fwb_sim_set_halo.argtypes = [p, p, p, p, c_int64, p, c_int64, p, p, c_int64, p, c_int64]
+    L.fwb_sim_set_slow_offset.argtypes = [p, c_int64]
+    L.fwb_sim_halo_sync.argtypes = [p]
 
 
 def lib():

@@ -99,6 +99,63 @@ __global__ void __launch_bounds__(1024) scan_final_kernel(const uint32_t *bits, 
 }
 
 // ---------------------------------------------------------------------------
+// work list: ids of the chunks that contain active nodes, in tile order
+// ---------------------------------------------------------------------------
+struct WlSeg {
+    int64_t s0, s1;        // slice range of the segment (slowest axis)
+    int64_t R, cpl;        // rows per slice, chunks per line
+    int ts, tr, tc;        // tile = ts slices x tr rows x tc column segments (ts*tr*tc = 8)
+    int64_t nTc, nTr;      // tiles along columns / rows
+    int64_t n_pos;         // positions = tiles * 8
+    int linear;            // 1: position == chunk id (line % 32 != 0)
+    int64_t n_chunks, n_nodes;
+};
+
+__global__ void worklist_mark_kernel(WlSeg sg, const uint8_t *mask, int32_t *cand, uint32_t *flag)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sg.n_pos) return;
+    int64_t chunk = -1;
+    if (sg.linear) {
+        chunk = q < sg.n_chunks ? q : -1;
+    } else {
+        const int w = (int)(q & 7);
+        const int64_t T = q >> 3;
+        const int ws = w / (sg.tr * sg.tc), wr = (w / sg.tc) % sg.tr, wc = w % sg.tc;
+        const int64_t Tc = T % sg.nTc, Tr = (T / sg.nTc) % sg.nTr, Ts = T / (sg.nTc * sg.nTr);
+        const int64_t slice = sg.s0 + Ts * sg.ts + ws, row = Tr * sg.tr + wr, seg = Tc * sg.tc + wc;
+        if (slice < sg.s1 && row < sg.R && seg < sg.cpl) chunk = (slice * sg.R + row) * sg.cpl + seg;
+    }
+    uint32_t on = 0;
+    if (chunk >= 0) {
+        const int64_t n0 = chunk * 32;
+        const int cnt = (int)min((int64_t)32, sg.n_nodes - n0);
+        for (int l = 0; l < cnt; ++l) on |= mask[n0 + l];
+        on = on ? 1u : 0u;
+    }
+    cand[q] = (int32_t)chunk;
+    flag[q] = on;
+}
+
+__global__ void worklist_scatter_kernel(int64_t n_pos, const int32_t *cand, const uint32_t *flag,
+                                        const uint32_t *base, int32_t *out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pos) return;
+    if (flag[q]) out[base[q]] = cand[q];
+}
+
+// slab halo: hold the stream until both neighbours have finished step `epoch - 1`
+__global__ void halo_wait_kernel(const unsigned *flag_lo, const unsigned *flag_hi, unsigned epoch)
+{
+    if (threadIdx.x == 0) {
+        if (flag_lo) while (*(volatile const unsigned *)flag_lo < epoch) __nanosleep(64);
+        if (flag_hi) while (*(volatile const unsigned *)flag_hi < epoch) __nanosleep(64);
+        __threadfence_system();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // dense <-> compact
 // ---------------------------------------------------------------------------
 __global__ void gather_kernel(const double *dense, double *compact, int64_t n_chunks,
@@ -286,9 +343,165 @@ int launch_point_gather(const int64_t *items, const double *fill, int n_items, c
     return 0;
 }
 
+int launch_halo_wait(const unsigned *flag_lo, const unsigned *flag_hi, unsigned epoch,
+                     cudaStream_t s)
+{
+    halo_wait_kernel<<<1, 32, 0, s>>>(flag_lo, flag_hi, epoch);
+    FWB_KERNEL_CHECK("halo_wait_kernel");
+    return 0;
+}
+
+// exclusive scan of popcount(bits[i]) into base[i]; total to the host (synchronises)
+static int scan_popc(const uint32_t *bits, int64_t n, uint32_t *base, unsigned long long *total,
+                     cudaStream_t s)
+{
+    const int n_sb = (int)((n + SCAN_ITEMS - 1) / SCAN_ITEMS);
+    unsigned long long *tot = nullptr;
+    FWB_CUDA(cudaMallocAsync((void **)&tot, sizeof(unsigned long long) * (n_sb + 1), s));
+    scan_totals_kernel<<<n_sb, 1024, 0, s>>>(bits, n, tot);
+    FWB_KERNEL_CHECK("scan_totals_kernel");
+    scan_blocks_kernel<<<1, 32, 0, s>>>(tot, n_sb, tot + n_sb);
+    FWB_KERNEL_CHECK("scan_blocks_kernel");
+    scan_final_kernel<<<n_sb, 1024, 0, s>>>(bits, n, tot, base);
+    FWB_KERNEL_CHECK("scan_final_kernel");
+    FWB_CUDA(cudaMemcpyAsync(total, tot + n_sb, sizeof(*total), cudaMemcpyDeviceToHost, s));
+    FWB_CUDA(cudaStreamSynchronize(s));
+    FWB_CUDA(cudaFreeAsync(tot, s));
+    return 0;
+}
+
 }  // namespace fwb
 
 using namespace fwb;
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+extern "C" int64_t fwb_worklist_capacity(int dim, const int64_t *shape)
+{
+    if (!shape || (dim != 2 && dim != 3)) return FWB_E_ARG;
+    int64_t n = 1;
+    for (int d = 0; d < dim; ++d) n *= shape[d];
+    // every chunk once + padding of each of the three segments and of partial tiles
+    const int64_t line = shape[dim - 1];
+    const int64_t S = shape[0], R = dim == 3 ? shape[1] : 1;
+    if (line % 32 != 0) return cdiv(n, 32) + 8;
+    const int64_t cpl = line / 32;
+    return (cdiv(S, 2) * 2 + 4) * (cdiv(R, 8) * 8) * (cdiv(cpl, 8) * 8) + 64;
+}
+
+extern "C" int fwb_build_worklist(int dim, const int64_t *shape, const uint8_t *active,
+                                  int halo_lo, int halo_hi, int32_t *worklist,
+                                  int64_t capacity, int64_t *n_work, int64_t *n_lo_blocks,
+                                  int64_t *n_hi_blocks, fwb_stream_t stream)
+{
+    if (!shape || (dim != 2 && dim != 3) || !active || !worklist || !n_work) {
+        set_error("fwb_build_worklist: bad argument");
+        return FWB_E_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n_nodes = 1;
+    for (int d = 0; d < dim; ++d) n_nodes *= shape[d];
+    const int64_t line = shape[dim - 1];
+    const int64_t S = shape[0], R = dim == 3 ? shape[1] : 1;
+    const bool tiled = line % 32 == 0;
+    if ((halo_lo || halo_hi) && (!tiled || S < 4)) {
+        set_error("fwb_build_worklist: a slab halo needs a contiguous axis that is a multiple "
+                  "of 32 nodes and at least 4 slices");
+        return FWB_E_UNSUPPORTED;
+    }
+    FWB_CUDA(cudaMemsetAsync(worklist, 0xff, sizeof(int32_t) * capacity, s));
+
+    WlSeg segs[3];
+    int n_segs = 0;
+    auto make = [&](int64_t s0, int64_t s1, bool boundary) {
+        WlSeg g;
+        memset(&g, 0, sizeof(g));
+        g.s0 = s0; g.s1 = s1; g.R = R; g.cpl = tiled ? line / 32 : 0;
+        g.n_chunks = cdiv(n_nodes, 32); g.n_nodes = n_nodes;
+        if (!tiled) { g.linear = 1; g.n_pos = g.n_chunks; return g; }
+        if (dim == 3) { if (boundary) { g.ts = 1; g.tr = 8; g.tc = 1; } else { g.ts = 2; g.tr = 4; g.tc = 1; } }
+        else { if (boundary) { g.ts = 1; g.tr = 1; g.tc = 8; } else { g.ts = 8; g.tr = 1; g.tc = 1; } }
+        g.nTc = cdiv(g.cpl, g.tc); g.nTr = cdiv(R, g.tr);
+        g.n_pos = cdiv(s1 - s0, g.ts) * g.nTr * g.nTc * 8;
+        return g;
+    };
+    int64_t lo0 = 0, hi1 = S;
+    if (halo_lo) { segs[n_segs++] = make(1, 2, true); lo0 = 2; }
+    if (halo_hi) { segs[n_segs++] = make(S - 2, S - 1, true); hi1 = S - 2; }
+    // ghost slices (0 / S-1 on a halo side) are never listed
+    segs[n_segs++] = make(halo_lo ? lo0 : 0, halo_hi ? hi1 : S, false);
+
+    int64_t off = 0, blocks[3] = {0, 0, 0};
+    for (int i = 0; i < n_segs; ++i) {
+        const WlSeg &g = segs[i];
+        if (g.n_pos <= 0) continue;
+        int32_t *cand = nullptr;
+        uint32_t *flag = nullptr, *base = nullptr;
+        FWB_CUDA(cudaMallocAsync((void **)&cand, sizeof(int32_t) * g.n_pos, s));
+        FWB_CUDA(cudaMallocAsync((void **)&flag, sizeof(uint32_t) * g.n_pos, s));
+        FWB_CUDA(cudaMallocAsync((void **)&base, sizeof(uint32_t) * g.n_pos, s));
+        const unsigned nb = (unsigned)cdiv(g.n_pos, 256);
+        worklist_mark_kernel<<<nb, 256, 0, s>>>(g, active, cand, flag);
+        FWB_KERNEL_CHECK("worklist_mark_kernel");
+        unsigned long long total = 0;
+        int rc = scan_popc(flag, g.n_pos, base, &total, s);
+        if (rc) return rc;
+        if (off + (int64_t)total > capacity) {
+            set_error("fwb_build_worklist: capacity %lld too small", (long long)capacity);
+            return FWB_E_ARG;
+        }
+        worklist_scatter_kernel<<<nb, 256, 0, s>>>(g.n_pos, cand, flag, base, worklist + off);
+        FWB_KERNEL_CHECK("worklist_scatter_kernel");
+        FWB_CUDA(cudaFreeAsync(cand, s));
+        FWB_CUDA(cudaFreeAsync(flag, s));
+        FWB_CUDA(cudaFreeAsync(base, s));
+        blocks[i] = cdiv((int64_t)total, WARPS_PER_BLOCK);
+        off += blocks[i] * WARPS_PER_BLOCK;      // segments start on a block boundary
+    }
+    FWB_CUDA(cudaStreamSynchronize(s));
+    *n_work = off;
+    int bi = 0;
+    if (n_lo_blocks) *n_lo_blocks = halo_lo ? blocks[bi] : 0;
+    if (halo_lo) ++bi;
+    if (n_hi_blocks) *n_hi_blocks = halo_hi ? blocks[bi] : 0;
+    return 0;
+}
+
+// ---- IPC-exportable device memory for slab halos ---------------------------
+extern "C" int fwb_dev_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) { set_error("fwb_dev_alloc: bad argument"); return FWB_E_ARG; }
+    FWB_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    FWB_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+    return 0;
+}
+extern "C" int fwb_dev_free(void *ptr)
+{
+    if (ptr) FWB_CUDA(cudaFree(ptr));
+    return 0;
+}
+extern "C" int fwb_ipc_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+extern "C" int fwb_ipc_get_handle(const void *ptr, void *handle_out)
+{
+    if (!ptr || !handle_out) { set_error("fwb_ipc_get_handle: bad argument"); return FWB_E_ARG; }
+    cudaIpcMemHandle_t h;
+    FWB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+extern "C" int fwb_ipc_open_handle(const void *handle, void **ptr_out)
+{
+    if (!handle || !ptr_out) { set_error("fwb_ipc_open_handle: bad argument"); return FWB_E_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    FWB_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int fwb_ipc_close_handle(void *ptr)
+{
+    if (ptr) FWB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
 
 extern "C" int fwb_build_chunks(const uint8_t *update_mask, int64_t n_nodes,
                                 uint32_t *chunk_bits, uint32_t *chunk_base,
@@ -303,19 +516,11 @@ extern "C" int fwb_build_chunks(const uint8_t *update_mask, int64_t n_nodes,
     chunk_bits_kernel<<<warp_blocks(n_chunks, 256), 256, 0, s>>>(update_mask, n_nodes, chunk_bits,
                                                                   n_chunks);
     FWB_KERNEL_CHECK("chunk_bits_kernel");
-    const int n_sb = (int)((n_chunks + SCAN_ITEMS - 1) / SCAN_ITEMS);
-    unsigned long long *tot = nullptr;
-    FWB_CUDA(cudaMallocAsync((void **)&tot, sizeof(unsigned long long) * (n_sb + 1), s));
-    scan_totals_kernel<<<n_sb, 1024, 0, s>>>(chunk_bits, n_chunks, tot);
-    FWB_KERNEL_CHECK("scan_totals_kernel");
-    scan_blocks_kernel<<<1, 32, 0, s>>>(tot, n_sb, tot + n_sb);
-    FWB_KERNEL_CHECK("scan_blocks_kernel");
-    scan_final_kernel<<<n_sb, 1024, 0, s>>>(chunk_bits, n_chunks, tot, chunk_base);
-    FWB_KERNEL_CHECK("scan_final_kernel");
     unsigned long long total = 0;
-    FWB_CUDA(cudaMemcpyAsync(&total, tot + n_sb, sizeof(total), cudaMemcpyDeviceToHost, s));
-    FWB_CUDA(cudaStreamSynchronize(s));
-    FWB_CUDA(cudaFreeAsync(tot, s));
+    {
+        int rc = scan_popc(chunk_bits, n_chunks, chunk_base, &total, s);
+        if (rc) return rc;
+    }
     if (total > 0xffffffffULL) {
         set_error("fwb_build_chunks: more than 2^32 updated nodes on one device");
         return FWB_E_UNSUPPORTED;

@@ -38,26 +38,27 @@ int cuda_fail(cudaError_t e, const char *what);
 // `line` is the contiguous axis.  A chunk is 32 consecutive FLAT nodes; a warp
 // owns one chunk, lane l owns node 32*chunk + l.
 //
-// Block -> chunk mapping (tile_* > 0, used when line % 32 == 0): a block of
-// WARPS_PER_BLOCK warps covers tile_p planes x tile_r rows of one 32-node
-// column segment, so that the stencil's neighbour lines are shared through L1.
-// Otherwise (cpl == 0) blocks take WARPS_PER_BLOCK consecutive chunks.
+// Which chunk a warp takes comes from the WORK LIST (fwb_build_worklist): the ids
+// of all chunks that contain tissue, in tile order (a block's 8 consecutive
+// entries are 2 planes x 4 rows, or 8 rows in 2D, of one 32-node column segment,
+// so the stencil's neighbour lines are shared through L1), padded with -1.  The
+// list removes all index arithmetic from the step kernel, skips empty space
+// (ventricle-shaped meshes) at block granularity, and fixes the block order:
+// with a halo the chunks of the two slab-boundary planes come first.
 // ---------------------------------------------------------------------------
 struct Grid {
     int dim;
+    int planes, rows, line;
     int64_t n_nodes;
     int64_t n_chunks;
     int64_t s_plane;   // flat stride of axis i (3D) ; 0 in 2D
     int64_t s_row;     // flat stride of the row axis (j in 3D, i in 2D) = line length
-    int planes, rows, line;
-    int cpl;           // chunks per line (line / 32) or 0 for the linear mapping
-    int tile_p, tile_r;
-    int tiles_r;       // ceil(rows / tile_r)
-    int tiles_p;       // ceil(planes / tile_p)
-    int64_t n_blocks;
+    int64_t slow_offset;   // global index of local slice 0 of the slowest axis (slab runs)
     const uint32_t *chunk_bits;
     const uint32_t *chunk_base;
     int64_t ld;
+    const int32_t *worklist;   // [n_work], -1 = padding
+    int64_t n_work;
 };
 
 inline Grid make_grid(int dim, const int64_t *shape, const uint32_t *bits,
@@ -80,40 +81,14 @@ inline Grid make_grid(int dim, const int64_t *shape, const uint32_t *bits,
     g.chunk_bits = bits;
     g.chunk_base = base;
     g.ld = ld;
-    if (g.line % 32 == 0) {
-        g.cpl = g.line / 32;
-        if (dim == 3 && g.planes >= 2) { g.tile_p = 2; g.tile_r = WARPS_PER_BLOCK / 2; }
-        else { g.tile_p = 1; g.tile_r = WARPS_PER_BLOCK; }
-        g.tiles_r = (g.rows + g.tile_r - 1) / g.tile_r;
-        g.tiles_p = (g.planes + g.tile_p - 1) / g.tile_p;
-        g.n_blocks = (int64_t)g.cpl * g.tiles_r * g.tiles_p;
-    } else {
-        g.cpl = 0;
-        g.n_blocks = (g.n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    }
     return g;
 }
 
-#ifdef __CUDACC__
-// chunk owned by this warp, or -1
-__device__ __forceinline__ int64_t warp_chunk(const Grid &g)
-{
-    const int warp = threadIdx.x >> 5;
-    if (g.cpl == 0) {
-        const int64_t c = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-        return c < g.n_chunks ? c : -1;
-    }
-    const unsigned b = blockIdx.x;
-    const unsigned seg = b % (unsigned)g.cpl;
-    const unsigned b2 = b / (unsigned)g.cpl;
-    const unsigned tr = b2 % (unsigned)g.tiles_r;
-    const unsigned tp = b2 / (unsigned)g.tiles_r;
-    const int r = (int)tr * g.tile_r + warp % g.tile_r;
-    const int p = (int)tp * g.tile_p + warp / g.tile_r;
-    if (r >= g.rows || p >= g.planes) return -1;
-    return ((int64_t)p * g.rows + r) * g.cpl + seg;
-}
+// nodes per slice of the slowest axis (the slab / halo unit): a plane in 3D, a row in 2D
+inline int64_t slow_stride(const Grid &g) { return g.dim == 3 ? g.s_plane : g.s_row; }
+inline int64_t slow_extent(const Grid &g) { return g.dim == 3 ? g.planes : g.rows; }
 
+#ifdef __CUDACC__
 // exact IEEE multiply/add that the compiler may never contract into an FMA
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }

@@ -10,10 +10,21 @@
 //   derive()          host: reference parameter vector -> Consts
 //   ionic()           device: one node, one time step.  `u` is the old
 //                     potential, `un` enters as the diffusion result and
-//                     leaves as u_new; s[] are the node's state values.
+//                     leaves as u_new; the node's state values are read and
+//                     written through `io.ld(slot)` / `io.st(slot, v)` where
+//                     they are needed, so that only a few are live at a time
+//                     (TP06 has 19 of them).
+//   MIN_BLOCKS        __launch_bounds__ occupancy target of the step kernel
 //
 // The arithmetic keeps the reference's association order; the translation
 // unit is compiled with -fmad=false so no multiply-add is contracted.
+// Divisions by parameters and literals go through divc(): multiply by the
+// correctly rounded reciprocal + one exact FMA residual correction, which
+// returns the correctly rounded quotient (Markstein's theorem; checked against
+// `/` on 1e9 random operands and bit-for-bit against the oracle in
+// tests/test_host_models.py) in 3 FP64 instructions instead of the ~20 of the
+// generic division -- whose slow path is taken whenever the numerator is zero,
+// which the Heaviside-gated terms of Fenton-Karma hit on every node.
 // Reference line numbers are cited per model.
 #pragma once
 #include <math.h>
@@ -28,6 +39,30 @@
 
 namespace fwb {
 
+// divisor known on the host: the value and its correctly rounded reciprocal
+struct DivC {
+    double c, rc;
+};
+inline DivC make_divc(double c)
+{
+    DivC d;
+    d.c = c;
+    d.rc = 1.0 / c;
+    return d;
+}
+// x / d.c, correctly rounded (for finite non-zero d.c and no over/underflow)
+FWB_HD double divc(double x, const DivC &d)
+{
+    const double q = x * d.rc;
+    const double r = fma(-q, d.c, x);
+    return fma(r, d.rc, q);
+}
+// x / k for a literal k (the reciprocal is folded at compile time)
+#define FWB_DIVK(x, k) ::fwb::divc((x), ::fwb::DivC{(k), 1.0 / (k)})
+
+// every DivC of a Consts block must be usable (parameter finite and non-zero)
+inline bool divc_ok(const DivC &d) { return d.rc == d.rc && d.rc != 0.0 && (d.rc - d.rc) == 0.0; }
+
 template <int MODEL> struct Model;
 
 // ---------------------------------------------------------------------------
@@ -35,18 +70,20 @@ template <int MODEL> struct Model;
 // (calc_v), :173-202 (ionic_kernel_2d); 3D: cpuwave3D/model/aliev_panfilov_3d.py:53-84
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_ALIEV_PANFILOV> {
-    static constexpr int NS = 1, NP = 5;
+    static constexpr int NS = 1, NP = 5, MIN_BLOCKS = 4;
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
     struct Consts { double dt, a, k, eap, mu_1, mu_2; };
-    static void derive(const double *p, double dt, Consts &c)
+    static bool derive(const double *p, double dt, Consts &c)
     {
         c.dt = dt; c.a = p[0]; c.k = p[1]; c.eap = p[2]; c.mu_1 = p[3]; c.mu_2 = p[4];
+        return true;
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        double v = s[0];
+        double v = io.ld(0);
         v += (-c.dt * (c.eap + (c.mu_1 * v) / (c.mu_2 + u)) * (v + c.k * u * (u - c.a - 1.)));
-        s[0] = v;
+        io.st(0, v);
         un += c.dt * (-c.k * u * (u - c.a) * (u - 1.) - u * v);
     }
 };
@@ -55,19 +92,21 @@ template <> struct Model<FWB_MODEL_ALIEV_PANFILOV> {
 // Barkley -- cpuwave2D/model/barkley_2d.py:113-137, :140-166; barkley_3d.py:53-83
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_BARKLEY> {
-    static constexpr int NS = 1, NP = 3;
+    static constexpr int NS = 1, NP = 3, MIN_BLOCKS = 4;
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
-    struct Consts { double dt, a, b, eap; };
-    static void derive(const double *p, double dt, Consts &c)
+    struct Consts { double dt, b; DivC a, eap; };
+    static bool derive(const double *p, double dt, Consts &c)
     {
-        c.dt = dt; c.a = p[0]; c.b = p[1]; c.eap = p[2];
+        c.dt = dt; c.a = make_divc(p[0]); c.b = p[1]; c.eap = make_divc(p[2]);
+        return divc_ok(c.a) && divc_ok(c.eap);
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        double v = s[0];
+        double v = io.ld(0);
         v += c.dt * (u - v);
-        s[0] = v;
-        un += c.dt * (u * (1 - u) * (u - (v + c.b) / c.a)) / c.eap;
+        io.st(0, v);
+        un += divc(c.dt * (u * (1 - u) * (u - divc(v + c.b, c.a))), c.eap);
     }
 };
 
@@ -76,22 +115,25 @@ template <> struct Model<FWB_MODEL_BARKLEY> {
 // :188-217; mitchell_schaeffer_3d.py:57-95.  strict `u < u_gate`.
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_MITCHELL_SCHAEFFER> {
-    static constexpr int NS = 1, NP = 5;
+    static constexpr int NS = 1, NP = 5, MIN_BLOCKS = 4;
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
-    struct Consts { double dt, tau_close, tau_open, tau_in, tau_out, u_gate; };
-    static void derive(const double *p, double dt, Consts &c)
+    struct Consts { double dt, u_gate; DivC tau_close, tau_open, tau_in, tau_out; };
+    static bool derive(const double *p, double dt, Consts &c)
     {
-        c.dt = dt; c.tau_close = p[0]; c.tau_open = p[1]; c.tau_in = p[2];
-        c.tau_out = p[3]; c.u_gate = p[4];
+        c.dt = dt; c.tau_close = make_divc(p[0]); c.tau_open = make_divc(p[1]);
+        c.tau_in = make_divc(p[2]); c.tau_out = make_divc(p[3]); c.u_gate = p[4];
+        return divc_ok(c.tau_close) && divc_ok(c.tau_open) && divc_ok(c.tau_in) &&
+               divc_ok(c.tau_out);
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        double h = s[0];
-        h += (u < c.u_gate) ? c.dt * (1.0 - h) / c.tau_open : c.dt * (-h) / c.tau_close;
-        s[0] = h;
+        double h = io.ld(0);
+        h += (u < c.u_gate) ? divc(c.dt * (1.0 - h), c.tau_open) : divc(c.dt * (-h), c.tau_close);
+        io.st(0, h);
         const double C = (u * u) * (1 - u);
-        const double J_in = h * C / c.tau_in;
-        const double J_out = -u / c.tau_out;
+        const double J_in = divc(h * C, c.tau_in);
+        const double J_out = divc(-u, c.tau_out);
         un += c.dt * (J_in + J_out);
     }
 };
@@ -102,31 +144,36 @@ template <> struct Model<FWB_MODEL_MITCHELL_SCHAEFFER> {
 // evaluated with v (not w) exactly as the reference does (:326).
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_FENTON_KARMA> {
-    static constexpr int NS = 2, NP = 11;
+    static constexpr int NS = 2, NP = 11, MIN_BLOCKS = 4;
     static constexpr uint32_t READ_MASK = 0x3, WRITE_MASK = 0x3;
     struct Consts {
-        double dt, tau_d, tau_o, tau_r, tau_si, tau_v_m, tau_v_p, tau_w_m, tau_w_p, k,
-            u_c, uc_si, two_tau_si;
+        double dt, k, u_c, uc_si;
+        DivC tau_d, tau_o, tau_r, tau_v_m, tau_v_p, tau_w_m, tau_w_p, two_tau_si;
     };
-    static void derive(const double *p, double dt, Consts &c)
+    static bool derive(const double *p, double dt, Consts &c)
     {
-        c.dt = dt; c.tau_d = p[0]; c.tau_o = p[1]; c.tau_r = p[2]; c.tau_si = p[3];
-        c.tau_v_m = p[4]; c.tau_v_p = p[5]; c.tau_w_m = p[6]; c.tau_w_p = p[7];
+        c.dt = dt; c.tau_d = make_divc(p[0]); c.tau_o = make_divc(p[1]);
+        c.tau_r = make_divc(p[2]); c.two_tau_si = make_divc(2 * p[3]);
+        c.tau_v_m = make_divc(p[4]); c.tau_v_p = make_divc(p[5]);
+        c.tau_w_m = make_divc(p[6]); c.tau_w_p = make_divc(p[7]);
         c.k = p[8]; c.u_c = p[9]; c.uc_si = p[10];
-        c.two_tau_si = 2 * c.tau_si;
+        return divc_ok(c.tau_d) && divc_ok(c.tau_o) && divc_ok(c.tau_r) &&
+               divc_ok(c.two_tau_si) && divc_ok(c.tau_v_m) && divc_ok(c.tau_v_p) &&
+               divc_ok(c.tau_w_m) && divc_ok(c.tau_w_p);
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
         const double H1 = (c.u_c - u >= 0) ? 1.0 : 0.0;
         const double H2 = (u - c.u_c >= 0) ? 1.0 : 0.0;
-        double v = s[0], w = s[1];
-        v += c.dt * (H1 * (1 - v) / c.tau_v_m - H2 * v / c.tau_v_p);
-        w += c.dt * (H1 * (1 - w) / c.tau_w_m - H2 * w / c.tau_w_p);
-        s[0] = v;
-        s[1] = w;
-        const double J_fi = -(v * H2 * (1 - u) * (u - c.u_c)) / c.tau_d;
-        const double J_so = u * H1 / c.tau_o + H2 / c.tau_r;
-        const double J_si = -v * (1 + tanh(c.k * (u - c.uc_si))) / c.two_tau_si;
+        double v = io.ld(0), w = io.ld(1);
+        v += c.dt * (divc(H1 * (1 - v), c.tau_v_m) - divc(H2 * v, c.tau_v_p));
+        w += c.dt * (divc(H1 * (1 - w), c.tau_w_m) - divc(H2 * w, c.tau_w_p));
+        io.st(0, v);
+        io.st(1, w);
+        const double J_fi = divc(-(v * H2 * (1 - u) * (u - c.u_c)), c.tau_d);
+        const double J_so = divc(u * H1, c.tau_o) + divc(H2, c.tau_r);
+        const double J_si = divc(-v * (1 + tanh(c.k * (u - c.uc_si))), c.two_tau_si);
         un += c.dt * (-J_fi - J_so - J_si);
     }
 };
@@ -138,13 +185,13 @@ template <> struct Model<FWB_MODEL_FENTON_KARMA> {
 // state: m,h,j,d,f,x,cai
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_LUO_RUDY91> {
-    static constexpr int NS = 7, NP = 15;
+    static constexpr int NS = 7, NP = 15, MIN_BLOCKS = 3;
     static constexpr uint32_t READ_MASK = 0x7f, WRITE_MASK = 0x7f;
     struct Consts {
         double dt, gna, gsi, gkp, gb;
         double E_Na, E_K, G_K, E_K1, G_K1;   // parameter-only (:478, :337-338, :496, :404)
     };
-    static void derive(const double *p, double dt, Consts &c)
+    static bool derive(const double *p, double dt, Consts &c)
     {
         const double gk = p[2], gk1 = p[3], ko = p[6], ki = p[7], nai = p[8], nao = p[9],
                      R = p[11], T = p[12], F = p[13], PR_NaK = p[14];
@@ -154,6 +201,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         c.G_K = gk * sqrt(ko / 5.4);
         c.E_K1 = (R * T / F) * log(ko / ki);
         c.G_K1 = gk1 * sqrt(ko / 5.4);
+        return true;
     }
     FWB_HD static double gate(double var, double dt, double alpha, double beta)
     {
@@ -162,30 +210,31 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         var += dt * (inf - var) / tau;
         return var;
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
         const double dt = c.dt;
         // calc_ina :185-241
         double alpha_h = 0, beta_h = 0, beta_J = 0, alpha_J = 0;
         if (u >= -40.) {
-            beta_h = 1. / (0.13 * (1 + exp((u + 10.66) / -11.1)));
+            beta_h = 1. / (0.13 * (1 + exp(FWB_DIVK(u + 10.66, -11.1))));
             beta_J = 0.3 * exp(-2.535 * 1e-07 * u) / (1 + exp(-0.1 * (u + 32)));
         } else {
-            alpha_h = 0.135 * exp((80 + u) / -6.8);
+            alpha_h = 0.135 * exp(FWB_DIVK(80 + u, -6.8));
             beta_h = 3.56 * exp(0.079 * u) + 3.1 * 1e5 * exp(0.35 * u);
             beta_J = 0.1212 * exp(-0.01052 * u) / (1 + exp(-0.1378 * (u + 40.14)));
             alpha_J = (-1.2714 * 1e5 * exp(0.2444 * u) - 3.474 * 1e-5 * exp(-0.04391 * u)) *
                       (u + 37.78) / (1 + exp(0.311 * (u + 79.23)));
         }
         const double alpha_m = 0.32 * (u + 47.13) / (1 - exp(-0.1 * (u + 47.13)));
-        const double beta_m = 0.08 * exp(-u / 11);
-        const double m = gate(s[0], dt, alpha_m, beta_m);
-        const double h = gate(s[1], dt, alpha_h, beta_h);
-        const double j = gate(s[2], dt, alpha_J, beta_J);
-        s[0] = m; s[1] = h; s[2] = j;
+        const double beta_m = 0.08 * exp(FWB_DIVK(-u, 11.));
+        const double m = gate(io.ld(0), dt, alpha_m, beta_m);
+        const double h = gate(io.ld(1), dt, alpha_h, beta_h);
+        const double j = gate(io.ld(2), dt, alpha_J, beta_J);
+        io.st(0, m); io.st(1, h); io.st(2, j);
         const double ina = c.gna * m * m * m * h * j * (u - c.E_Na);
         // calc_isk :244-294
-        double d = s[3], f = s[4], cai = s[6];
+        double d = io.ld(3), f = io.ld(4), cai = io.ld(6);
         const double E_Si = 7.7 - 13.0287 * log(cai);
         const double I_Si = c.gsi * d * f * (u - E_Si);
         const double alpha_d = 0.095 * exp(-0.01 * (u - 5)) / (1 + exp(-0.072 * (u - 5)));
@@ -195,19 +244,19 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         d = gate(d, dt, alpha_d, beta_d);
         f = gate(f, dt, alpha_f, beta_f);
         cai += dt * (-0.0001 * I_Si + 0.07 * (0.0001 - cai));
-        s[3] = d; s[4] = f; s[6] = cai;
+        io.st(3, d); io.st(4, f); io.st(6, cai);
         // calc_ik :297-356
         double Xi;
         if (u > -100)
             Xi = 2.837 * (exp(0.04 * (u + 77)) - 1) / ((u + 77) * exp(0.04 * (u + 35)));
         else
             Xi = 1;
-        double x = s[5];
+        double x = io.ld(5);
         const double I_K = c.G_K * x * Xi * (u - c.E_K);
         const double alpha_x = 0.0005 * exp(0.083 * (u + 50)) / (1 + exp(0.057 * (u + 50)));
         const double beta_x = 0.0013 * exp(-0.06 * (u + 20)) / (1 + exp(-0.04 * (u + 20)));
         x = gate(x, dt, alpha_x, beta_x);
-        s[5] = x;
+        io.st(5, x);
         // calc_ik1 :359-408, calc_ikp :411-427, calc_ib :430-443, kernel :496-510
         const double E_K1 = c.E_K1;
         const double alpha_K1 = 1.02 / (1 + exp(0.2385 * (u - E_K1 - 59.215)));
@@ -216,7 +265,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
                                (1 + exp(-0.5143 * (u - E_K1 + 4.753)));
         const double K_1x = alpha_K1 / (alpha_K1 + beta_K1);
         const double ik1 = c.G_K1 * K_1x * (u - E_K1);
-        const double K_p = 1. / (1 + exp((7.488 - u) / 5.98));
+        const double K_p = 1. / (1 + exp(FWB_DIVK(7.488 - u, 5.98)));
         const double ikp = c.gkp * K_p * (u - E_K1);
         const double ib = c.gb * (u + 59.87);
         const double ik1t = ik1 + ikp + ib;
@@ -234,20 +283,21 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
 //        10 xs, 11 r, 12 s, 13 d, 14 f, 15 f2, 16 fcass, 17 rr, 18 oo
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_TP06> {
-    static constexpr int NS = 19, NP = 49;
+    static constexpr int NS = 19, NP = 49, MIN_BLOCKS = 2;
     static constexpr uint32_t READ_MASK = 0x3ffff;          // all but oo
     static constexpr uint32_t WRITE_MASK = 0x7ffff & ~0x1u;  // all but cai
     struct Consts {
         double dt, ko, cao, nao, RTONF, half_RTONF, CAPACITANCE;
         double pKNa_nao, ko_pKNa_nao, pKNa;
         double gna, gcal, gto, gkr_sqrt, gks, gk1, gpca, KpCa, gpk, gbna, gbca;
-        double F, RT, FF_RT;
+        double F, FF_RT;
+        DivC RT;
         double inaca_pref, ksat, n_, n_m1, knak_pref, KmNa;
         double Bufsr, Kbufsr, Bufss, Kbufss, Vmaxup, Kup2, Vrel, k1_, k2_, k3, k4, EC;
         double maxsr, maxsr_m_minsr, Vleak, Vxfer, Vc_Vss, Vsr_Vss;
         double inverseVcF, inversevssF2;
     };
-    static void derive(const double *p, double dt, Consts &c)
+    static bool derive(const double *p, double dt, Consts &c)
     {
         const double ko = p[0], cao = p[1], nao = p[2], Vc = p[3], Vsr = p[4], Vss = p[5],
                      R = p[24], F = p[25], T = p[26], gkr = p[29], pKNa = p[30],
@@ -259,7 +309,7 @@ template <> struct Model<FWB_MODEL_TP06> {
         c.gkr_sqrt = gkr * sqrt(ko / 5.4);
         c.gks = p[48]; c.gk1 = p[31]; c.gpca = p[44]; c.KpCa = p[45]; c.gpk = p[46];
         c.gbna = p[33]; c.gbca = p[38];
-        c.F = F; c.RT = R * T; c.FF_RT = F * F / (R * T);
+        c.F = F; c.RT = make_divc(R * T); c.FF_RT = F * F / (R * T);
         c.inaca_pref = knaca * (1. / (KmNai * KmNai * KmNai + nao * nao * nao)) * (1. / (KmCa + cao));
         c.ksat = p[42]; c.n_ = p[43]; c.n_m1 = p[43] - 1;
         c.knak_pref = knak * (ko / (ko + KmK)); c.KmNa = p[35];
@@ -270,126 +320,138 @@ template <> struct Model<FWB_MODEL_TP06> {
         c.Vc_Vss = Vc / Vss; c.Vsr_Vss = Vsr / Vss;
         c.inverseVcF = 1. / (Vc * F);
         c.inversevssF2 = 1. / (2 * Vss * F);
+        return divc_ok(c.RT);
     }
-    FWB_HD static void ionic(double u, double &un, double *s, const Consts &c)
+    // Rush-Larsen update (tp06_2d.py:307-309 and twins)
+    FWB_HD static double rl(double inf, double x, double dt, double tau)
+    {
+        return inf - (inf - x) * exp(-dt / tau);
+    }
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
         const double dt = c.dt;
-        const double cai = s[0], casr = s[1], cass = s[2], nai = s[3], Ki = s[4];
+        const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
         // reversal potentials :1072-1075
         const double Ek = c.RTONF * log(c.ko / Ki);
         const double Ena = c.RTONF * log(c.nao / nai);
         const double Eks = c.RTONF * log(c.ko_pKNa_nao / (Ki + c.pKNa * nai));
         const double Eca = c.half_RTONF * log(c.cao / cai);
 
+        // running sums in the reference's final association orders:
+        //   itot = ikr+iks+ik1+ito+ina+ibna+ical+ibca+inak+inaca+ipca+ipk   (:1103)
+        //   dNai: ina+ibna+3 inak+3 inaca        dKi: ik1+ito+ikr+iks-2 inak+ipk
         // calc_ina :242-318
-        double m = s[5], h = s[6], j = s[7];
+        double ina;
         {
-            const double alpha_m = 1. / (1. + exp((-60. - u) / 5.));
-            const double beta_m = 0.1 / (1. + exp((u + 35.) / 5.)) +
-                                  0.10 / (1. + exp((u - 50.) / 200.));
+            const double alpha_m = 1. / (1. + exp(FWB_DIVK(-60. - u, 5.)));
+            const double beta_m = 0.1 / (1. + exp(FWB_DIVK(u + 35., 5.))) +
+                                  0.10 / (1. + exp(FWB_DIVK(u - 50., 200.)));
             const double tau_m = alpha_m * beta_m;
-            const double em = 1. + exp((-56.86 - u) / 9.03);
+            const double em = 1. + exp(FWB_DIVK(-56.86 - u, 9.03));
             const double m_inf = 1. / (em * em);
             double alpha_h, beta_h, alpha_j, beta_j;
             if (u >= -40.) {
                 alpha_h = 0.;
-                beta_h = 0.77 / (0.13 * (1. + exp(-(u + 10.66) / 11.1)));
+                beta_h = 0.77 / (0.13 * (1. + exp(FWB_DIVK(-(u + 10.66), 11.1))));
                 alpha_j = 0.;
                 beta_j = 0.6 * exp(0.057 * u) / (1. + exp(-0.1 * (u + 32.)));
             } else {
-                alpha_h = 0.057 * exp(-(u + 80.) / 6.8);
+                alpha_h = 0.057 * exp(FWB_DIVK(-(u + 80.), 6.8));
                 beta_h = 2.7 * exp(0.079 * u) + 3.1e5 * exp(0.3485 * u);
                 alpha_j = (-2.5428e4 * exp(0.2444 * u) - 6.948e-6 * exp(-0.04391 * u)) *
                           (u + 37.78) / (1. + exp(0.311 * (u + 79.23)));
                 beta_j = 0.02424 * exp(-0.01052 * u) / (1. + exp(-0.1378 * (u + 40.14)));
             }
             const double tau_h = 1.0 / (alpha_h + beta_h);
-            const double eh = 1. + exp((u + 71.55) / 7.43);
+            const double eh = 1. + exp(FWB_DIVK(u + 71.55, 7.43));
             const double h_inf = 1. / (eh * eh);
             const double tau_j = 1.0 / (alpha_j + beta_j);
-            const double j_inf = h_inf;
-            m = m_inf - (m_inf - m) * exp(-dt / tau_m);
-            h = h_inf - (h_inf - h) * exp(-dt / tau_h);
-            j = j_inf - (j_inf - j) * exp(-dt / tau_j);
+            const double m = rl(m_inf, io.ld(5), dt, tau_m);
+            const double h = rl(h_inf, io.ld(6), dt, tau_h);
+            const double j = rl(h_inf, io.ld(7), dt, tau_j);
+            io.st(5, m); io.st(6, h); io.st(7, j);
+            ina = c.gna * m * m * m * h * j * (u - Ena);
         }
-        s[5] = m; s[6] = h; s[7] = j;
-        const double ina = c.gna * m * m * m * h * j * (u - Ena);
 
         // calc_ical :321-380
-        double d = s[13], f = s[14], f2 = s[15], fcass = s[16];
+        const double cass = io.ld(2);
         double ical;
         {
-            const double d_inf = 1. / (1. + exp((-8 - u) / 7.5));
-            const double Ad = 1.4 / (1. + exp((-35 - u) / 13)) + 0.25;
-            const double Bd = 1.4 / (1. + exp((u + 5) / 5));
-            const double Cd = 1. / (1. + exp((50 - u) / 20));
+            const double d_inf = 1. / (1. + exp(FWB_DIVK(-8 - u, 7.5)));
+            const double Ad = 1.4 / (1. + exp(FWB_DIVK(-35 - u, 13.))) + 0.25;
+            const double Bd = 1.4 / (1. + exp(FWB_DIVK(u + 5, 5.)));
+            const double Cd = 1. / (1. + exp(FWB_DIVK(50 - u, 20.)));
             const double tau_d = Ad * Bd + Cd;
-            const double f_inf = 1. / (1. + exp((u + 20) / 7));
-            const double Af = 1102.5 * exp(-(u + 27) * (u + 27) / 225);
-            const double Bf = 200. / (1 + exp((13 - u) / 10.));
-            const double e30 = exp((u + 30) / 10);
+            const double d = rl(d_inf, io.ld(13), dt, tau_d);
+            io.st(13, d);
+            const double f_inf = 1. / (1. + exp(FWB_DIVK(u + 20, 7.)));
+            const double Af = 1102.5 * exp(FWB_DIVK(-(u + 27) * (u + 27), 225.));
+            const double Bf = 200. / (1 + exp(FWB_DIVK(13 - u, 10.)));
+            const double e30 = exp(FWB_DIVK(u + 30, 10.));
             const double Cf = (180. / (1 + e30)) + 20;
             const double tau_f = Af + Bf + Cf;
-            const double f2_inf = 0.67 / (1. + exp((u + 35) / 7)) + 0.33;
-            const double Af2 = 600 * exp(-(u + 25) * (u + 25) / 170);
-            const double Bf2 = 31 / (1. + exp((25 - u) / 10));
+            const double f = rl(f_inf, io.ld(14), dt, tau_f);
+            io.st(14, f);
+            const double f2_inf = 0.67 / (1. + exp(FWB_DIVK(u + 35, 7.))) + 0.33;
+            const double Af2 = 600 * exp(FWB_DIVK(-(u + 25) * (u + 25), 170.));
+            const double Bf2 = 31 / (1. + exp(FWB_DIVK(25 - u, 10.)));
             const double Cf2 = 16 / (1. + e30);
             const double tau_f2 = Af2 + Bf2 + Cf2;
-            const double cq = 1 + (cass / 0.05) * (cass / 0.05);
+            const double f2 = rl(f2_inf, io.ld(15), dt, tau_f2);
+            io.st(15, f2);
+            const double cq = 1 + FWB_DIVK(cass, 0.05) * FWB_DIVK(cass, 0.05);
             const double fcass_inf = 0.6 / cq + 0.4;
             const double tau_fcass = 80. / cq + 2.;
-            d = d_inf - (d_inf - d) * exp(-dt / tau_d);
-            f = f_inf - (f_inf - f) * exp(-dt / tau_f);
-            f2 = f2_inf - (f2_inf - f2) * exp(-dt / tau_f2);
-            fcass = fcass_inf - (fcass_inf - fcass) * exp(-dt / tau_fcass);
-            const double e2 = exp(2 * (u - 15) * c.F / c.RT);
+            const double fcass = rl(fcass_inf, io.ld(16), dt, tau_fcass);
+            io.st(16, fcass);
+            const double e2 = exp(divc(2 * (u - 15) * c.F, c.RT));
             ical = c.gcal * d * f * f2 * fcass * 4 * (u - 15) * c.FF_RT *
                    (0.25 * e2 * cass - c.cao) / (e2 - 1.);
         }
-        s[13] = d; s[14] = f; s[15] = f2; s[16] = fcass;
 
         // calc_ito :383-413
-        double r = s[11], sg = s[12];
+        double ito;
         {
-            const double r_inf = 1. / (1. + exp((20 - u) / 6.));
-            const double s_inf = 1. / (1. + exp((u + 20) / 5.));
-            const double tau_r = 9.5 * exp(-(u + 40.) * (u + 40.) / 1800.) + 0.8;
-            const double tau_s = 85. * exp(-(u + 45.) * (u + 45.) / 320.) +
-                                 5. / (1. + exp((u - 20.) / 5.)) + 3.;
-            sg = s_inf - (s_inf - sg) * exp(-dt / tau_s);
-            r = r_inf - (r_inf - r) * exp(-dt / tau_r);
+            const double r_inf = 1. / (1. + exp(FWB_DIVK(20 - u, 6.)));
+            const double s_inf = 1. / (1. + exp(FWB_DIVK(u + 20, 5.)));
+            const double tau_r = 9.5 * exp(FWB_DIVK(-(u + 40.) * (u + 40.), 1800.)) + 0.8;
+            const double tau_s = 85. * exp(FWB_DIVK(-(u + 45.) * (u + 45.), 320.)) +
+                                 5. / (1. + exp(FWB_DIVK(u - 20., 5.))) + 3.;
+            const double sg = rl(s_inf, io.ld(12), dt, tau_s);
+            const double r = rl(r_inf, io.ld(11), dt, tau_r);
+            io.st(11, r); io.st(12, sg);
+            ito = c.gto * r * sg * (u - Ek);
         }
-        s[11] = r; s[12] = sg;
-        const double ito = c.gto * r * sg * (u - Ek);
 
         // calc_ikr :416-452
-        double xr1 = s[8], xr2 = s[9];
+        double ikr;
         {
-            const double xr1_inf = 1. / (1. + exp((-26. - u) / 7.));
-            const double axr1 = 450. / (1. + exp((-45. - u) / 10.));
-            const double bxr1 = 6. / (1. + exp((u - (-30.)) / 11.5));
+            const double xr1_inf = 1. / (1. + exp(FWB_DIVK(-26. - u, 7.)));
+            const double axr1 = 450. / (1. + exp(FWB_DIVK(-45. - u, 10.)));
+            const double bxr1 = 6. / (1. + exp(FWB_DIVK(u - (-30.), 11.5)));
             const double tau_xr1 = axr1 * bxr1;
-            const double xr2_inf = 1. / (1. + exp((u - (-88.)) / 24.));
-            const double axr2 = 3. / (1. + exp((-60. - u) / 20.));
-            const double bxr2 = 1.12 / (1. + exp((u - 60.) / 20.));
+            const double xr2_inf = 1. / (1. + exp(FWB_DIVK(u - (-88.), 24.)));
+            const double axr2 = 3. / (1. + exp(FWB_DIVK(-60. - u, 20.)));
+            const double bxr2 = 1.12 / (1. + exp(FWB_DIVK(u - 60., 20.)));
             const double tau_xr2 = axr2 * bxr2;
-            xr1 = xr1_inf - (xr1_inf - xr1) * exp(-dt / tau_xr1);
-            xr2 = xr2_inf - (xr2_inf - xr2) * exp(-dt / tau_xr2);
+            const double xr1 = rl(xr1_inf, io.ld(8), dt, tau_xr1);
+            const double xr2 = rl(xr2_inf, io.ld(9), dt, tau_xr2);
+            io.st(8, xr1); io.st(9, xr2);
+            ikr = c.gkr_sqrt * xr1 * xr2 * (u - Ek);
         }
-        s[8] = xr1; s[9] = xr2;
-        const double ikr = c.gkr_sqrt * xr1 * xr2 * (u - Ek);
 
         // calc_iks :455-485
-        double xs = s[10];
+        double iks;
         {
-            const double xs_inf = 1. / (1. + exp((-5. - u) / 14.));
-            const double Axs = (1400. / (sqrt(1. + exp((5. - u) / 6))));
-            const double Bxs = (1. / (1. + exp((u - 35.) / 15.)));
+            const double xs_inf = 1. / (1. + exp(FWB_DIVK(-5. - u, 14.)));
+            const double Axs = (1400. / (sqrt(1. + exp(FWB_DIVK(5. - u, 6.)))));
+            const double Bxs = (1. / (1. + exp(FWB_DIVK(u - 35., 15.))));
             const double tau_xs = Axs * Bxs + 80;
-            xs = xs_inf - (xs_inf - xs) * exp(-dt / tau_xs);
+            const double xs = rl(xs_inf, io.ld(10), dt, tau_xs);
+            io.st(10, xs);
+            iks = c.gks * xs * xs * (u - Eks);
         }
-        s[10] = xs;
-        const double iks = c.gks * xs * xs * (u - Eks);
 
         // calc_ik1 :488-514
         const double ak1 = 0.1 / (1. + exp(0.06 * (u - Ek - 200)));
@@ -398,33 +460,44 @@ template <> struct Model<FWB_MODEL_TP06> {
         const double rec_iK1 = ak1 / (ak1 + bk1);
         const double ik1 = c.gk1 * rec_iK1 * (u - Ek);
         // calc_inaca :517-565
-        const double e_nm1 = exp(c.n_m1 * u * c.F / c.RT);
+        const double e_nm1 = exp(divc(c.n_m1 * u * c.F, c.RT));
         const double inaca = c.inaca_pref * (1. / (1 + c.ksat * e_nm1)) *
-                             (exp(c.n_ * u * c.F / c.RT) * nai * nai * nai * c.cao -
+                             (exp(divc(c.n_ * u * c.F, c.RT)) * nai * nai * nai * c.cao -
                               e_nm1 * c.nao * c.nao * c.nao * cai * 2.5);
         // calc_inak :568-604
-        const double rec_iNaK = (1. / (1. + 0.1245 * exp(-0.1 * u * c.F / c.RT) +
-                                       0.0353 * exp(-u * c.F / c.RT)));
+        const double rec_iNaK = (1. / (1. + 0.1245 * exp(divc(-0.1 * u * c.F, c.RT)) +
+                                       0.0353 * exp(divc(-u * c.F, c.RT))));
         const double inak = c.knak_pref * (nai / (nai + c.KmNa)) * rec_iNaK;
         // calc_ipca :607-627, calc_ipk :630-653, calc_ibna :656-675, calc_ibca :678-697
         const double ipca = c.gpca * cai / (c.KpCa + cai);
-        const double rec_ipK = 1. / (1. + exp((25 - u) / 5.98));
+        const double rec_ipK = 1. / (1. + exp(FWB_DIVK(25 - u, 5.98)));
         const double ipk = c.gpk * rec_ipK * (u - Ek);
         const double ibna = c.gbna * (u - Ena);
         const double ibca = c.gbca * (u - Eca);
 
-        // calc_irel :700-730
-        double rr = s[17], oo, irel;
+        // calc_nai :928-953, calc_ki :956-984 (old nai, Ki)
         {
+            const double dNai = -(ina + ibna + 3 * inak + 3 * inaca) * c.inverseVcF * c.CAPACITANCE;
+            io.st(3, nai + dt * dNai);
+            const double dKi = -(ik1 + ito + ikr + iks - 2 * inak + ipk) * c.inverseVcF * c.CAPACITANCE;
+            io.st(4, Ki + dt * dKi);
+        }
+        un -= dt * (ikr + iks + ik1 + ito + ina + ibna + ical + ibca + inak + inaca + ipca + ipk);
+
+        // calc_irel :700-730
+        const double casr = io.ld(1);
+        double irel;
+        {
+            double rr = io.ld(17);
             const double kCaSR = c.maxsr - (c.maxsr_m_minsr / (1 + (c.EC / casr) * (c.EC / casr)));
             const double k1 = c.k1_ / kCaSR;
             const double k2 = c.k2_ * kCaSR;
             const double drr = c.k4 * (1 - rr) - k2 * cass * rr;
             rr += dt * drr;
-            oo = k1 * cass * cass * rr / (c.k3 + k1 * cass * cass);
+            const double oo = k1 * cass * cass * rr / (c.k3 + k1 * cass * cass);
             irel = c.Vrel * oo * (casr - cass);
+            io.st(17, rr); io.st(18, oo);
         }
-        s[17] = rr; s[18] = oo;
         // calc_ileak :733-752, calc_iup :755-774, calc_ixfer :777-796
         const double ileak = c.Vleak * (casr - cai);
         const double iup = c.Vmaxup / (1. + (c.Kup2 / (cai * cai)));
@@ -435,7 +508,7 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double dCaSR = dt * (iup - irel - ileak);
             const double bjsr = c.Bufsr - CaCSQN - dCaSR - casr + c.Kbufsr;
             const double cjsr = c.Kbufsr * (CaCSQN + dCaSR + casr);
-            s[1] = (sqrt(bjsr * bjsr + 4 * cjsr) - bjsr) / 2;
+            io.st(1, (sqrt(bjsr * bjsr + 4 * cjsr) - bjsr) * 0.5);   // == / 2
         }
         // calc_cass :831-872
         {
@@ -444,17 +517,9 @@ template <> struct Model<FWB_MODEL_TP06> {
                                        (-ical * c.inversevssF2 * c.CAPACITANCE));
             const double bcss = c.Bufss - CaSSBuf - dCaSS - cass + c.Kbufss;
             const double ccss = c.Kbufss * (CaSSBuf + dCaSS + cass);
-            s[2] = (sqrt(bcss * bcss + 4 * ccss) - bcss) / 2;
+            io.st(2, (sqrt(bcss * bcss + 4 * ccss) - bcss) * 0.5);   // == / 2
         }
         // calc_cai :875-925 is dead: cai keeps its old value (:1098)
-        // calc_nai :928-953, calc_ki :956-984
-        {
-            const double dNai = -(ina + ibna + 3 * inak + 3 * inaca) * c.inverseVcF * c.CAPACITANCE;
-            s[3] = nai + dt * dNai;
-            const double dKi = -(ik1 + ito + ikr + iks - 2 * inak + ipk) * c.inverseVcF * c.CAPACITANCE;
-            s[4] = Ki + dt * dKi;
-        }
-        un -= dt * (ikr + iks + ik1 + ito + ina + ibna + ical + ibca + inak + inaca + ipca + ipk);
     }
 };
 

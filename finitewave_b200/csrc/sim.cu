@@ -84,6 +84,7 @@ struct Tracker {
     // ecg / point output
     double *out;
     int64_t capacity;
+    bool primed;     // act: the full-grid first sample has been taken
 };
 
 }  // namespace fwb
@@ -111,6 +112,14 @@ struct FwbSim {
     double *ecg_partial;
     int64_t ecg_partial_cap;
     int64_t launches;
+    // slab halo
+    bool halo_on;
+    unsigned epoch;
+    uint32_t *flags;                 // local flag block
+    double *peer_u[2][2];            // [side][buffer]
+    int64_t peer_slices[2];
+    uint32_t *peer_flags[2];
+    unsigned n_side_blocks[2];
 };
 
 extern "C" const char *fwb_last_error(void) { return g_err; }
@@ -146,11 +155,12 @@ extern "C" int fwb_stencil_k(int dim, int stencil)
 extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int model, int stencil,
                               const uint8_t *tissue, const uint32_t *chunk_bits,
                               const uint32_t *chunk_base, int64_t n_myo, int64_t ld,
+                              const int32_t *worklist, int64_t n_work,
                               double *u, double *u_new, const double *weights, double *state,
                               const double *params, int n_params, double dt, fwb_stream_t stream)
 {
     if (!out || !shape || (dim != 2 && dim != 3) || !chunk_bits || !chunk_base || !u || !u_new ||
-        !weights || !tissue) {
+        !weights || !tissue || !worklist || n_work < 0 || n_work % WARPS_PER_BLOCK != 0) {
         set_error("fwb_sim_create: bad argument");
         return FWB_E_ARG;
     }
@@ -169,14 +179,24 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
     s->dim = dim; s->model = model; s->stencil = stencil;
     for (int d = 0; d < 3; ++d) s->shape[d] = d < dim ? shape[d] : 1;
     s->g = make_grid(dim, shape, chunk_bits, chunk_base, ld);
+    s->g.worklist = worklist; s->g.n_work = n_work;
     s->entry = e; s->tissue = tissue; s->n_myo = n_myo;
     s->buf[0] = u; s->buf[1] = u_new; s->cur = 0;
     s->weights = weights; s->state = state;
     s->dt = dt; s->t = 0.0; s->step = 0;
     s->stream = (cudaStream_t)stream;
     memset(s->consts, 0, sizeof(s->consts));
-    e->derive(params, dt, s->consts);
+    if (!e->derive(params, dt, s->consts)) {
+        delete s;
+        set_error("fwb_sim_create: model %d has a zero or non-finite divisor parameter", model);
+        return FWB_E_ARG;
+    }
     s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0;
+    s->halo_on = false; s->epoch = 0; s->flags = nullptr;
+    memset(s->peer_u, 0, sizeof(s->peer_u));
+    memset(s->peer_flags, 0, sizeof(s->peer_flags));
+    s->peer_slices[0] = s->peer_slices[1] = 0;
+    s->n_side_blocks[0] = s->n_side_blocks[1] = 0;
     *out = s;
     return 0;
 }
@@ -213,7 +233,47 @@ extern "C" int fwb_sim_set_params(FwbSim *s, const double *params, int n_params,
 {
     if (!s || n_params != s->entry->n_params) { set_error("fwb_sim_set_params: bad argument"); return FWB_E_ARG; }
     s->dt = dt;
-    s->entry->derive(params, dt, s->consts);
+    if (!s->entry->derive(params, dt, s->consts)) {
+        set_error("fwb_sim_set_params: zero or non-finite divisor parameter");
+        return FWB_E_ARG;
+    }
+    return 0;
+}
+
+extern "C" int fwb_sim_set_slow_offset(FwbSim *s, int64_t offset)
+{
+    if (!s) return FWB_E_ARG;
+    s->g.slow_offset = offset;
+    return 0;
+}
+
+extern "C" int fwb_sim_set_halo(FwbSim *s, uint32_t *local_flags,
+                                double *peer_lo_u0, double *peer_lo_u1, int64_t peer_lo_slices,
+                                uint32_t *peer_lo_flags, int64_t n_lo_blocks,
+                                double *peer_hi_u0, double *peer_hi_u1, int64_t peer_hi_slices,
+                                uint32_t *peer_hi_flags, int64_t n_hi_blocks)
+{
+    if (!s || !local_flags) { set_error("fwb_sim_set_halo: bad argument"); return FWB_E_ARG; }
+    const bool lo = peer_lo_u0 != nullptr, hi = peer_hi_u0 != nullptr;
+    if ((lo && (!peer_lo_u1 || !peer_lo_flags || peer_lo_slices < 3 || n_lo_blocks < 0)) ||
+        (hi && (!peer_hi_u1 || !peer_hi_flags || peer_hi_slices < 3 || n_hi_blocks < 0))) {
+        set_error("fwb_sim_set_halo: incomplete neighbour description");
+        return FWB_E_ARG;
+    }
+    if (slow_stride(s->g) % 32 != 0 || slow_extent(s->g) < 4) {
+        set_error("fwb_sim_set_halo: slab slices must be a multiple of 32 nodes, >= 4 slices");
+        return FWB_E_UNSUPPORTED;
+    }
+    s->halo_on = lo || hi;
+    s->flags = local_flags;
+    s->peer_u[0][0] = peer_lo_u0; s->peer_u[0][1] = peer_lo_u1;
+    s->peer_u[1][0] = peer_hi_u0; s->peer_u[1][1] = peer_hi_u1;
+    s->peer_slices[0] = peer_lo_slices; s->peer_slices[1] = peer_hi_slices;
+    s->peer_flags[0] = lo ? peer_lo_flags : nullptr;
+    s->peer_flags[1] = hi ? peer_hi_flags : nullptr;
+    s->n_side_blocks[0] = lo ? (unsigned)n_lo_blocks : 0;
+    s->n_side_blocks[1] = hi ? (unsigned)n_hi_blocks : 0;
+    s->epoch = 0;
     return 0;
 }
 
@@ -317,7 +377,7 @@ extern "C" int fwb_sim_add_tracker_ecg(FwbSim *s, const double *coords, int n_le
     Tracker tr{};
     tr.kind = TR_ECG; tr.start = start_time; tr.end = end_time; tr.every = every;
     tr.coords = coords; tr.n_leads = n_leads; tr.dr = dr; tr.out = out; tr.capacity = capacity;
-    const int64_t need = s->g.n_blocks * n_leads;
+    const int64_t need = step_blocks(s->g) * n_leads;
     if (need > s->ecg_partial_cap) {
         if (s->ecg_partial) cudaFree(s->ecg_partial);
         FWB_CUDA(cudaMalloc((void **)&s->ecg_partial, sizeof(double) * need));
@@ -364,8 +424,19 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         const double t = s->t;
 
         // 1. stimuli (StimSequence.stimulate_next)
+        bool halo_waited = false;
         for (Stim &sm : s->stims) {
             if (t >= sm.t && !sm.passed) {
+                if (s->halo_on && !halo_waited) {
+                    // the neighbours' stores of the previous step into our ghost slices
+                    // must have landed before a stimulus edits those slices
+                    int rcw = launch_halo_wait(s->peer_flags[0] ? s->flags + 0 : nullptr,
+                                               s->peer_flags[1] ? s->flags + 1 : nullptr,
+                                               s->epoch, st);
+                    if (rcw) return rcw;
+                    s->launches++;
+                    halo_waited = true;
+                }
                 double value = sm.value;
                 int mode = sm.mode;
                 if (mode == FWB_STIM_VOLTAGE_LIST) {
@@ -392,12 +463,34 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         memset(&k, 0, sizeof(k));
         k.g = s->g; k.u = u; k.u_new = u_new; k.w = s->weights; k.state = s->state;
         k.t = t;
+        if (s->halo_on) {
+            Halo &h = k.halo;
+            h.on = 1; h.slice = slow_stride(s->g); h.epoch = s->epoch;
+            const int64_t S = slow_extent(s->g);
+            const int nxt = s->cur ^ 1;
+            unsigned first = 0;
+            if (s->peer_flags[0]) {
+                h.lo.on = 1; h.lo.first = h.slice;
+                h.lo.peer_dst = s->peer_u[0][nxt] + (s->peer_slices[0] - 1) * h.slice;
+                h.lo.peer_flag = s->peer_flags[0] + 1;      // we are its hi neighbour
+                h.lo.flag = s->flags + 0; h.lo.counter = s->flags + 2;
+                h.lo.n_blocks = s->n_side_blocks[0]; h.lo.first_block = first;
+                first += h.lo.n_blocks;
+            }
+            if (s->peer_flags[1]) {
+                h.hi.on = 1; h.hi.first = (S - 2) * h.slice;
+                h.hi.peer_dst = s->peer_u[1][nxt];
+                h.hi.peer_flag = s->peer_flags[1] + 0;      // we are its lo neighbour
+                h.hi.flag = s->flags + 1; h.hi.counter = s->flags + 3;
+                h.hi.n_blocks = s->n_side_blocks[1]; h.hi.first_block = first;
+            }
+        }
         bool track = false;
         Tracker *ecg = nullptr;
         bool act_fused = false;
         for (Tracker &tr : s->trackers) {
             if (!gate(tr, t, s->step)) continue;
-            if (tr.kind == TR_ACT && !act_fused) {
+            if (tr.kind == TR_ACT && !act_fused && tr.primed) {
                 k.act_t = tr.act_t; k.act_thr = tr.thr; k.do_act = 1;
                 act_fused = true; track = true; tr.samples++;
             } else if (tr.kind == TR_ECG) {
@@ -411,20 +504,22 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         if (rc) return rc;
         s->launches++;
         if (ecg) {
-            rc = launch_ecg_finalize(s->ecg_partial, s->g.n_blocks, ecg->n_leads,
+            rc = launch_ecg_finalize(s->ecg_partial, step_blocks(s->g), ecg->n_leads,
                                      ecg->out + ecg->samples * ecg->n_leads, st);
             if (rc) return rc;
             s->launches++;
             ecg->samples++;
         }
-        bool first_act = true;
         for (Tracker &tr : s->trackers) {
             if (!gate(tr, t, s->step)) continue;
             if (tr.kind == TR_ACT) {
-                if (first_act) { first_act = false; continue; }   // fused above
+                if (act_fused && k.act_t == tr.act_t) continue;   // fused above
+                // first sample of a tracker (and any further tracker): the whole grid,
+                // including chunks without tissue that the work list skips -- their u
+                // never changes afterwards, so later samples only need listed chunks
                 rc = launch_act(tr.act_t, u, s->g.n_nodes, tr.thr, t, st);
                 if (rc) return rc;
-                s->launches++; tr.samples++;
+                s->launches++; tr.samples++; tr.primed = true;
             } else if (tr.kind == TR_POINT) {
                 if (tr.samples >= tr.capacity) { set_error("point tracker output buffer full"); return FWB_E_STATE; }
                 rc = launch_point_gather(tr.items, tr.fill, tr.n_items, u, s->state, s->g.ld,
@@ -438,16 +533,32 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         s->t += s->dt;
         s->step += 1;
         s->cur ^= 1;
+        if (s->halo_on) s->epoch += 1;
     }
+    return 0;
+}
+
+extern "C" int fwb_sim_halo_sync(FwbSim *s)
+{
+    if (!s) return FWB_E_ARG;
+    if (!s->halo_on) return 0;
+    // hold the stream until the neighbours' stores of the last step into our ghost
+    // slices have landed (needed before the host reads or edits u)
+    int rc = launch_halo_wait(s->peer_flags[0] ? s->flags + 0 : nullptr,
+                              s->peer_flags[1] ? s->flags + 1 : nullptr, s->epoch, s->stream);
+    if (rc) return rc;
+    s->launches++;
     return 0;
 }
 
 extern "C" int fwb_diffuse(int dim, int stencil, const int64_t *shape,
                            const uint32_t *chunk_bits, const uint32_t *chunk_base, int64_t ld,
+                           const int32_t *worklist, int64_t n_work,
                            const double *u, double *u_new, const double *weights,
                            fwb_stream_t stream)
 {
-    if (!shape || !chunk_bits || !chunk_base || !u || !u_new || !weights ||
+    if (!shape || !chunk_bits || !chunk_base || !u || !u_new || !weights || !worklist ||
+        n_work < 0 || n_work % WARPS_PER_BLOCK != 0 ||
         fwb_stencil_k(dim, stencil) < 0) {
         set_error("fwb_diffuse: bad argument");
         return FWB_E_ARG;
@@ -455,6 +566,7 @@ extern "C" int fwb_diffuse(int dim, int stencil, const int64_t *shape,
     StepCommon k;
     memset(&k, 0, sizeof(k));
     k.g = make_grid(dim, shape, chunk_bits, chunk_base, ld);
+    k.g.worklist = worklist; k.g.n_work = n_work;
     k.u = u; k.u_new = u_new; k.w = weights; k.state = nullptr;
     NoModel::Consts c{0.0};
     return model_entry(FWB_N_MODELS)->launch(dim, stencil, false, k, &c, (cudaStream_t)stream);

@@ -8,18 +8,45 @@
 // for every node the solver updates.  u is read-only, u_new and the state are
 // written only by the thread that owns the node, so the kernel is race free.
 //
-// Thread mapping: warp = 32 consecutive flat nodes (one "chunk"), lane = node.
-// A node's weights and state live at its COMPACT index (rank among updated
-// nodes = position in the reference's myo_indexes), so warps read contiguous,
-// fully used lines even on 30 %-fibrotic or shell-shaped tissues, and chunks
-// without tissue cost one 4-byte load.  Neighbour values of u come from
-// global memory through L1 (read-only path); the block's tile shape (see
-// Grid) makes the neighbour lines L1 hits.
+// Thread mapping: warp = 32 consecutive flat nodes (one "chunk", taken from the
+// work list), lane = node.  A node's weights and state live at its COMPACT
+// index (rank among updated nodes = position in the reference's myo_indexes),
+// so warps read contiguous, fully used lines even on 30 %-fibrotic or
+// shell-shaped tissues.  Neighbour values of u come from global memory through
+// L1 (read-only path); the work list's tile order makes the neighbour lines L1
+// hits.  State values are loaded where the model needs them and stored as soon
+// as they are final, which keeps the 19-state TP06 kernel at 2 blocks per SM.
+//
+// Slab runs (one process per GPU, slabs along the slowest axis): the blocks that
+// own the two slab-boundary slices come first in the work list.  They wait for
+// the neighbour's "previous step done" flag, compute, store u_new both locally
+// and straight into the neighbour's ghost slice through a peer-mapped pointer
+// (NVLink), and the last of them to finish raises the neighbour's flag for the
+// next step.  Interior blocks never wait: the exchange overlaps the interior.
 #pragma once
 #include "fwb_common.cuh"
 #include "models.cuh"
 
 namespace fwb {
+
+// one side (lo = towards slice 0, hi = towards the last slice) of a slab halo
+struct HaloSide {
+    int on;
+    int64_t first;            // first flat node of the owned boundary slice
+    double *peer_dst;         // neighbour's ghost slice inside ITS u_new buffer (peer pointer)
+    unsigned *peer_flag;      // neighbour's flag that this side raises (peer pointer)
+    const unsigned *flag;     // local flag the neighbour raises
+    unsigned *counter;        // local count of finished boundary blocks
+    unsigned n_blocks;        // boundary blocks of this side
+    unsigned first_block;     // first block index of this side in the work list
+};
+
+struct Halo {
+    int on;
+    int64_t slice;            // nodes per slice
+    unsigned epoch;           // this step's number; flags must be >= epoch to start
+    HaloSide lo, hi;
+};
 
 struct StepCommon {
     Grid g;
@@ -37,15 +64,16 @@ struct StepCommon {
     const double *ecg_coords;   // (n_leads, 3)
     double dr;
     double *ecg_partial;        // [n_blocks][n_leads]
+    Halo halo;
 };
 
 // "no model": diffusion only (fwb_diffuse, ECG re-application)
 struct NoModel {
-    static constexpr int NS = 0, NP = 0;
+    static constexpr int NS = 0, NP = 0, MIN_BLOCKS = 4;
     static constexpr uint32_t READ_MASK = 0, WRITE_MASK = 0;
     struct Consts { double dt; };
-    static void derive(const double *, double dt, Consts &c) { c.dt = dt; }
-    FWB_HD static void ionic(double, double &, double *, const Consts &) {}
+    static bool derive(const double *, double dt, Consts &c) { c.dt = dt; return true; }
+    template <class IO> FWB_HD static void ionic(double, double &, IO &, const Consts &) {}
 };
 
 template <class M> struct StepArgs {
@@ -102,8 +130,27 @@ template <> struct Stencil<3, FWB_STENCIL_ANISO> {
 
 #ifdef __CUDACC__
 
-template <class M, int DIM, int ST, bool TRACK>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+// state accessor of one node: slot q lives at state[q * ld + c]
+struct StateIO {
+    double *base;
+    int64_t stride;
+    __device__ __forceinline__ double ld(int q) const { return ld_stream(base + (int64_t)q * stride); }
+    __device__ __forceinline__ void st(int q, double v) const { st_stream(base + (int64_t)q * stride, v); }
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO>
+__global__ void __launch_bounds__(BLOCK_THREADS, M::MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs<M> A)
 {
     using S = Stencil<DIM, ST>;
@@ -111,11 +158,28 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     const StepCommon &P = A.k;
     const Grid &g = P.g;
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
 
-    const int64_t chunk = warp_chunk(g);
+    // which slab boundary (if any) this block belongs to
+    const HaloSide *side = nullptr;
+    if (HALO) {
+        const unsigned b = blockIdx.x;
+        if (P.halo.lo.on && b - P.halo.lo.first_block < P.halo.lo.n_blocks) side = &P.halo.lo;
+        else if (P.halo.hi.on && b - P.halo.hi.first_block < P.halo.hi.n_blocks) side = &P.halo.hi;
+        if (side) {
+            // the neighbour has finished the previous step on this interface: its
+            // stores into our ghost slice have landed and it no longer reads the
+            // ghost slice (in its other buffer) that we are about to overwrite
+            if (threadIdx.x == 0)
+                while (ld_acquire_sys(side->flag) < P.halo.epoch) __nanosleep(64);
+            __syncthreads();
+        }
+    }
+
+    const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int64_t chunk = slot < g.n_work ? (int64_t)__ldg(g.worklist + slot) : -1;
     uint32_t bits = 0;
     if (chunk >= 0) bits = __ldg(g.chunk_bits + chunk);
-    if (!TRACK && bits == 0) return;
 
     const int64_t n = chunk * 32 + lane;
     const bool myo = (bits >> lane) & 1u;
@@ -124,34 +188,31 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     if (TRACK && P.do_act && chunk >= 0 && n < g.n_nodes) {
         // ActivationTime{2,3}DTracker._track: every grid node, strict >
         const double a = P.act_t[n];
-        const double uu = __ldg(P.u + n);
+        const double uu = P.u[n];
         if (a < 0 && uu > P.act_thr) P.act_t[n] = P.t;
     }
 
     if (myo) {
         const int64_t c = (int64_t)__ldg(g.chunk_base + chunk) +
                           __popc(bits & ((1u << lane) - 1u));
-        const double *__restrict__ u = P.u;
+        const double *__restrict__ u = P.u + n;
         const double *__restrict__ w = P.w + c;
         const int64_t ld = g.ld;
 
-        // issue every load of this node up front
+        // diffusion: issue the 2K loads, then the left-to-right sum in slot order
+        // (no FMA contraction: -fmad=false)
         double un[K], wn[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const Off o = S::at(k);
             const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
                                 (int64_t)o.r * g.s_row + o.l;
-            un[k] = __ldg(u + n + off);
-            wn[k] = ld_stream(w + (int64_t)k * ld);
+            // boundary blocks of a slab read ghost values a peer GPU wrote during the
+            // previous step: they must not come from the non-coherent path
+            un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
+            wn[k] = ld_stream(w);
+            w += ld;
         }
-        double s[M::NS > 0 ? M::NS : 1];
-        double *__restrict__ st = P.state + c;
-#pragma unroll
-        for (int q = 0; q < M::NS; ++q)
-            if (M::READ_MASK & (1u << q)) s[q] = ld_stream(st + (int64_t)q * ld);
-
-        // diffusion: left-to-right sum in slot order, no FMA contraction
         double acc = mul(un[0], wn[0]);
 #pragma unroll
         for (int k = 1; k < K; ++k) acc = add(acc, mul(un[k], wn[k]));
@@ -164,12 +225,26 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 
         if (TRACK) diff = acc - uc;
 
-        M::ionic(uc, acc, s, A.c);
+        StateIO io{P.state + c, ld};
+        M::ionic(uc, acc, io, A.c);
 
         P.u_new[n] = acc;
-#pragma unroll
-        for (int q = 0; q < M::NS; ++q)
-            if (M::WRITE_MASK & (1u << q)) st_stream(st + (int64_t)q * ld, s[q]);
+        if (HALO && side) side->peer_dst[n - side->first] = acc;
+    }
+
+    if (HALO && side) {
+        // publish: all of this block's peer stores are visible system-wide before the
+        // block is counted; the last block of the side raises the neighbour's flag
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(side->counter, 1u) + 1u;
+            if (done == side->n_blocks) {
+                *side->counter = 0;
+                __threadfence_system();
+                st_release_sys(side->peer_flag, P.halo.epoch + 1u);
+            }
+        }
     }
 
     if (TRACK && P.do_ecg) {
@@ -178,14 +253,14 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
         // Deterministic: warp tree -> fixed-order sum over warps -> per-block
         // partial; ecg_finalize sums the partials in a fixed order.
         __shared__ double red[WARPS_PER_BLOCK][32];
-        const int warp = threadIdx.x >> 5;
         double ci = 0, cj = 0, ck = 0;
         if (myo) {
             if (DIM == 3) {
                 const int64_t i = n / g.s_plane, rem = n % g.s_plane;
-                ci = (double)i; cj = (double)(rem / g.s_row); ck = (double)(rem % g.s_row);
+                ci = (double)(i + g.slow_offset);
+                cj = (double)(rem / g.s_row); ck = (double)(rem % g.s_row);
             } else {
-                ci = (double)(n / g.s_row); cj = (double)(n % g.s_row);
+                ci = (double)(n / g.s_row + g.slow_offset); cj = (double)(n % g.s_row);
             }
         }
         for (int l0 = 0; l0 < P.n_leads; l0 += 32) {
@@ -216,14 +291,17 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     }
 }
 
-template <class M, int DIM, int ST, bool TRACK>
+inline int64_t step_blocks(const Grid &g) { return (g.n_work + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO>
 static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
 {
     StepArgs<M> a;
     a.k = k;
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
-    if (k.g.n_blocks <= 0) return 0;
-    step_kernel<M, DIM, ST, TRACK><<<(unsigned)k.g.n_blocks, BLOCK_THREADS, 0, s>>>(a);
+    const int64_t blocks = step_blocks(k.g);
+    if (blocks <= 0) return 0;
+    step_kernel<M, DIM, ST, TRACK, HALO><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
     FWB_KERNEL_CHECK("step_kernel");
     return 0;
 }
@@ -232,10 +310,15 @@ template <class M>
 static int launch_model(int dim, int stencil, bool track, const StepCommon &k,
                         const void *consts, cudaStream_t s)
 {
-#define FWB_CASE(D, ST)                                                         \
-    if (dim == D && stencil == ST)                                              \
-        return track ? launch_one<M, D, ST, true>(k, consts, s)                 \
-                     : launch_one<M, D, ST, false>(k, consts, s);
+    const bool halo = k.halo.on != 0;
+#define FWB_CASE(D, ST)                                                              \
+    if (dim == D && stencil == ST) {                                                 \
+        if (halo)                                                                    \
+            return track ? launch_one<M, D, ST, true, true>(k, consts, s)            \
+                         : launch_one<M, D, ST, false, true>(k, consts, s);          \
+        return track ? launch_one<M, D, ST, true, false>(k, consts, s)               \
+                     : launch_one<M, D, ST, false, false>(k, consts, s);             \
+    }
     FWB_CASE(2, FWB_STENCIL_ISO)
     FWB_CASE(2, FWB_STENCIL_ANISO)
     FWB_CASE(3, FWB_STENCIL_ISO)
@@ -245,16 +328,16 @@ static int launch_model(int dim, int stencil, bool track, const StepCommon &k,
     return FWB_E_UNSUPPORTED;
 }
 
-template <class M> static void derive_model(const double *p, double dt, void *out)
+template <class M> static bool derive_model(const double *p, double dt, void *out)
 {
-    M::derive(p, dt, *reinterpret_cast<typename M::Consts *>(out));
+    return M::derive(p, dt, *reinterpret_cast<typename M::Consts *>(out));
 }
 #endif  // __CUDACC__
 
 // per-model entry points (one translation unit each)
 typedef int (*LaunchFn)(int dim, int stencil, bool track, const StepCommon &k,
                         const void *consts, cudaStream_t s);
-typedef void (*DeriveFn)(const double *p, double dt, void *consts_out);
+typedef bool (*DeriveFn)(const double *p, double dt, void *consts_out);
 struct ModelEntry {
     int n_state, n_params;
     uint32_t read_mask, write_mask;

@@ -15,6 +15,7 @@ tracker outputs).
 ``model`` is an un-run CardiacModel instance: it supplies the model id, parameter
 values, ``init_*`` constants, ``dt``, ``dr``, ``D_model`` and optionally ``stencil``.
 """
+import copy
 import ctypes
 
 import numpy as np
@@ -41,7 +42,10 @@ class _Shim:
 
 
 class DeviceSimulation:
-    def __init__(self, model, mesh, fibers=None, conductivity=1.0, device=None, stencil=None):
+    def __init__(self, model, mesh, fibers=None, conductivity=1.0, device=None, stencil=None,
+                 halo=(False, False), slow_offset=0, global_slices=None):
+        """halo / slow_offset / global_slices describe a slab of a larger tissue cut along
+        axis 0 (see slab.py): ``mesh`` then includes one ghost slice per neighbour."""
         self.model = model
         shape = tuple(int(s) for s in mesh.shape)
         if len(shape) != model._DIM:
@@ -51,7 +55,10 @@ class DeviceSimulation:
         self.state_names = list(model._STATE)
         self.engine = eng = Engine(shape, device)
         self._mesh = mesh
-        eng.set_tissue(mesh)
+        self.halo = (bool(halo[0]), bool(halo[1]))
+        self.slow_offset = int(slow_offset)
+        self.global_slices = int(global_slices) if global_slices is not None else shape[0]
+        eng.set_tissue(mesh, halo=self.halo)
         if stencil is None:
             stencil = model.stencil
         aniso = fibers is not None if stencil is None else isinstance(stencil, AsymmetricStencil2D)
@@ -61,12 +68,14 @@ class DeviceSimulation:
         D_ac = getattr(stencil, "D_ac", 1 / 9) if stencil is not None else 1 / 9
         eng.compute_weights(_lib.STENCIL_ANISO if aniso else _lib.STENCIL_ISO, conductivity,
                             fibers if aniso else None, D_al, D_ac, model.D_model, self.dt, self.dr)
-        eng.allocate(len(self.state_names), staging=False)
+        eng.allocate(len(self.state_names), staging=False, peer=any(self.halo))
         eng.ubuf[0].fill_(float(model.init_u))
         eng.ubuf[1].fill_(float(model.init_u) if model._INIT_U_NEW else 0.0)
         for slot, name in enumerate(self.state_names):
             eng.fill_state(slot, getattr(model, "init_" + name))
         eng.create_sim(_lib.MODEL_IDS[model._MODEL], model._param_vector(), self.dt)
+        if self.slow_offset:
+            _lib.check(eng.L.fwb_sim_set_slow_offset(eng.sim, self.slow_offset))
         self.t, self.step = 0.0, 0
         self.stims, self.trackers = [], []
         self._shim = _Shim(self)
@@ -86,7 +95,18 @@ class DeviceSimulation:
 
     # ---- stimuli / trackers (same classes as the host API) -----------------
     def add_stim(self, stim):
+        """Stimulus boxes are given in GLOBAL tissue indices; a slab registers the part
+        that falls into its stored slices (ghost slices included, so both neighbours
+        apply the identical edit to their copy of a shared slice)."""
         stim.initialize(self._shim)
+        if any(self.halo) or self.slow_offset:
+            if not hasattr(stim, "_box"):
+                raise NotImplementedError("slab runs take coordinate-box stimuli only")
+            stim = copy.copy(stim)
+            lo, hi, _ = slice(stim.x1, stim.x2).indices(self.global_slices)
+            lo, hi = lo - self.slow_offset, max(lo, hi) - self.slow_offset
+            stim.x1 = min(max(lo, 0), self.shape[0])
+            stim.x2 = min(max(hi, stim.x1), self.shape[0])
         sid = stim._register(self.engine, self._shim)
         self.stims.append((sid, stim))
         return stim
@@ -105,11 +125,40 @@ class DeviceSimulation:
         return tracker
 
     # ---- time loop -----------------------------------------------------------
-    def run(self, n_steps):
+    def run(self, n_steps, halo_sync=True):
         eng = self.engine
         eng.set_time(self.t, self.step)
         eng.run(int(n_steps))
+        if any(self.halo) and halo_sync:
+            _lib.check(eng.L.fwb_sim_halo_sync(eng.sim), "fwb_sim_halo_sync")
         self.t, self.step = eng.get_time()
+
+    # ---- slab wiring -----------------------------------------------------------
+    def halo_export(self):
+        """What a neighbour needs to reach this slab's buffers from another process."""
+        eng = self.engine
+        return dict(u0=eng.peer_mem[0].ipc_handle(), u1=eng.peer_mem[1].ipc_handle(),
+                    flags=eng.peer_flags.ipc_handle(), slices=self.shape[0])
+
+    def halo_pointers(self):
+        """Same, as raw device pointers (neighbour slab in the same process)."""
+        eng = self.engine
+        return dict(u0=eng.peer_mem[0].ptr, u1=eng.peer_mem[1].ptr, flags=eng.peer_flags.ptr,
+                    slices=self.shape[0])
+
+    def halo_connect(self, lo=None, hi=None):
+        """lo / hi: dict(u0, u1, flags, slices) with device pointers valid in this process."""
+        eng = self.engine
+        vp = ctypes.c_void_p
+
+        def side(d):
+            if d is None:
+                return vp(0), vp(0), 0, vp(0)
+            return vp(d["u0"]), vp(d["u1"]), int(d["slices"]), vp(d["flags"])
+        l, h = side(lo), side(hi)
+        n_lo, n_hi = eng.halo_blocks
+        _lib.check(eng.L.fwb_sim_set_halo(eng.sim, vp(eng.peer_flags.ptr), l[0], l[1], l[2], l[3],
+                                          n_lo, h[0], h[1], h[2], h[3], n_hi), "fwb_sim_set_halo")
 
     def synchronize(self):
         self.engine.synchronize()

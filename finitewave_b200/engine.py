@@ -34,6 +34,39 @@ def pinned_empty(shape, dtype=torch.float64):
     return torch.empty(tuple(int(s) for s in shape), dtype=dtype, pin_memory=True)
 
 
+class PeerMemory:
+    """cudaMalloc'ed, zero-filled device block from fwb_dev_alloc: exportable through
+    CUDA IPC (torch's caching allocator sub-allocates, which IPC handles cannot
+    address).  Exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, shape, dtype):
+        self.L = lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = ctypes.c_void_p(0)
+        check(self.L.fwb_dev_alloc(ctypes.byref(p), max(self.nbytes, 16)), "fwb_dev_alloc")
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": self.dtype.str,
+                                         "data": (self.ptr, False), "version": 2}
+
+    def tensor(self, device):
+        return torch.as_tensor(self, device=device)
+
+    def ipc_handle(self):
+        buf = ctypes.create_string_buffer(self.L.fwb_ipc_handle_size())
+        check(self.L.fwb_ipc_get_handle(ctypes.c_void_p(self.ptr), buf), "fwb_ipc_get_handle")
+        return bytes(buf.raw)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.L.fwb_dev_free(ctypes.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:
+            pass
+
+
 class Engine:
     """Device side of one CardiacModel instance."""
 
@@ -62,8 +95,10 @@ class Engine:
         self._keep = []          # tensors borrowed by the C side (stims, trackers)
 
     # ---- tissue ---------------------------------------------------------
-    def set_tissue(self, mesh, special_boundaries=None):
-        """mesh: host ndarray or device tensor with values 0/1/2."""
+    def set_tissue(self, mesh, special_boundaries=None, halo=(False, False)):
+        """mesh: host ndarray or device tensor with values 0/1/2.  halo = (lo, hi): the
+        first / last slice of the slowest axis is a ghost slice owned by a neighbour
+        rank (its tissue feeds weights and stimuli, its nodes are never updated here)."""
         dev = self.device
         if isinstance(mesh, torch.Tensor):
             m = mesh.to(dev)
@@ -72,9 +107,18 @@ class Engine:
         tissue = (m == 1)
         # the solver never updates the outer ring (CardiacTissue.add_boundaries)
         interior = torch.zeros(self.shape, dtype=torch.bool, device=dev)
-        interior[tuple(slice(1, -1) for _ in self.shape)] = True
+        inner = [slice(1, -1) for _ in self.shape]
+        # a ghost slice is real tissue of the neighbour, not the empty outer ring
+        inner[0] = slice(0 if halo[0] else 1, None if halo[1] else -1)
+        interior[tuple(inner)] = True
         tissue = tissue & interior
         update = tissue
+        if halo[0] or halo[1]:
+            update = tissue.clone()
+            if halo[0]:
+                update[0] = False
+            if halo[1]:
+                update[-1] = False
         if special_boundaries is not None:
             sb = special_boundaries
             sb = sb.to(dev) if isinstance(sb, torch.Tensor) else torch.from_numpy(
@@ -90,6 +134,28 @@ class Engine:
               "fwb_build_chunks")
         self.n_myo = int(n_myo.value)
         self.ld = max(32, (self.n_myo + 31) // 32 * 32)
+        self._build_worklist(halo)
+
+    def _build_worklist(self, halo=(False, False)):
+        """Chunks with tissue in tile order (ghost slices of a slab left out)."""
+        active = self.tissue
+        if halo[0] or halo[1]:
+            active = self.tissue.clone()
+            if halo[0]:
+                active[0] = 0
+            if halo[1]:
+                active[-1] = 0
+        shp = shape_arr(self.shape)
+        cap = int(self.L.fwb_worklist_capacity(self.dim, shp))
+        self.worklist = torch.empty(cap, dtype=torch.int32, device=self.device)
+        n_work, n_lo, n_hi = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        check(self.L.fwb_build_worklist(self.dim, shp, _ptr(active), int(halo[0]), int(halo[1]),
+                                        _ptr(self.worklist), cap, ctypes.byref(n_work),
+                                        ctypes.byref(n_lo), ctypes.byref(n_hi), _stream()),
+              "fwb_build_worklist")
+        self.n_work = int(n_work.value)
+        self.halo_blocks = (int(n_lo.value), int(n_hi.value))
+        self.worklist = self.worklist[:max(self.n_work, 8)].clone()
 
     # ---- weights --------------------------------------------------------
     def compute_weights(self, stencil, conductivity, fibers, D_al, D_ac, D_model, dt, dr):
@@ -147,10 +213,16 @@ class Engine:
         return out.cpu().numpy()
 
     # ---- buffers --------------------------------------------------------
-    def allocate(self, n_state, staging=True):
+    def allocate(self, n_state, staging=True, peer=False):
         dev = self.device
         self.n_state = n_state
-        self.ubuf = [torch.empty(self.shape, dtype=torch.float64, device=dev) for _ in range(2)]
+        if peer:
+            # slab runs: neighbours store into these buffers through CUDA IPC mappings
+            self.peer_mem = [PeerMemory(self.shape, np.float64) for _ in range(2)]
+            self.peer_flags = PeerMemory((4,), np.uint32)
+            self.ubuf = [m.tensor(dev) for m in self.peer_mem]
+        else:
+            self.ubuf = [torch.empty(self.shape, dtype=torch.float64, device=dev) for _ in range(2)]
         self.state = torch.zeros((max(n_state, 1), self.ld), dtype=torch.float64, device=dev)
         self.staging = None
         if staging:
@@ -193,6 +265,7 @@ class Engine:
         check(self.L.fwb_sim_create(
             ctypes.byref(sim), self.dim, shape_arr(self.shape), model_id, self.stencil,
             _ptr(self.tissue), _ptr(self.chunk_bits), _ptr(self.chunk_base), self.n_myo, self.ld,
+            _ptr(self.worklist), self.n_work,
             _ptr(self.ubuf[0]), _ptr(self.ubuf[1]), _ptr(self.weights), _ptr(self.state),
             p, len(params), float(dt), _stream()), "fwb_sim_create")
         self.sim = sim

@@ -41,6 +41,12 @@ def diffuse_host(dim, kind, u_new, u, w, indexes):
     check(L.fwb_build_chunks(_p(d_mask), n_nodes, _p(bits), _p(base), ctypes.byref(n_myo),
                              stream), "fwb_build_chunks")
     ld = max(32, (int(n_myo.value) + 31) // 32 * 32)
+    shp = shape_arr(shape)
+    cap = int(L.fwb_worklist_capacity(dim, shp))
+    worklist = torch.empty(cap, dtype=torch.int32, device=dev)
+    n_work = ctypes.c_int64(0)
+    check(L.fwb_build_worklist(dim, shp, _p(d_mask), 0, 0, _p(worklist), cap, ctypes.byref(n_work),
+                               None, None, stream), "fwb_build_worklist")
     w_host = np.ascontiguousarray(np.asarray(w), dtype=np.float64)
     K = w_host.shape[-1]
     if L.fwb_stencil_k(dim, kind) != K or w_host.shape[:-1] != shape:
@@ -51,7 +57,8 @@ def diffuse_host(dim, kind, u_new, u, w, indexes):
           "fwb_weights_pack")
     d_u = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(dev)
     d_un = torch.from_numpy(np.ascontiguousarray(u_new, dtype=np.float64)).to(dev)
-    check(L.fwb_diffuse(dim, kind, shape_arr(shape), _p(bits), _p(base), ld, _p(d_u), _p(d_un),
+    check(L.fwb_diffuse(dim, kind, shp, _p(bits), _p(base), ld, _p(worklist), int(n_work.value),
+                        _p(d_u), _p(d_un),
                         _p(d_ws), stream), "fwb_diffuse")
     u_new[...] = d_un.cpu().numpy()
     return u_new

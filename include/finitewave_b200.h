@@ -24,6 +24,9 @@
  *                          special_boundaries == 0) and the exclusive prefix
  *                          count of such nodes -> "compact index" of a node =
  *                          its position in the reference's myo_indexes array
+ *   worklist               int32 ids of the chunks that contain tissue, in the
+ *                          order the step kernel's blocks take them (8 per block,
+ *                          -1 = padding), see fwb_build_worklist
  *   weights                compact SoA: weights[k * ld + c], k = stencil slot
  *                          in the reference's slot order, c = compact index
  *   state                  compact SoA: state[s * ld + c], s in the model's
@@ -99,6 +102,21 @@ FWB_API int fwb_build_chunks(const uint8_t *update_mask, int64_t n_nodes,
                      uint32_t *chunk_bits, uint32_t *chunk_base,
                      int64_t *n_myo, fwb_stream_t stream);
 
+/* Work list of the step kernel: the chunks that contain at least one node of
+ * `active` (dense uint8; normally the tissue mask mesh == 1), in tile order (8
+ * consecutive entries = 2 planes x 4 rows (3D) or 8 rows (2D) of one 32-node column
+ * segment), every segment padded to whole blocks with -1.  With halo_lo / halo_hi
+ * the chunks of slice 1 / slice shape[0]-2 of the slowest axis (the slab's owned
+ * boundary slices) come first, ghost slices 0 / shape[0]-1 are left out, and the
+ * number of blocks of each boundary segment is returned.
+ *   worklist   [capacity] out, capacity >= fwb_worklist_capacity(dim, shape)
+ *   n_work     host out: entries used (multiple of 8)            (synchronises) */
+FWB_API int64_t fwb_worklist_capacity(int dim, const int64_t *shape);
+FWB_API int fwb_build_worklist(int dim, const int64_t *shape, const uint8_t *active,
+                       int halo_lo, int halo_hi, int32_t *worklist, int64_t capacity,
+                       int64_t *n_work, int64_t *n_lo_blocks, int64_t *n_hi_blocks,
+                       fwb_stream_t stream);
+
 /* dense (*shape) <-> compact [ld] conversions of one array.
  * gather:  compact[c] = dense[n]            for update nodes
  * scatter: dense[n] = update ? compact[c] : fill   (all n < n_nodes)        */
@@ -155,6 +173,7 @@ FWB_API int fwb_sim_create(FwbSim **sim, int dim, const int64_t *shape, int mode
                    const uint8_t *tissue,              /* dense uint8, mesh == 1 (stimulus target) */
                    const uint32_t *chunk_bits, const uint32_t *chunk_base,
                    int64_t n_myo, int64_t ld,
+                   const int32_t *worklist, int64_t n_work,
                    double *u, double *u_new,           /* dense; swapped every step */
                    const double *weights,              /* compact SoA [K][ld] */
                    double *state,                      /* compact SoA [S][ld] */
@@ -215,11 +234,53 @@ FWB_API int fwb_sim_run(FwbSim *sim, int64_t n_steps);
 FWB_API int64_t fwb_sim_launch_count(const FwbSim *sim);
 
 /* ------------------------------------------------------------------------
+ * Slab decomposition across GPUs (one process per GPU; no reference counterpart:
+ * the reference is single-process).
+ * The tissue is cut along the slowest axis; each rank stores its owned slices
+ * plus one ghost slice per neighbour (local slice 0 / shape[0]-1).  Per step the
+ * blocks of the owned boundary slices store u_new both locally and directly into
+ * the neighbour's ghost slice through a peer-mapped pointer (CUDA IPC over
+ * NVLink) and raise a flag in the neighbour's memory; the neighbour's boundary
+ * blocks of the next step wait for that flag.  No host involvement, no collective.
+ *
+ * fwb_dev_alloc     cudaMalloc'ed (IPC-exportable), zero-filled device memory
+ * fwb_ipc_*         cudaIpcMemHandle plumbing (handle = fwb_ipc_handle_size() bytes)
+ * fwb_sim_set_halo  for each side (0 = lo, 1 = hi; NULL peer_u0 = no neighbour):
+ *     peer_u0/peer_u1   the neighbour's two u buffers in ITS creation order
+ *     peer_slices       the neighbour's local shape[0] (its ghost slice towards us
+ *                       is 0 for our hi side, peer_slices-1 for our lo side)
+ *     peer_flags        the neighbour's flag block (4 uint32: [0] raised by its lo
+ *                       neighbour, [1] by its hi neighbour, [2],[3] its counters)
+ *     local_flags       this rank's flag block (same layout, fwb_dev_alloc(16))
+ *     n_lo_blocks/n_hi_blocks from fwb_build_worklist
+ *   All ranks must then call fwb_sim_run with the same n_steps, followed by
+ *   fwb_sim_halo_sync before the host looks at u.
+ * fwb_sim_set_slow_offset  global index of local slice 0 (ECG lead distances)
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_dev_alloc(void **ptr, int64_t bytes);
+FWB_API int fwb_dev_free(void *ptr);
+FWB_API int fwb_ipc_handle_size(void);
+FWB_API int fwb_ipc_get_handle(const void *ptr, void *handle_out);
+FWB_API int fwb_ipc_open_handle(const void *handle, void **ptr_out);
+FWB_API int fwb_ipc_close_handle(void *ptr);
+FWB_API int fwb_sim_set_halo(FwbSim *sim, uint32_t *local_flags,
+                     double *peer_lo_u0, double *peer_lo_u1, int64_t peer_lo_slices,
+                     uint32_t *peer_lo_flags, int64_t n_lo_blocks,
+                     double *peer_hi_u0, double *peer_hi_u1, int64_t peer_hi_slices,
+                     uint32_t *peer_hi_flags, int64_t n_hi_blocks);
+FWB_API int fwb_sim_set_slow_offset(FwbSim *sim, int64_t offset);
+/* enqueue a wait for the neighbours' last ghost-slice stores (call after
+ * fwb_sim_run, before the host reads u; every rank must have issued the same
+ * number of steps or the wait never ends) */
+FWB_API int fwb_sim_halo_sync(FwbSim *sim);
+
+/* ------------------------------------------------------------------------
  * Single unfused pieces (used for ECG-style re-application and tests).
  * fwb_diffuse replaces diffusion_kernel_{2d,3d}_{iso,aniso}(u_new, u, w, idx).
  * ---------------------------------------------------------------------- */
 FWB_API int fwb_diffuse(int dim, int stencil, const int64_t *shape,
                 const uint32_t *chunk_bits, const uint32_t *chunk_base, int64_t ld,
+                const int32_t *worklist, int64_t n_work,
                 const double *u, double *u_new, const double *weights,
                 fwb_stream_t stream);
 

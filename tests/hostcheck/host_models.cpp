@@ -18,15 +18,19 @@ static void run(double *u_new, const double *u, double *const *st, int64_t n, do
 {
     using M = Model<MODEL>;
     typename M::Consts c;
-    M::derive(p, dt, c);
+    if (!M::derive(p, dt, c)) return;
+    // state accessor that also enforces the declared read / write masks
+    struct IO {
+        double *const *arr;
+        int64_t i;
+        double ld(int q) const { return (M::READ_MASK >> q) & 1 ? arr[q][i] : -12345.0; }
+        void st(int q, double v) const { arr[q][i] = (M::WRITE_MASK >> q) & 1 ? v : -54321.0; }
+    };
     for (int64_t i = 0; i < n; ++i) {
-        double s[M::NS];
-        for (int q = 0; q < M::NS; ++q) s[q] = (M::READ_MASK >> q) & 1 ? st[q][i] : -12345.0;
+        IO io{st, i};
         double un = u_new[i];
-        M::ionic(u[i], un, s, c);
+        M::ionic(u[i], un, io, c);
         u_new[i] = un;
-        for (int q = 0; q < M::NS; ++q)
-            if ((M::WRITE_MASK >> q) & 1) st[q][i] = s[q];
     }
 }
 

@@ -68,11 +68,15 @@ def test_argument_errors_do_not_touch_the_device(L):
     null = ctypes.c_void_p(0)
     shape = (ctypes.c_int64 * 2)(8, 8)
     sim = ctypes.c_void_p(0)
-    rc = L.fwb_sim_create(ctypes.byref(sim), 2, shape, 0, 0, null, null, null, 0, 32, null, null,
-                          null, null, None, 0, 0.01, null)
+    rc = L.fwb_sim_create(ctypes.byref(sim), 2, shape, 0, 0, null, null, null, 0, 32, null, 0,
+                          null, null, null, null, None, 0, 0.01, null)
     assert rc < 0 and b"bad argument" in L.fwb_last_error()
     assert L.fwb_sim_run(null, 1) < 0
-    assert L.fwb_diffuse(2, 7, shape, null, null, 32, null, null, null, null) < 0
+    assert L.fwb_diffuse(2, 7, shape, null, null, 32, null, 0, null, null, null, null) < 0
+    assert L.fwb_build_worklist(2, shape, null, 0, 0, null, 0, None, None, None, null) < 0
+    assert L.fwb_worklist_capacity(2, shape) >= 2
+    assert L.fwb_sim_set_halo(null, null, null, null, 0, null, 0, null, null, 0, null, 0) < 0
+    assert L.fwb_ipc_handle_size() == 64
     assert L.fwb_compute_weights(5, 0, shape, null, null, 1.0, null, 1, 1 / 9, 1, 0.01, 0.0625,
                                  null, null, 32, null, null) < 0
 

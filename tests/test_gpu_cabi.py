@@ -150,8 +150,8 @@ def test_unknown_model_or_missing_fibers_raise(env):
     sim = ctypes.c_void_p(0)
     shape = (ctypes.c_int64 * 2)(10, 10)
     one = ctypes.c_void_p(8)
-    rc = L.fwb_sim_create(ctypes.byref(sim), 2, shape, 17, 0, one, one, one, 0, 32, one, one, one,
-                          one, None, 0, 0.01, ctypes.c_void_p(0))
+    rc = L.fwb_sim_create(ctypes.byref(sim), 2, shape, 17, 0, one, one, one, 0, 32, one, 8, one,
+                          one, one, one, None, 0, 0.01, ctypes.c_void_p(0))
     assert rc == -1
     with pytest.raises(lib.FwbError):
         lib.check(rc, "fwb_sim_create")
