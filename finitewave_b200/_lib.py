@@ -39,6 +39,8 @@ def _sig(L):
     L.fwb_worklist_capacity.restype = c_int64
     L.fwb_build_worklist.argtypes = [c_int, POINTER(c_int64), p, c_int, c_int, p, c_int64,
                                      POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), p]
+    L.fwb_order_compact.argtypes = [p, c_int64, p, c_int64, p, p, p, POINTER(c_int64), p]
+    L.fwb_sim_set_tile_base.argtypes = [p, p, p]
     L.fwb_gather_compact.argtypes = [p, p, c_int64, p, p, p]
     L.fwb_scatter_compact.argtypes = [p, p, c_double, c_int64, p, p, p]
     L.fwb_weights_pack.argtypes = [p, p, c_int, c_int64, c_int64, p, p, p]

@@ -145,6 +145,30 @@ __global__ void worklist_scatter_kernel(int64_t n_pos, const int32_t *cand, cons
     if (flag[q]) out[base[q]] = cand[q];
 }
 
+// compact order = work-list order (tile-contiguous weights / state rows)
+__global__ void order_gather_kernel(const uint32_t *bits, const int32_t *wl, int64_t n_work,
+                                    uint32_t *tmp)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_work) return;
+    const int32_t c = wl[i];
+    tmp[i] = c >= 0 ? bits[c] : 0u;
+}
+__global__ void order_scatter_kernel(const int32_t *wl, int64_t n_work, const uint32_t *ord,
+                                     const uint32_t *tmp_bits, uint32_t total,
+                                     uint32_t *chunk_base, uint32_t *tile_base, uint4 *records)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_work) return;
+    if (i == n_work) { tile_base[n_work / 8] = total; return; }
+    const int32_t c = wl[i];
+    if (c >= 0) chunk_base[c] = ord[i];
+    if ((i & 7) == 0) tile_base[i >> 3] = ord[i];
+    // what the TMA kernel needs per work-list entry: chunk id, update bits, compact
+    // index of the chunk's first node, compact index of the tile's first node
+    if (records) records[i] = make_uint4((uint32_t)c, tmp_bits[i], ord[i], ord[i & ~(int64_t)7]);
+}
+
 // slab halo: hold the stream until both neighbours have finished step `epoch - 1`
 __global__ void halo_wait_kernel(const unsigned *flag_lo, const unsigned *flag_hi, unsigned epoch)
 {
@@ -464,6 +488,41 @@ extern "C" int fwb_build_worklist(int dim, const int64_t *shape, const uint8_t *
     if (n_lo_blocks) *n_lo_blocks = halo_lo ? blocks[bi] : 0;
     if (halo_lo) ++bi;
     if (n_hi_blocks) *n_hi_blocks = halo_hi ? blocks[bi] : 0;
+    return 0;
+}
+
+extern "C" int fwb_order_compact(const uint32_t *chunk_bits, int64_t n_chunks,
+                                 const int32_t *worklist, int64_t n_work, uint32_t *chunk_base,
+                                 uint32_t *tile_base, uint32_t *records, int64_t *n_myo,
+                                 fwb_stream_t stream)
+{
+    if (!chunk_bits || !worklist || !chunk_base || !tile_base || n_work < 0 || n_work % 8 != 0) {
+        set_error("fwb_order_compact: bad argument");
+        return FWB_E_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    FWB_CUDA(cudaMemsetAsync(chunk_base, 0, sizeof(uint32_t) * n_chunks, s));
+    unsigned long long total = 0;
+    if (n_work > 0) {
+        uint32_t *tmp = nullptr, *ord = nullptr;
+        FWB_CUDA(cudaMallocAsync((void **)&tmp, sizeof(uint32_t) * n_work, s));
+        FWB_CUDA(cudaMallocAsync((void **)&ord, sizeof(uint32_t) * n_work, s));
+        const unsigned nb = (unsigned)cdiv(n_work + 1, 256);
+        order_gather_kernel<<<nb, 256, 0, s>>>(chunk_bits, worklist, n_work, tmp);
+        FWB_KERNEL_CHECK("order_gather_kernel");
+        int rc = scan_popc(tmp, n_work, ord, &total, s);
+        if (rc) return rc;
+        order_scatter_kernel<<<nb, 256, 0, s>>>(worklist, n_work, ord, tmp, (uint32_t)total,
+                                                chunk_base, tile_base,
+                                                reinterpret_cast<uint4 *>(records));
+        FWB_KERNEL_CHECK("order_scatter_kernel");
+        FWB_CUDA(cudaFreeAsync(tmp, s));
+        FWB_CUDA(cudaFreeAsync(ord, s));
+    } else {
+        FWB_CUDA(cudaMemsetAsync(tile_base, 0, sizeof(uint32_t), s));
+    }
+    FWB_CUDA(cudaStreamSynchronize(s));
+    if (n_myo) *n_myo = (int64_t)total;
     return 0;
 }
 

@@ -71,6 +71,7 @@ template <int MODEL> struct Model;
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_ALIEV_PANFILOV> {
     static constexpr int NS = 1, NP = 5, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
     struct Consts { double dt, a, k, eap, mu_1, mu_2; };
     static bool derive(const double *p, double dt, Consts &c)
@@ -93,6 +94,7 @@ template <> struct Model<FWB_MODEL_ALIEV_PANFILOV> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_BARKLEY> {
     static constexpr int NS = 1, NP = 3, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
     struct Consts { double dt, b; DivC a, eap; };
     static bool derive(const double *p, double dt, Consts &c)
@@ -116,6 +118,7 @@ template <> struct Model<FWB_MODEL_BARKLEY> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_MITCHELL_SCHAEFFER> {
     static constexpr int NS = 1, NP = 5, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x1, WRITE_MASK = 0x1;
     struct Consts { double dt, u_gate; DivC tau_close, tau_open, tau_in, tau_out; };
     static bool derive(const double *p, double dt, Consts &c)
@@ -145,6 +148,7 @@ template <> struct Model<FWB_MODEL_MITCHELL_SCHAEFFER> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_FENTON_KARMA> {
     static constexpr int NS = 2, NP = 11, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x3, WRITE_MASK = 0x3;
     struct Consts {
         double dt, k, u_c, uc_si;
@@ -186,6 +190,7 @@ template <> struct Model<FWB_MODEL_FENTON_KARMA> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_LUO_RUDY91> {
     static constexpr int NS = 7, NP = 15, MIN_BLOCKS = 3;
+    static constexpr bool USE_TMA = false;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x7f, WRITE_MASK = 0x7f;
     struct Consts {
         double dt, gna, gsi, gkp, gb;
@@ -284,6 +289,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_TP06> {
     static constexpr int NS = 19, NP = 49, MIN_BLOCKS = 2;
+    static constexpr bool USE_TMA = false;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x3ffff;          // all but oo
     static constexpr uint32_t WRITE_MASK = 0x7ffff & ~0x1u;  // all but cai
     struct Consts {

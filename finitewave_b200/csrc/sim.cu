@@ -112,6 +112,8 @@ struct FwbSim {
     double *ecg_partial;
     int64_t ecg_partial_cap;
     int64_t launches;
+    const uint32_t *tile_base;
+    const uint32_t *records;
     // slab halo
     bool halo_on;
     unsigned epoch;
@@ -192,6 +194,7 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
         return FWB_E_ARG;
     }
     s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0;
+    s->tile_base = nullptr; s->records = nullptr;
     s->halo_on = false; s->epoch = 0; s->flags = nullptr;
     memset(s->peer_u, 0, sizeof(s->peer_u));
     memset(s->peer_flags, 0, sizeof(s->peer_flags));
@@ -237,6 +240,18 @@ extern "C" int fwb_sim_set_params(FwbSim *s, const double *params, int n_params,
         set_error("fwb_sim_set_params: zero or non-finite divisor parameter");
         return FWB_E_ARG;
     }
+    return 0;
+}
+
+extern "C" int fwb_sim_set_tile_base(FwbSim *s, const uint32_t *tile_base,
+                                     const uint32_t *records)
+{
+    if (!s || ((tile_base == nullptr) != (records == nullptr))) {
+        set_error("fwb_sim_set_tile_base: bad argument");
+        return FWB_E_ARG;
+    }
+    s->tile_base = tile_base;
+    s->records = records;
     return 0;
 }
 
@@ -463,6 +478,8 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         memset(&k, 0, sizeof(k));
         k.g = s->g; k.u = u; k.u_new = u_new; k.w = s->weights; k.state = s->state;
         k.t = t;
+        k.tile_base = s->tile_base;
+        k.records = reinterpret_cast<const uint4 *>(s->records);
         if (s->halo_on) {
             Halo &h = k.halo;
             h.on = 1; h.slice = slow_stride(s->g); h.epoch = s->epoch;

@@ -17,6 +17,17 @@
 // hits.  State values are loaded where the model needs them and stored as soon
 // as they are final, which keeps the 19-state TP06 kernel at 2 blocks per SM.
 //
+// Two kernels implement this step:
+//   step_kernel      one block per tile, every operand through LDG (all models;
+//                    the compute-bound LR91 / TP06 always use it)
+//   step_kernel_tma  persistent blocks (grid = resident blocks of the GPU) that walk
+//                    the tile list; the tile's weight rows and state rows -- the
+//                    HBM streams, contiguous in the tile-ordered compact layout --
+//                    are fetched by TMA bulk copies (cp.async.bulk -> UBLKCP) into a
+//                    2-4 stage shared-memory ring guarded by mbarriers, so tens of KB
+//                    per SM are in flight independent of register occupancy while
+//                    the warps compute the previous tile (light, HBM-bound models).
+//
 // Slab runs (one process per GPU, slabs along the slowest axis): the blocks that
 // own the two slab-boundary slices come first in the work list.  They wait for
 // the neighbour's "previous step done" flag, compute, store u_new both locally
@@ -65,11 +76,14 @@ struct StepCommon {
     double dr;
     double *ecg_partial;        // [n_blocks][n_leads]
     Halo halo;
+    const uint32_t *tile_base;  // [n_work/8 + 1] compact index of each tile's first node, or NULL
+    const uint4 *records;       // [n_work] {chunk, bits, chunk base, tile base} (TMA kernel)
 };
 
 // "no model": diffusion only (fwb_diffuse, ECG re-application)
 struct NoModel {
     static constexpr int NS = 0, NP = 0, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;
     static constexpr uint32_t READ_MASK = 0, WRITE_MASK = 0;
     struct Consts { double dt; };
     static bool derive(const double *, double dt, Consts &c) { c.dt = dt; return true; }
@@ -291,6 +305,227 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// step_kernel_tma: persistent, TMA-fed variant (see the header comment)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
+{
+    const uint32_t a = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (TMA, 1-D); bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int tma_popc(uint32_t m) { return m ? (int)(m & 1u) + tma_popc(m >> 1) : 0; }
+// position of state slot q among the staged (read) slots
+constexpr int tma_slot(uint32_t mask, int q) { return tma_popc(mask & ((1u << q) - 1u)); }
+// q-th staged slot -> state slot
+__host__ __device__ constexpr int tma_nth(uint32_t mask, int n)
+{
+    int q = 0;
+    for (; q < 32; ++q)
+        if ((mask >> q) & 1u) { if (n == 0) break; --n; }
+    return q;
+}
+
+constexpr int TMA_SEG = 258;   // doubles per staged row: 256 nodes + 16-B alignment slack
+
+constexpr int TMA_REC_BYTES = WARPS_PER_BLOCK * 16;   // the tile's 8 work records
+
+template <class M, int K> struct TmaCfg {
+    static constexpr int NSR = tma_popc(M::READ_MASK);
+    static constexpr int NARR = K + NSR;
+    static constexpr int NSTAGE = 2;
+    // blocks per SM the launch bounds ask for: as many as the ring allows (227 KB / SM)
+    static constexpr size_t STAGE = (size_t)NARR * TMA_SEG * sizeof(double) + TMA_REC_BYTES;
+    static constexpr size_t SMEM = NSTAGE * STAGE + 64;
+    static constexpr int BLOCKS = SMEM * 4 <= 224 * 1024 ? 4 : (SMEM * 3 <= 224 * 1024 ? 3 : 2);
+};
+
+// state accessor of the TMA kernel: reads from the staged rows, writes to global
+template <class M> struct StateIOTma {
+    const double *sm;     // this node's column in the staged state rows
+    double *gp;           // this node's column in the global compact state
+    int64_t stride;
+    __device__ __forceinline__ double ld(int q) const { return sm[tma_slot(M::READ_MASK, q) * TMA_SEG]; }
+    __device__ __forceinline__ void st(int q, double v) const { st_stream(gp + (int64_t)q * stride, v); }
+};
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO>
+__global__ void __launch_bounds__(BLOCK_THREADS, (TmaCfg<M, Stencil<DIM, ST>::K>::BLOCKS))
+step_kernel_tma(const __grid_constant__ StepArgs<M> A)
+{
+    using S = Stencil<DIM, ST>;
+    constexpr int K = S::K;
+    using C = TmaCfg<M, K>;
+    constexpr int NARR = C::NARR, NSTAGE = C::NSTAGE;
+    constexpr int STAGE_D = (int)(C::STAGE / sizeof(double));   // doubles per ring stage
+    const StepCommon &P = A.k;
+    const Grid &g = P.g;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);     // [NSTAGE]{[NARR][SEG] rows, 8 records}
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NSTAGE * STAGE_D);
+
+    const int64_t n_tiles = g.n_work / WARPS_PER_BLOCK;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer (warp 0): start the bulk copies of tile t (compact range [c0, c1)) into
+    // ring stage s
+    auto issue = [&](int64_t t, int s, uint32_t c0, uint32_t c1) {
+        const uint32_t c0a = c0 & ~1u;
+        const unsigned bytes = c1 > c0 ? (((c1 - c0a) + 1u) & ~1u) * 8u : 0u;
+        if (lane == 0) mbar_arrive_expect_tx(full + s, bytes * NARR + TMA_REC_BYTES);
+        __syncwarp();
+        double *stage = ring + (size_t)s * STAGE_D;
+        if (lane == 31)
+            tma_load_1d(stage + NARR * TMA_SEG, P.records + t * WARPS_PER_BLOCK, TMA_REC_BYTES,
+                        full + s);
+        if (bytes) {
+            for (int a = lane; a < NARR; a += 32) {
+                const double *src = a < K
+                    ? P.w + (int64_t)a * g.ld + c0a
+                    : P.state + (int64_t)tma_nth(M::READ_MASK, a - K) * g.ld + c0a;
+                tma_load_1d(stage + a * TMA_SEG, src, bytes, full + s);
+            }
+        }
+    };
+    // compact range of the tile that will be issued next (loaded one iteration early so
+    // that the producer warp never waits on it)
+    uint32_t nx0 = 0, nx1 = 0;
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE - 1; ++s) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < n_tiles) issue(t, s, __ldg(P.tile_base + t), __ldg(P.tile_base + t + 1));
+        }
+        const int64_t t = (int64_t)blockIdx.x + (int64_t)(NSTAGE - 1) * gridDim.x;
+        if (t < n_tiles) { nx0 = __ldg(P.tile_base + t); nx1 = __ldg(P.tile_base + t + 1); }
+    }
+
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % NSTAGE;
+        const unsigned phase = (unsigned)(it / NSTAGE) & 1u;
+        if (warp == 0) {
+            // the stage consumed in the previous iteration is free (barrier at loop end)
+            const int64_t t2 = t + (int64_t)(NSTAGE - 1) * gridDim.x;
+            if (t2 < n_tiles) issue(t2, (it + NSTAGE - 1) % NSTAGE, nx0, nx1);
+            const int64_t t3 = t2 + gridDim.x;
+            if (t3 < n_tiles) { nx0 = __ldg(P.tile_base + t3); nx1 = __ldg(P.tile_base + t3 + 1); }
+        }
+
+        const HaloSide *side = nullptr;
+        if (HALO) {
+            const unsigned b = (unsigned)t;
+            if (P.halo.lo.on && b - P.halo.lo.first_block < P.halo.lo.n_blocks) side = &P.halo.lo;
+            else if (P.halo.hi.on && b - P.halo.hi.first_block < P.halo.hi.n_blocks) side = &P.halo.hi;
+            if (side) {
+                if (threadIdx.x == 0)
+                    while (ld_acquire_sys(side->flag) < P.halo.epoch) __nanosleep(64);
+                __syncthreads();
+            }
+        }
+
+        // everything this tile needs from HBM (work records, weight rows, state rows) was
+        // requested one iteration ago; normally the wait returns at once
+        mbar_wait(full + s, phase);
+        const double *stage = ring + (size_t)s * STAGE_D;
+        const uint4 rec = reinterpret_cast<const uint4 *>(stage + NARR * TMA_SEG)[warp];
+        const int64_t chunk = (int64_t)(int32_t)rec.x;
+        const uint32_t bits = chunk >= 0 ? rec.y : 0u;
+        const int64_t n = chunk * 32 + lane;
+        const bool myo = (bits >> lane) & 1u;
+
+        if (TRACK && P.do_act && chunk >= 0 && n < g.n_nodes) {
+            const double a = P.act_t[n];
+            const double uu = P.u[n];
+            if (a < 0 && uu > P.act_thr) P.act_t[n] = P.t;
+        }
+
+        double un[K];
+        if (myo) {
+            const double *__restrict__ u = P.u + n;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const Off o = S::at(k);
+                const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
+                                    (int64_t)o.r * g.s_row + o.l;
+                un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
+            }
+        }
+
+        if (myo) {
+            const uint32_t c = rec.z + __popc(bits & ((1u << lane) - 1u));
+            const double *row = stage + (c - (rec.w & ~1u));
+
+            double acc = mul(un[0], row[0]);
+#pragma unroll
+            for (int k = 1; k < K; ++k) acc = add(acc, mul(un[k], row[k * TMA_SEG]));
+            double uc = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (S::at(k).p == 0 && S::at(k).r == 0 && S::at(k).l == 0) uc = un[k];
+
+            StateIOTma<M> io{row + K * TMA_SEG, P.state + c, g.ld};
+            M::ionic(uc, acc, io, A.c);
+
+            P.u_new[n] = acc;
+            if (HALO && side) side->peer_dst[n - side->first] = acc;
+        }
+
+        if (HALO && side) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned done = atomicAdd(side->counter, 1u) + 1u;
+                if (done == side->n_blocks) {
+                    *side->counter = 0;
+                    __threadfence_system();
+                    st_release_sys(side->peer_flag, P.halo.epoch + 1u);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with stage s before it is refilled
+    }
+}
+
 inline int64_t step_blocks(const Grid &g) { return (g.n_work + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
@@ -306,6 +541,48 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     return 0;
 }
 
+template <class M, int DIM, int ST, bool TRACK, bool HALO>
+static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
+{
+    using C = TmaCfg<M, Stencil<DIM, ST>::K>;
+    auto kern = step_kernel_tma<M, DIM, ST, TRACK, HALO>;
+    static int resident = 0;      // blocks of this instantiation the device holds at once
+    if (resident == 0) {
+        FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::SMEM));
+        int dev = 0, sms = 0, per_sm = 0;
+        FWB_CUDA(cudaGetDevice(&dev));
+        FWB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS,
+                                                               C::SMEM));
+        if (per_sm < 1) { set_error("step_kernel_tma does not fit on an SM"); return FWB_E_UNSUPPORTED; }
+        resident = sms * per_sm;
+    }
+    StepArgs<M> a;
+    a.k = k;
+    a.c = *reinterpret_cast<const typename M::Consts *>(consts);
+    const int64_t tiles = step_blocks(k.g);
+    if (tiles <= 0) return 0;
+    int64_t blocks = tiles < resident ? tiles : resident;
+    if (HALO) {
+        // boundary tiles wait on a neighbour GPU: they must all be resident in the first round
+        const int64_t nb = (int64_t)k.halo.lo.n_blocks + k.halo.hi.n_blocks;
+        if (nb > blocks) { set_error("slab boundary does not fit the resident grid"); return FWB_E_UNSUPPORTED; }
+    }
+    kern<<<(unsigned)blocks, BLOCK_THREADS, C::SMEM, s>>>(a);
+    FWB_KERNEL_CHECK("step_kernel_tma");
+    return 0;
+}
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO>
+static int launch_pick(const StepCommon &k, const void *consts, cudaStream_t s)
+{
+    if constexpr (M::USE_TMA) {
+        if (k.tile_base && !k.do_ecg) return launch_tma<M, DIM, ST, TRACK, HALO>(k, consts, s);
+    }
+    return launch_one<M, DIM, ST, TRACK, HALO>(k, consts, s);
+}
+
 template <class M>
 static int launch_model(int dim, int stencil, bool track, const StepCommon &k,
                         const void *consts, cudaStream_t s)
@@ -314,10 +591,10 @@ static int launch_model(int dim, int stencil, bool track, const StepCommon &k,
 #define FWB_CASE(D, ST)                                                              \
     if (dim == D && stencil == ST) {                                                 \
         if (halo)                                                                    \
-            return track ? launch_one<M, D, ST, true, true>(k, consts, s)            \
-                         : launch_one<M, D, ST, false, true>(k, consts, s);          \
-        return track ? launch_one<M, D, ST, true, false>(k, consts, s)               \
-                     : launch_one<M, D, ST, false, false>(k, consts, s);             \
+            return track ? launch_pick<M, D, ST, true, true>(k, consts, s)           \
+                         : launch_pick<M, D, ST, false, true>(k, consts, s);         \
+        return track ? launch_pick<M, D, ST, true, false>(k, consts, s)              \
+                     : launch_pick<M, D, ST, false, false>(k, consts, s);            \
     }
     FWB_CASE(2, FWB_STENCIL_ISO)
     FWB_CASE(2, FWB_STENCIL_ANISO)

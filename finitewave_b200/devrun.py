@@ -174,7 +174,8 @@ class DeviceSimulation:
         return self.u_device().cpu().numpy()
 
     def state_compact(self, name):
-        """Device view [n_myo] of one state variable in myocyte (myo_indexes) order."""
+        """Device view [n_myo] of one state variable in the device's compact (tile)
+        order; use state_host() for the dense array."""
         return self.engine.state[self.state_names.index(name), :self.engine.n_myo]
 
     def state_host(self, name):

@@ -156,6 +156,15 @@ class Engine:
         self.n_work = int(n_work.value)
         self.halo_blocks = (int(n_lo.value), int(n_hi.value))
         self.worklist = self.worklist[:max(self.n_work, 8)].clone()
+        # compact (weights / state) layout in work-list order: one contiguous range per tile
+        self.tile_base = torch.zeros(self.n_work // 8 + 1, dtype=torch.int32, device=self.device)
+        self.records = torch.zeros((max(self.n_work, 8), 4), dtype=torch.int32, device=self.device)
+        n_myo = ctypes.c_int64(0)
+        check(self.L.fwb_order_compact(_ptr(self.chunk_bits), self.n_chunks, _ptr(self.worklist),
+                                       self.n_work, _ptr(self.chunk_base), _ptr(self.tile_base),
+                                       _ptr(self.records), ctypes.byref(n_myo), _stream()),
+              "fwb_order_compact")
+        assert int(n_myo.value) == self.n_myo
 
     # ---- weights --------------------------------------------------------
     def compute_weights(self, stencil, conductivity, fibers, D_al, D_ac, D_model, dt, dr):
@@ -258,7 +267,7 @@ class Engine:
         self.state[slot].fill_(float(value))
 
     # ---- simulation object ---------------------------------------------
-    def create_sim(self, model_id, params, dt):
+    def create_sim(self, model_id, params, dt, use_tma=True):
         self.destroy_sim()
         p = (ctypes.c_double * len(params))(*[float(x) for x in params])
         sim = ctypes.c_void_p(0)
@@ -270,6 +279,9 @@ class Engine:
             p, len(params), float(dt), _stream()), "fwb_sim_create")
         self.sim = sim
         self._keep = []
+        if use_tma:
+            check(self.L.fwb_sim_set_tile_base(sim, _ptr(self.tile_base), _ptr(self.records)),
+                  "fwb_sim_set_tile_base")
 
     def destroy_sim(self):
         if self.sim:

@@ -117,6 +117,21 @@ FWB_API int fwb_build_worklist(int dim, const int64_t *shape, const uint8_t *act
                        int64_t *n_work, int64_t *n_lo_blocks, int64_t *n_hi_blocks,
                        fwb_stream_t stream);
 
+/* Re-number the compact indices in WORK-LIST order (fwb_build_chunks numbers them in
+ * flat order = the reference's myo_indexes order): afterwards the nodes of one tile
+ * (8 consecutive work-list entries) occupy one contiguous range of every weight /
+ * state row, which is what the TMA-fed step kernel copies per tile.
+ *   chunk_base  [n_chunks]       rewritten
+ *   tile_base   [n_work/8 + 1]   out: compact index of the first node of each tile
+ *   records     [n_work][4]      out (or NULL): per work-list entry {chunk id, update
+ *                                bits, compact index of the chunk's first node,
+ *                                compact index of the tile's first node}; 16-B aligned
+ * Every array in compact layout must be (re)filled after this call.  (synchronises) */
+FWB_API int fwb_order_compact(const uint32_t *chunk_bits, int64_t n_chunks,
+                      const int32_t *worklist, int64_t n_work, uint32_t *chunk_base,
+                      uint32_t *tile_base, uint32_t *records, int64_t *n_myo,
+                      fwb_stream_t stream);
+
 /* dense (*shape) <-> compact [ld] conversions of one array.
  * gather:  compact[c] = dense[n]            for update nodes
  * scatter: dense[n] = update ? compact[c] : fill   (all n < n_nodes)        */
@@ -187,6 +202,10 @@ FWB_API int fwb_sim_set_time(FwbSim *sim, double t, int64_t step);
 FWB_API int fwb_sim_get_time(const FwbSim *sim, double *t, int64_t *step);
 /* which of the two buffers passed at creation currently is `u` (0 or 1) */
 FWB_API int fwb_sim_current_buffer(const FwbSim *sim);
+/* enable the TMA-fed persistent step kernel for the HBM-bound models: tile_base and
+ * records from fwb_order_compact (NULL = one-block-per-tile kernel with plain loads) */
+FWB_API int fwb_sim_set_tile_base(FwbSim *sim, const uint32_t *tile_base,
+                          const uint32_t *records);
 /* rebind after the caller re-uploaded / recomputed arrays (same sizes) */
 FWB_API int fwb_sim_set_weights(FwbSim *sim, const double *weights);
 FWB_API int fwb_sim_set_params(FwbSim *sim, const double *params, int n_params, double dt);

@@ -37,7 +37,8 @@ def test_chunks_and_compaction_roundtrip(env, shape):
     flat = np.arange(mesh.size)
     cidx = eng.compact_index(flat)
     assert np.array_equal(np.flatnonzero(cidx >= 0), idx)
-    assert np.array_equal(cidx[idx], np.arange(len(idx)))        # myo_indexes order
+    # compact indices are a permutation of 0..n_myo-1 (tile order, see fwb_order_compact)
+    assert np.array_equal(np.sort(cidx[idx]), np.arange(len(idx)))
     eng.allocate(1)
     rng = np.random.default_rng(0)
     a = rng.random(shape)
@@ -47,7 +48,16 @@ def test_chunks_and_compaction_roundtrip(env, shape):
     eng.synchronize()
     expect = np.where(mesh == 1, a, -7.0)
     assert np.array_equal(back, expect)
-    assert np.array_equal(eng.state[0, :eng.n_myo].cpu().numpy(), a.ravel()[idx])
+    assert np.array_equal(eng.state[0].cpu().numpy()[cidx[idx]], a.ravel()[idx])
+    # every tile (8 work-list entries) owns one contiguous compact range
+    tb = eng.tile_base.cpu().numpy().astype(np.int64)
+    wl = eng.worklist[:eng.n_work].cpu().numpy().reshape(-1, 8)
+    assert tb[0] == 0 and tb[-1] == eng.n_myo and np.all(np.diff(tb) >= 0)
+    for t in (0, len(wl) // 2, len(wl) - 1):
+        nodes = np.concatenate([np.arange(c * 32, c * 32 + 32) for c in wl[t] if c >= 0])
+        nodes = nodes[nodes < mesh.size]
+        got = np.sort(cidx[nodes][cidx[nodes] >= 0])
+        assert np.array_equal(got, np.arange(tb[t], tb[t + 1]))
     del torch
 
 
