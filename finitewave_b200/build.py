@@ -49,7 +49,8 @@ def _compile(src, verbose):
     if (obj.exists() and obj.stat().st_mtime >= srcp.stat().st_mtime
             and obj.stat().st_mtime >= _deps_mtime()):
         return obj, ""
-    cmd = [nvcc(), *NVCC_FLAGS, "-c", str(srcp), "-o", str(obj)]
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("FWB_EXTRA_FLAGS", "").split(), "-c", str(srcp),
+           "-o", str(obj)]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")

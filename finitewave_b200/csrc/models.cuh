@@ -30,6 +30,7 @@
 #include <math.h>
 
 #include "fwb_common.cuh"
+#include "fexp.cuh"
 
 #ifdef __CUDACC__
 #define FWB_HD __host__ __device__ __forceinline__
@@ -38,6 +39,35 @@
 #endif
 
 namespace fwb {
+
+// Math policies of the two FP64-issue-bound models (LR91, TP06).  LibMath is the
+// reference statement (library exp, IEEE division); it is what the host transcription
+// check compiles and what the device uses for nodes whose potential is outside
+// (-300, 300) mV.  FastMath is the device's normal path: table-driven exp (fexp.cuh),
+// and the division fast path without its special-operand test where the denominator
+// is 1 + exp(.) >= 1.
+//   eu(x)  exp of an affine function of u   (|x| < 700 follows from |u| < 300)
+//   en(x)  exp of a non-positive, state-dependent argument (Rush-Larsen factors)
+//   ec(x)  exp of any state-dependent argument
+//   dv(a, b)  a / b for b = 1 + exp(.)
+struct LibMath {
+    FWB_HD static double eu(double x) { return exp(x); }
+    FWB_HD static double en(double x) { return exp(x); }
+    FWB_HD static double ec(double x) { return exp(x); }
+    FWB_HD static double dv(double a, double b) { return a / b; }
+};
+struct FastMath {
+    FWB_HD static double eu(double x) { return fexp(x); }
+    FWB_HD static double en(double x) { return fexp_neg(x); }
+    FWB_HD static double ec(double x) { return fexp_clamped(x); }
+    FWB_HD static double dv(double a, double b)
+    {
+        const double y = frcp(b);
+        const double q = a * y;
+        return fma(fma(-b, q, a), y, q);
+    }
+};
+constexpr double FAST_MATH_U_LIMIT = 300.0;
 
 // divisor known on the host: the value and its correctly rounded reciprocal
 struct DivC {
@@ -218,21 +248,31 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
+#ifdef __CUDA_ARCH__
+        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
+        else
+#endif
+            ionic_impl<IO, LibMath>(u, un, io, c);
+    }
+    template <class IO, class E>
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
+    {
         const double dt = c.dt;
         // calc_ina :185-241
         double alpha_h = 0, beta_h = 0, beta_J = 0, alpha_J = 0;
         if (u >= -40.) {
-            beta_h = 1. / (0.13 * (1 + exp(FWB_DIVK(u + 10.66, -11.1))));
-            beta_J = 0.3 * exp(-2.535 * 1e-07 * u) / (1 + exp(-0.1 * (u + 32)));
+            beta_h = 1. / (0.13 * (1 + E::eu(FWB_DIVK(u + 10.66, -11.1))));
+            beta_J = E::dv(0.3 * E::eu(-2.535 * 1e-07 * u), 1 + E::eu(-0.1 * (u + 32)));
         } else {
-            alpha_h = 0.135 * exp(FWB_DIVK(80 + u, -6.8));
-            beta_h = 3.56 * exp(0.079 * u) + 3.1 * 1e5 * exp(0.35 * u);
-            beta_J = 0.1212 * exp(-0.01052 * u) / (1 + exp(-0.1378 * (u + 40.14)));
-            alpha_J = (-1.2714 * 1e5 * exp(0.2444 * u) - 3.474 * 1e-5 * exp(-0.04391 * u)) *
-                      (u + 37.78) / (1 + exp(0.311 * (u + 79.23)));
+            alpha_h = 0.135 * E::eu(FWB_DIVK(80 + u, -6.8));
+            beta_h = 3.56 * E::eu(0.079 * u) + 3.1 * 1e5 * E::eu(0.35 * u);
+            beta_J = E::dv(0.1212 * E::eu(-0.01052 * u), 1 + E::eu(-0.1378 * (u + 40.14)));
+            alpha_J = E::dv((-1.2714 * 1e5 * E::eu(0.2444 * u) - 3.474 * 1e-5 * E::eu(-0.04391 * u)) *
+                                (u + 37.78),
+                            1 + E::eu(0.311 * (u + 79.23)));
         }
-        const double alpha_m = 0.32 * (u + 47.13) / (1 - exp(-0.1 * (u + 47.13)));
-        const double beta_m = 0.08 * exp(FWB_DIVK(-u, 11.));
+        const double alpha_m = 0.32 * (u + 47.13) / (1 - E::eu(-0.1 * (u + 47.13)));
+        const double beta_m = 0.08 * E::eu(FWB_DIVK(-u, 11.));
         const double m = gate(io.ld(0), dt, alpha_m, beta_m);
         const double h = gate(io.ld(1), dt, alpha_h, beta_h);
         const double j = gate(io.ld(2), dt, alpha_J, beta_J);
@@ -242,10 +282,10 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         double d = io.ld(3), f = io.ld(4), cai = io.ld(6);
         const double E_Si = 7.7 - 13.0287 * log(cai);
         const double I_Si = c.gsi * d * f * (u - E_Si);
-        const double alpha_d = 0.095 * exp(-0.01 * (u - 5)) / (1 + exp(-0.072 * (u - 5)));
-        const double beta_d = 0.07 * exp(-0.017 * (u + 44)) / (1 + exp(0.05 * (u + 44)));
-        const double alpha_f = 0.012 * exp(-0.008 * (u + 28)) / (1 + exp(0.15 * (u + 28)));
-        const double beta_f = 0.0065 * exp(-0.02 * (u + 30)) / (1 + exp(-0.2 * (u + 30)));
+        const double alpha_d = E::dv(0.095 * E::eu(-0.01 * (u - 5)), 1 + E::eu(-0.072 * (u - 5)));
+        const double beta_d = E::dv(0.07 * E::eu(-0.017 * (u + 44)), 1 + E::eu(0.05 * (u + 44)));
+        const double alpha_f = E::dv(0.012 * E::eu(-0.008 * (u + 28)), 1 + E::eu(0.15 * (u + 28)));
+        const double beta_f = E::dv(0.0065 * E::eu(-0.02 * (u + 30)), 1 + E::eu(-0.2 * (u + 30)));
         d = gate(d, dt, alpha_d, beta_d);
         f = gate(f, dt, alpha_f, beta_f);
         cai += dt * (-0.0001 * I_Si + 0.07 * (0.0001 - cai));
@@ -253,24 +293,24 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         // calc_ik :297-356
         double Xi;
         if (u > -100)
-            Xi = 2.837 * (exp(0.04 * (u + 77)) - 1) / ((u + 77) * exp(0.04 * (u + 35)));
+            Xi = 2.837 * (E::eu(0.04 * (u + 77)) - 1) / ((u + 77) * E::eu(0.04 * (u + 35)));
         else
             Xi = 1;
         double x = io.ld(5);
         const double I_K = c.G_K * x * Xi * (u - c.E_K);
-        const double alpha_x = 0.0005 * exp(0.083 * (u + 50)) / (1 + exp(0.057 * (u + 50)));
-        const double beta_x = 0.0013 * exp(-0.06 * (u + 20)) / (1 + exp(-0.04 * (u + 20)));
+        const double alpha_x = E::dv(0.0005 * E::eu(0.083 * (u + 50)), 1 + E::eu(0.057 * (u + 50)));
+        const double beta_x = E::dv(0.0013 * E::eu(-0.06 * (u + 20)), 1 + E::eu(-0.04 * (u + 20)));
         x = gate(x, dt, alpha_x, beta_x);
         io.st(5, x);
         // calc_ik1 :359-408, calc_ikp :411-427, calc_ib :430-443, kernel :496-510
         const double E_K1 = c.E_K1;
-        const double alpha_K1 = 1.02 / (1 + exp(0.2385 * (u - E_K1 - 59.215)));
-        const double beta_K1 = (0.49124 * exp(0.08032 * (u - E_K1 + 5.476)) +
-                                exp(0.06175 * (u - E_K1 - 594.31))) /
-                               (1 + exp(-0.5143 * (u - E_K1 + 4.753)));
+        const double alpha_K1 = E::dv(1.02, 1 + E::eu(0.2385 * (u - E_K1 - 59.215)));
+        const double beta_K1 = (0.49124 * E::eu(0.08032 * (u - E_K1 + 5.476)) +
+                                E::eu(0.06175 * (u - E_K1 - 594.31))) /
+                               (1 + E::eu(-0.5143 * (u - E_K1 + 4.753)));
         const double K_1x = alpha_K1 / (alpha_K1 + beta_K1);
         const double ik1 = c.G_K1 * K_1x * (u - E_K1);
-        const double K_p = 1. / (1 + exp(FWB_DIVK(7.488 - u, 5.98)));
+        const double K_p = E::dv(1., 1 + E::eu(FWB_DIVK(7.488 - u, 5.98)));
         const double ikp = c.gkp * K_p * (u - E_K1);
         const double ib = c.gb * (u + 59.87);
         const double ik1t = ik1 + ikp + ib;
@@ -288,7 +328,10 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
 //        10 xs, 11 r, 12 s, 13 d, 14 f, 15 f2, 16 fcass, 17 rr, 18 oo
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_TP06> {
-    static constexpr int NS = 19, NP = 49, MIN_BLOCKS = 2;
+#ifndef FWB_TP06_MIN_BLOCKS
+#define FWB_TP06_MIN_BLOCKS 4
+#endif
+    static constexpr int NS = 19, NP = 49, MIN_BLOCKS = FWB_TP06_MIN_BLOCKS;
     static constexpr bool USE_TMA = false;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x3ffff;          // all but oo
     static constexpr uint32_t WRITE_MASK = 0x7ffff & ~0x1u;  // all but cai
@@ -329,12 +372,21 @@ template <> struct Model<FWB_MODEL_TP06> {
         return divc_ok(c.RT);
     }
     // Rush-Larsen update (tp06_2d.py:307-309 and twins)
-    FWB_HD static double rl(double inf, double x, double dt, double tau)
+    template <class E> FWB_HD static double rl(double inf, double x, double dt, double tau)
     {
-        return inf - (inf - x) * exp(-dt / tau);
+        return inf - (inf - x) * E::en(-dt / tau);
     }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
+    {
+#ifdef __CUDA_ARCH__
+        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
+        else
+#endif
+            ionic_impl<IO, LibMath>(u, un, io, c);
+    }
+    template <class IO, class E>
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
     {
         const double dt = c.dt;
         const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
@@ -350,32 +402,33 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ina :242-318
         double ina;
         {
-            const double alpha_m = 1. / (1. + exp(FWB_DIVK(-60. - u, 5.)));
-            const double beta_m = 0.1 / (1. + exp(FWB_DIVK(u + 35., 5.))) +
-                                  0.10 / (1. + exp(FWB_DIVK(u - 50., 200.)));
+            const double alpha_m = E::dv(1., 1. + E::eu(FWB_DIVK(-60. - u, 5.)));
+            const double beta_m = E::dv(0.1, 1. + E::eu(FWB_DIVK(u + 35., 5.))) +
+                                  E::dv(0.10, 1. + E::eu(FWB_DIVK(u - 50., 200.)));
             const double tau_m = alpha_m * beta_m;
-            const double em = 1. + exp(FWB_DIVK(-56.86 - u, 9.03));
-            const double m_inf = 1. / (em * em);
+            const double em = 1. + E::eu(FWB_DIVK(-56.86 - u, 9.03));
+            const double m_inf = E::dv(1., em * em);
             double alpha_h, beta_h, alpha_j, beta_j;
             if (u >= -40.) {
                 alpha_h = 0.;
-                beta_h = 0.77 / (0.13 * (1. + exp(FWB_DIVK(-(u + 10.66), 11.1))));
+                beta_h = E::dv(0.77, 0.13 * (1. + E::eu(FWB_DIVK(-(u + 10.66), 11.1))));
                 alpha_j = 0.;
-                beta_j = 0.6 * exp(0.057 * u) / (1. + exp(-0.1 * (u + 32.)));
+                beta_j = E::dv(0.6 * E::eu(0.057 * u), 1. + E::eu(-0.1 * (u + 32.)));
             } else {
-                alpha_h = 0.057 * exp(FWB_DIVK(-(u + 80.), 6.8));
-                beta_h = 2.7 * exp(0.079 * u) + 3.1e5 * exp(0.3485 * u);
-                alpha_j = (-2.5428e4 * exp(0.2444 * u) - 6.948e-6 * exp(-0.04391 * u)) *
-                          (u + 37.78) / (1. + exp(0.311 * (u + 79.23)));
-                beta_j = 0.02424 * exp(-0.01052 * u) / (1. + exp(-0.1378 * (u + 40.14)));
+                alpha_h = 0.057 * E::eu(FWB_DIVK(-(u + 80.), 6.8));
+                beta_h = 2.7 * E::eu(0.079 * u) + 3.1e5 * E::eu(0.3485 * u);
+                alpha_j = E::dv((-2.5428e4 * E::eu(0.2444 * u) - 6.948e-6 * E::eu(-0.04391 * u)) *
+                                    (u + 37.78),
+                                1. + E::eu(0.311 * (u + 79.23)));
+                beta_j = E::dv(0.02424 * E::eu(-0.01052 * u), 1. + E::eu(-0.1378 * (u + 40.14)));
             }
             const double tau_h = 1.0 / (alpha_h + beta_h);
-            const double eh = 1. + exp(FWB_DIVK(u + 71.55, 7.43));
-            const double h_inf = 1. / (eh * eh);
+            const double eh = 1. + E::eu(FWB_DIVK(u + 71.55, 7.43));
+            const double h_inf = E::dv(1., eh * eh);
             const double tau_j = 1.0 / (alpha_j + beta_j);
-            const double m = rl(m_inf, io.ld(5), dt, tau_m);
-            const double h = rl(h_inf, io.ld(6), dt, tau_h);
-            const double j = rl(h_inf, io.ld(7), dt, tau_j);
+            const double m = rl<E>(m_inf, io.ld(5), dt, tau_m);
+            const double h = rl<E>(h_inf, io.ld(6), dt, tau_h);
+            const double j = rl<E>(h_inf, io.ld(7), dt, tau_j);
             io.st(5, m); io.st(6, h); io.st(7, j);
             ina = c.gna * m * m * m * h * j * (u - Ena);
         }
@@ -384,34 +437,34 @@ template <> struct Model<FWB_MODEL_TP06> {
         const double cass = io.ld(2);
         double ical;
         {
-            const double d_inf = 1. / (1. + exp(FWB_DIVK(-8 - u, 7.5)));
-            const double Ad = 1.4 / (1. + exp(FWB_DIVK(-35 - u, 13.))) + 0.25;
-            const double Bd = 1.4 / (1. + exp(FWB_DIVK(u + 5, 5.)));
-            const double Cd = 1. / (1. + exp(FWB_DIVK(50 - u, 20.)));
+            const double d_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-8 - u, 7.5)));
+            const double Ad = E::dv(1.4, 1. + E::eu(FWB_DIVK(-35 - u, 13.))) + 0.25;
+            const double Bd = E::dv(1.4, 1. + E::eu(FWB_DIVK(u + 5, 5.)));
+            const double Cd = E::dv(1., 1. + E::eu(FWB_DIVK(50 - u, 20.)));
             const double tau_d = Ad * Bd + Cd;
-            const double d = rl(d_inf, io.ld(13), dt, tau_d);
+            const double d = rl<E>(d_inf, io.ld(13), dt, tau_d);
             io.st(13, d);
-            const double f_inf = 1. / (1. + exp(FWB_DIVK(u + 20, 7.)));
-            const double Af = 1102.5 * exp(FWB_DIVK(-(u + 27) * (u + 27), 225.));
-            const double Bf = 200. / (1 + exp(FWB_DIVK(13 - u, 10.)));
-            const double e30 = exp(FWB_DIVK(u + 30, 10.));
-            const double Cf = (180. / (1 + e30)) + 20;
+            const double f_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u + 20, 7.)));
+            const double Af = 1102.5 * E::eu(FWB_DIVK(-(u + 27) * (u + 27), 225.));
+            const double Bf = E::dv(200., 1 + E::eu(FWB_DIVK(13 - u, 10.)));
+            const double e30 = E::eu(FWB_DIVK(u + 30, 10.));
+            const double Cf = E::dv(180., 1 + e30) + 20;
             const double tau_f = Af + Bf + Cf;
-            const double f = rl(f_inf, io.ld(14), dt, tau_f);
+            const double f = rl<E>(f_inf, io.ld(14), dt, tau_f);
             io.st(14, f);
-            const double f2_inf = 0.67 / (1. + exp(FWB_DIVK(u + 35, 7.))) + 0.33;
-            const double Af2 = 600 * exp(FWB_DIVK(-(u + 25) * (u + 25), 170.));
-            const double Bf2 = 31 / (1. + exp(FWB_DIVK(25 - u, 10.)));
-            const double Cf2 = 16 / (1. + e30);
+            const double f2_inf = E::dv(0.67, 1. + E::eu(FWB_DIVK(u + 35, 7.))) + 0.33;
+            const double Af2 = 600 * E::eu(FWB_DIVK(-(u + 25) * (u + 25), 170.));
+            const double Bf2 = E::dv(31., 1. + E::eu(FWB_DIVK(25 - u, 10.)));
+            const double Cf2 = E::dv(16., 1. + e30);
             const double tau_f2 = Af2 + Bf2 + Cf2;
-            const double f2 = rl(f2_inf, io.ld(15), dt, tau_f2);
+            const double f2 = rl<E>(f2_inf, io.ld(15), dt, tau_f2);
             io.st(15, f2);
             const double cq = 1 + FWB_DIVK(cass, 0.05) * FWB_DIVK(cass, 0.05);
-            const double fcass_inf = 0.6 / cq + 0.4;
-            const double tau_fcass = 80. / cq + 2.;
-            const double fcass = rl(fcass_inf, io.ld(16), dt, tau_fcass);
+            const double fcass_inf = E::dv(0.6, cq) + 0.4;
+            const double tau_fcass = E::dv(80., cq) + 2.;
+            const double fcass = rl<E>(fcass_inf, io.ld(16), dt, tau_fcass);
             io.st(16, fcass);
-            const double e2 = exp(divc(2 * (u - 15) * c.F, c.RT));
+            const double e2 = E::eu(divc(2 * (u - 15) * c.F, c.RT));
             ical = c.gcal * d * f * f2 * fcass * 4 * (u - 15) * c.FF_RT *
                    (0.25 * e2 * cass - c.cao) / (e2 - 1.);
         }
@@ -419,13 +472,13 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ito :383-413
         double ito;
         {
-            const double r_inf = 1. / (1. + exp(FWB_DIVK(20 - u, 6.)));
-            const double s_inf = 1. / (1. + exp(FWB_DIVK(u + 20, 5.)));
-            const double tau_r = 9.5 * exp(FWB_DIVK(-(u + 40.) * (u + 40.), 1800.)) + 0.8;
-            const double tau_s = 85. * exp(FWB_DIVK(-(u + 45.) * (u + 45.), 320.)) +
-                                 5. / (1. + exp(FWB_DIVK(u - 20., 5.))) + 3.;
-            const double sg = rl(s_inf, io.ld(12), dt, tau_s);
-            const double r = rl(r_inf, io.ld(11), dt, tau_r);
+            const double r_inf = E::dv(1., 1. + E::eu(FWB_DIVK(20 - u, 6.)));
+            const double s_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u + 20, 5.)));
+            const double tau_r = 9.5 * E::eu(FWB_DIVK(-(u + 40.) * (u + 40.), 1800.)) + 0.8;
+            const double tau_s = 85. * E::eu(FWB_DIVK(-(u + 45.) * (u + 45.), 320.)) +
+                                 E::dv(5., 1. + E::eu(FWB_DIVK(u - 20., 5.))) + 3.;
+            const double sg = rl<E>(s_inf, io.ld(12), dt, tau_s);
+            const double r = rl<E>(r_inf, io.ld(11), dt, tau_r);
             io.st(11, r); io.st(12, sg);
             ito = c.gto * r * sg * (u - Ek);
         }
@@ -433,16 +486,16 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ikr :416-452
         double ikr;
         {
-            const double xr1_inf = 1. / (1. + exp(FWB_DIVK(-26. - u, 7.)));
-            const double axr1 = 450. / (1. + exp(FWB_DIVK(-45. - u, 10.)));
-            const double bxr1 = 6. / (1. + exp(FWB_DIVK(u - (-30.), 11.5)));
+            const double xr1_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-26. - u, 7.)));
+            const double axr1 = E::dv(450., 1. + E::eu(FWB_DIVK(-45. - u, 10.)));
+            const double bxr1 = E::dv(6., 1. + E::eu(FWB_DIVK(u - (-30.), 11.5)));
             const double tau_xr1 = axr1 * bxr1;
-            const double xr2_inf = 1. / (1. + exp(FWB_DIVK(u - (-88.), 24.)));
-            const double axr2 = 3. / (1. + exp(FWB_DIVK(-60. - u, 20.)));
-            const double bxr2 = 1.12 / (1. + exp(FWB_DIVK(u - 60., 20.)));
+            const double xr2_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u - (-88.), 24.)));
+            const double axr2 = E::dv(3., 1. + E::eu(FWB_DIVK(-60. - u, 20.)));
+            const double bxr2 = E::dv(1.12, 1. + E::eu(FWB_DIVK(u - 60., 20.)));
             const double tau_xr2 = axr2 * bxr2;
-            const double xr1 = rl(xr1_inf, io.ld(8), dt, tau_xr1);
-            const double xr2 = rl(xr2_inf, io.ld(9), dt, tau_xr2);
+            const double xr1 = rl<E>(xr1_inf, io.ld(8), dt, tau_xr1);
+            const double xr2 = rl<E>(xr2_inf, io.ld(9), dt, tau_xr2);
             io.st(8, xr1); io.st(9, xr2);
             ikr = c.gkr_sqrt * xr1 * xr2 * (u - Ek);
         }
@@ -450,33 +503,33 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_iks :455-485
         double iks;
         {
-            const double xs_inf = 1. / (1. + exp(FWB_DIVK(-5. - u, 14.)));
-            const double Axs = (1400. / (sqrt(1. + exp(FWB_DIVK(5. - u, 6.)))));
-            const double Bxs = (1. / (1. + exp(FWB_DIVK(u - 35., 15.))));
+            const double xs_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-5. - u, 14.)));
+            const double Axs = (1400. / (sqrt(1. + E::eu(FWB_DIVK(5. - u, 6.)))));
+            const double Bxs = E::dv(1., 1. + E::eu(FWB_DIVK(u - 35., 15.)));
             const double tau_xs = Axs * Bxs + 80;
-            const double xs = rl(xs_inf, io.ld(10), dt, tau_xs);
+            const double xs = rl<E>(xs_inf, io.ld(10), dt, tau_xs);
             io.st(10, xs);
             iks = c.gks * xs * xs * (u - Eks);
         }
 
         // calc_ik1 :488-514
-        const double ak1 = 0.1 / (1. + exp(0.06 * (u - Ek - 200)));
-        const double bk1 = (3. * exp(0.0002 * (u - Ek + 100)) + exp(0.1 * (u - Ek - 10))) /
-                           (1. + exp(-0.5 * (u - Ek)));
+        const double ak1 = E::dv(0.1, 1. + E::ec(0.06 * (u - Ek - 200)));
+        const double bk1 = E::dv(3. * E::ec(0.0002 * (u - Ek + 100)) + E::ec(0.1 * (u - Ek - 10)),
+                                 1. + E::ec(-0.5 * (u - Ek)));
         const double rec_iK1 = ak1 / (ak1 + bk1);
         const double ik1 = c.gk1 * rec_iK1 * (u - Ek);
         // calc_inaca :517-565
-        const double e_nm1 = exp(divc(c.n_m1 * u * c.F, c.RT));
+        const double e_nm1 = E::eu(divc(c.n_m1 * u * c.F, c.RT));
         const double inaca = c.inaca_pref * (1. / (1 + c.ksat * e_nm1)) *
-                             (exp(divc(c.n_ * u * c.F, c.RT)) * nai * nai * nai * c.cao -
+                             (E::eu(divc(c.n_ * u * c.F, c.RT)) * nai * nai * nai * c.cao -
                               e_nm1 * c.nao * c.nao * c.nao * cai * 2.5);
         // calc_inak :568-604
-        const double rec_iNaK = (1. / (1. + 0.1245 * exp(divc(-0.1 * u * c.F, c.RT)) +
-                                       0.0353 * exp(divc(-u * c.F, c.RT))));
+        const double rec_iNaK = E::dv(1., 1. + 0.1245 * E::eu(divc(-0.1 * u * c.F, c.RT)) +
+                                              0.0353 * E::eu(divc(-u * c.F, c.RT)));
         const double inak = c.knak_pref * (nai / (nai + c.KmNa)) * rec_iNaK;
         // calc_ipca :607-627, calc_ipk :630-653, calc_ibna :656-675, calc_ibca :678-697
         const double ipca = c.gpca * cai / (c.KpCa + cai);
-        const double rec_ipK = 1. / (1. + exp(FWB_DIVK(25 - u, 5.98)));
+        const double rec_ipK = E::dv(1., 1. + E::eu(FWB_DIVK(25 - u, 5.98)));
         const double ipk = c.gpk * rec_ipK * (u - Ek);
         const double ibna = c.gbna * (u - Ena);
         const double ibca = c.gbca * (u - Eca);

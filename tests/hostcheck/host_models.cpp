@@ -48,3 +48,11 @@ int fwb_host_ionic(int model, double *u_new, const double *u, double *const *st,
     }
     return -1;
 }
+
+// host build of the device's table-driven exp (finitewave_b200/csrc/fexp.cuh)
+extern "C" __attribute__((visibility("default")))
+void fwb_host_fexp(const double *x, double *out, int64_t n, int mode)
+{
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = mode == 0 ? fwb::fexp(x[i]) : mode == 1 ? fwb::fexp_neg(x[i]) : fwb::fexp_clamped(x[i]);
+}

@@ -27,7 +27,8 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 
 @pytest.fixture(scope="module")
 def hostlib():
-    deps = [SRC, ROOT / "finitewave_b200" / "csrc" / "models.cuh"]
+    deps = [SRC, ROOT / "finitewave_b200" / "csrc" / "models.cuh",
+            ROOT / "finitewave_b200" / "csrc" / "fexp.cuh"]
     if not SO.exists() or SO.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                                "-fno-fast-math", "-fvisibility=hidden",
@@ -109,3 +110,32 @@ def test_param_order_matches_oracle_tables():
         for k, v in spec["init"].items():
             assert float(getattr(obj, "init_" + k)) == float(v), (cls.__name__, k)
         assert obj.D_model == spec["D_model"]
+
+
+def _fexp(hostlib, x, mode):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    hostlib.fwb_host_fexp(x.ctypes.data_as(c_double_p), out.ctypes.data_as(c_double_p),
+                          ctypes.c_int64(len(x)), ctypes.c_int(mode))
+    return out
+
+
+def test_fexp_within_two_ulp_of_libm(hostlib):
+    """The device's table-driven exp (same source, host build): <= 2 ulp against libm
+    over its whole domain |x| < 700; NaN stays NaN; the clamped variants saturate."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-700, 700, 2_000_000), rng.uniform(-40, 40, 2_000_000),
+                        rng.uniform(-1, 1, 1_000_000), rng.uniform(-1e-3, 1e-3, 200_000),
+                        np.array([0.0, -0.0, 1.0, -1.0, 699.999, -699.999, 1e-300, -1e-300])])
+    out = _fexp(hostlib, x, 0)
+    ref = np.exp(x)
+    ulp = np.abs(out - ref) / np.spacing(ref)
+    assert ulp.max() <= 2.0, ulp.max()
+    assert np.isnan(_fexp(hostlib, [np.nan], 0)[0])
+    assert np.isnan(_fexp(hostlib, [np.nan], 1)[0]) and np.isnan(_fexp(hostlib, [np.nan], 2)[0])
+    lo = _fexp(hostlib, [-1e6, -np.inf, -800.0, -700.0, -3.5], 1)
+    assert np.all(lo[:4] == np.exp(-700.0)) and abs(lo[4] / np.exp(-3.5) - 1) < 1e-15
+    both = _fexp(hostlib, [-1e300, 1e300, np.inf, 12.0], 2)
+    assert both[0] == np.exp(-700.0) and both[1] == both[2] == _fexp(hostlib, [700.0], 0)[0]
+    assert abs(both[3] / np.exp(12.0) - 1) < 1e-15
+    print(f"fexp max error {ulp.max():.3f} ulp, mean {ulp.mean():.3f}")
