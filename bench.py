@@ -16,7 +16,8 @@ One JSON line on stdout (rank 0):
   value      device-resident whole-job node-updates/s (CUDA events, max over ranks)
   e2e        the same metric through the public host API (model.run() on numpy
              arrays in pinned host memory): every timed call uploads u, u_new and
-             all state arrays, runs `steps_per_call` time steps, downloads them again
+             all state arrays, runs `steps_per_call` time steps (1000, the run length
+             of the reference's README quick start), downloads them again
   roofline   fused step kernel vs the measured HBM copy bandwidth
              (MEASURED_PEAKS.json), algorithmic bytes per node from SURVEY.md 8d
   cpu_baseline  the CPU oracle port (oracle/, OpenMP, all host threads) timed on a
@@ -43,6 +44,16 @@ UNIT = "node-updates/s"
 
 
 # ---------------------------------------------------------------------------
+def measured_traffic(workload):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return float(json.loads(p.read_text())[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -271,7 +282,10 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": measured_traffic(args.workload) if world == 1 and args.scale == 1.0 else None,
+                     "algorithmic_bytes": info["bytes_per_node"] * info["n_myo"],
+                     "peak_source": peak_src,
                      "kernel": "fwb::step_kernel (fused diffusion + ionic + trackers)",
                      "kernel_ms": kernel_ms},
     }
@@ -280,7 +294,7 @@ def run_b200(args):
 
     if rank == 0 and world == 1:
         try:
-            line["e2e"] = None if args.no_e2e else e2e_host_api(args.workload, args.e2e_steps, 3,
+            line["e2e"] = None if args.no_e2e else e2e_host_api(args.workload, args.e2e_steps, 2,
                                                                 scale=args.scale)
         except Exception as e:                               # never lose the device number
             line["e2e"] = {"error": repr(e)}
@@ -328,7 +342,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOAD_NAMES))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every axis (debugging)")
-    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=1000,
+                    help="time steps per model.run() call of the e2e leg (README quick start: 1000)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
