@@ -43,6 +43,8 @@ def _sig(L):
     L.fwb_sim_set_tile_base.argtypes = [p, p, p]
     L.fwb_gather_compact.argtypes = [p, p, c_int64, p, p, p]
     L.fwb_scatter_compact.argtypes = [p, p, c_double, c_int64, p, p, p]
+    L.fwb_scatter_compact_keep.argtypes = [p, p, c_int64, p, p, p]
+    L.fwb_count_offfill.argtypes = [p, c_double, c_int64, p, p, p]
     L.fwb_weights_pack.argtypes = [p, p, c_int, c_int64, c_int64, p, p, p]
     L.fwb_weights_unpack.argtypes = [p, p, c_int, c_int64, c_int64, p, p, p]
     L.fwb_compute_weights.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_double, p,

@@ -193,7 +193,7 @@ __global__ void gather_kernel(const double *dense, double *compact, int64_t n_ch
         compact[(int64_t)base[gw] + __popc(b & ((1u << lane) - 1u))] = dense[gw * 32 + lane];
 }
 
-__global__ void scatter_kernel(const double *compact, double *dense, double fill,
+__global__ void scatter_kernel(const double *compact, double *dense, double fill, int keep,
                                int64_t n_nodes, int64_t n_chunks, const uint32_t *bits,
                                const uint32_t *base)
 {
@@ -203,9 +203,25 @@ __global__ void scatter_kernel(const double *compact, double *dense, double fill
     const uint32_t b = bits[gw];
     const int64_t n = gw * 32 + lane;
     if (n >= n_nodes) return;
-    dense[n] = ((b >> lane) & 1u)
-                   ? compact[(int64_t)base[gw] + __popc(b & ((1u << lane) - 1u))]
-                   : fill;
+    if ((b >> lane) & 1u)
+        dense[n] = compact[(int64_t)base[gw] + __popc(b & ((1u << lane) - 1u))];
+    else if (!keep)
+        dense[n] = fill;
+}
+
+// how many nodes the solver does NOT update hold a value different from `fill`
+__global__ void count_offfill_kernel(const double *dense, double fill, int64_t n_nodes,
+                                     int64_t n_chunks, const uint32_t *bits,
+                                     unsigned long long *count)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_chunks) return;
+    const int64_t n = gw * 32 + lane;
+    const bool off = n < n_nodes && !((bits[gw] >> lane) & 1u) &&
+                     __double_as_longlong(dense[n]) != __double_as_longlong(fill);
+    const unsigned m = __ballot_sync(0xffffffffu, off);
+    if (lane == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
 __global__ void weights_pack_kernel(const double *aos, double *soa, int K, int64_t ld,
@@ -607,8 +623,32 @@ extern "C" int fwb_scatter_compact(const double *compact, double *dense, double 
     if (!dense || !compact || !chunk_bits || !chunk_base) { set_error("fwb_scatter_compact: bad argument"); return FWB_E_ARG; }
     const int64_t n_chunks = (n_nodes + 31) / 32;
     scatter_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
-        compact, dense, fill, n_nodes, n_chunks, chunk_bits, chunk_base);
+        compact, dense, fill, 0, n_nodes, n_chunks, chunk_bits, chunk_base);
     FWB_KERNEL_CHECK("scatter_kernel");
+    return 0;
+}
+
+extern "C" int fwb_scatter_compact_keep(const double *compact, double *dense, int64_t n_nodes,
+                                        const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                                        fwb_stream_t stream)
+{
+    if (!dense || !compact || !chunk_bits || !chunk_base) { set_error("fwb_scatter_compact_keep: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    scatter_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        compact, dense, 0.0, 1, n_nodes, n_chunks, chunk_bits, chunk_base);
+    FWB_KERNEL_CHECK("scatter_kernel");
+    return 0;
+}
+
+extern "C" int fwb_count_offfill(const double *dense, double fill, int64_t n_nodes,
+                                 const uint32_t *chunk_bits, unsigned long long *count,
+                                 fwb_stream_t stream)
+{
+    if (!dense || !chunk_bits || !count) { set_error("fwb_count_offfill: bad argument"); return FWB_E_ARG; }
+    const int64_t n_chunks = (n_nodes + 31) / 32;
+    count_offfill_kernel<<<warp_blocks(n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+        dense, fill, n_nodes, n_chunks, chunk_bits, count);
+    FWB_KERNEL_CHECK("count_offfill_kernel");
     return 0;
 }
 

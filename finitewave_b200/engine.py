@@ -92,6 +92,8 @@ class Engine:
         self.state = None        # [S, ld]
         self.ubuf = [None, None]
         self.staging = None
+        self._offfill = None
+        self.n_state = 0
         self._keep = []          # tensors borrowed by the C side (stims, trackers)
 
     # ---- tissue ---------------------------------------------------------
@@ -100,6 +102,7 @@ class Engine:
         first / last slice of the slowest axis is a ghost slice owned by a neighbour
         rank (its tissue feeds weights and stimuli, its nodes are never updated here)."""
         dev = self.device
+        self.destroy_sim()      # it borrows the index structures replaced below
         if isinstance(mesh, torch.Tensor):
             m = mesh.to(dev)
         else:
@@ -250,16 +253,42 @@ class Engine:
     def download_dense(self, which, host_out):
         _as_tensor(host_out).copy_(self.ubuf[which], non_blocking=True)
 
-    def upload_state(self, slot, host):
+    def upload_state(self, slot, host, fill=None):
+        """Dense host array -> compact device row.  With `fill`, also counts (on the
+        device) the non-updated nodes whose value differs from it, see off_fill()."""
         self._staging().copy_(_as_tensor(host), non_blocking=True)
         check(self.L.fwb_gather_compact(_ptr(self.staging), _ptr(self.state[slot]), self.n_nodes,
                                         _ptr(self.chunk_bits), _ptr(self.chunk_base), _stream()),
               "fwb_gather_compact")
+        if fill is not None:
+            if self._offfill is None or len(self._offfill) <= slot:
+                self._offfill = torch.zeros(max(self.n_state, slot + 1), dtype=torch.int64,
+                                            device=self.device)
+            self._offfill[slot] = 0
+            check(self.L.fwb_count_offfill(_ptr(self.staging), float(fill), self.n_nodes,
+                                           _ptr(self.chunk_bits), _ptr(self._offfill[slot:]),
+                                           _stream()), "fwb_count_offfill")
 
-    def download_state(self, slot, host_out, fill):
-        check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(self._staging()), float(fill),
-                                         self.n_nodes, _ptr(self.chunk_bits),
-                                         _ptr(self.chunk_base), _stream()), "fwb_scatter_compact")
+    def off_fill(self):
+        """Per state slot: number of non-updated nodes that do not hold the model's
+        init_* constant (after a StateLoader, a Command or a mesh edit).  Synchronises."""
+        return [] if self._offfill is None else self._offfill.cpu().tolist()
+
+    def download_state(self, slot, host_out, fill, keep=False):
+        """Compact device row -> dense host array.  keep=False refills the nodes the solver
+        does not update with `fill` (they cannot have changed); keep=True preserves the
+        values the host array holds there (one extra H2D of the array)."""
+        if keep:
+            self._staging().copy_(_as_tensor(host_out), non_blocking=True)
+            check(self.L.fwb_scatter_compact_keep(_ptr(self.state[slot]), _ptr(self.staging),
+                                                  self.n_nodes, _ptr(self.chunk_bits),
+                                                  _ptr(self.chunk_base), _stream()),
+                  "fwb_scatter_compact_keep")
+        else:
+            check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(self._staging()),
+                                             float(fill), self.n_nodes, _ptr(self.chunk_bits),
+                                             _ptr(self.chunk_base), _stream()),
+                  "fwb_scatter_compact")
         _as_tensor(host_out).copy_(self.staging, non_blocking=True)
         # staging is reused by the next call on the same stream: ordering is by stream
 

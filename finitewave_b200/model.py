@@ -129,16 +129,19 @@ class CardiacModel:
         if self.stencil is None:
             self.stencil = self.select_stencil(tissue)
         eng = self._engine_for(tissue)
-        old = (eng.n_myo, eng.ld)
+        if eng.sim:
+            # every index structure of the device simulation is about to be replaced
+            # (new mask -> new chunks, work list, compact order): keep what the native
+            # trackers sampled so far, drop the simulation object, rebuild on upload
+            if getattr(self, "_live", None):
+                self._collect_native()
+            eng.destroy_sim()
         eng.set_tissue(tissue.mesh, tissue.special_boundaries)
         w = self.stencil.compute_weights(self, tissue)
         if not isinstance(w, DeviceWeights):
             eng.set_weights_dense(np.asarray(w))
             w = DeviceWeights(eng)
         self.weights = w
-        if eng.sim and (eng.n_myo, eng.ld) != old:
-            # the node set changed under a live simulation: rebuild device state
-            self._mesh_changed = True
 
     def select_stencil(self, cardiac_tissue):
         iso, aniso = ((IsotropicStencil2D, AsymmetricStencil2D) if self._DIM == 2
@@ -163,14 +166,10 @@ class CardiacModel:
         """Push u, u_new and every state array from model.__dict__ to the device
         (creating / re-creating the device simulation when needed)."""
         eng = self._engine
-        recreate = (eng.state is None or getattr(self, "_mesh_changed", False)
-                    or eng.state.shape != (max(len(self._STATE), 1), eng.ld))
-        if recreate:
-            if eng.sim and getattr(self, "_live", None):
-                self._collect_native()          # keep what the trackers sampled so far
-            eng.allocate(len(self._STATE))
-            self._mesh_changed = False
+        if (eng.state is None or eng.ubuf[0] is None
+                or eng.state.shape != (max(len(self._STATE), 1), eng.ld)):
             eng.destroy_sim()
+            eng.allocate(len(self._STATE))
         if not eng.sim:
             eng.create_sim(_lib.MODEL_IDS[self._MODEL], self._param_vector(), self.dt)
             if getattr(self, "_live", None):
@@ -184,8 +183,11 @@ class CardiacModel:
         eng.upload_dense(cur, self._host_array("u"))
         eng.upload_dense(cur ^ 1, self._host_array("u_new"))
         for slot, name in enumerate(self._STATE):
-            eng.upload_state(slot, self._host_array(name))
+            eng.upload_state(slot, self._host_array(name), fill=getattr(self, "init_" + name))
         eng.synchronize()
+        # state rows only exist for updated nodes; where the host arrays hold something
+        # else than init_* on the other nodes, downloads must preserve it
+        self._keep_offnodes = [c != 0 for c in eng.off_fill()]
 
     def _register_native(self):
         """(Re-)register the built-in stimuli and trackers with the device runner."""
@@ -232,13 +234,16 @@ class CardiacModel:
                 host = np.empty(eng.shape, dtype=np.float64)
                 self.__dict__[name] = host
             eng.download_dense(which, host)
+        keep_flags = getattr(self, "_keep_offnodes", [])
         for slot, name in enumerate(self._STATE):
             host = self.__dict__[name]
+            keep = slot < len(keep_flags) and keep_flags[slot]
             if not (isinstance(host, np.ndarray) and host.dtype == np.float64
                     and host.flags.c_contiguous and host.shape == eng.shape):
-                host = np.empty(eng.shape, dtype=np.float64)
+                host = np.array(host, dtype=np.float64, order="C") if keep else \
+                    np.empty(eng.shape, dtype=np.float64)
                 self.__dict__[name] = host
-            eng.download_state(slot, host, getattr(self, "init_" + name))
+            eng.download_state(slot, host, getattr(self, "init_" + name), keep=keep)
         eng.synchronize()
 
     # ------------------------------------------------------------------ the loop

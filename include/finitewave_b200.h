@@ -141,6 +141,16 @@ FWB_API int fwb_gather_compact(const double *dense, double *compact, int64_t n_n
 FWB_API int fwb_scatter_compact(const double *compact, double *dense, double fill,
                         int64_t n_nodes, const uint32_t *chunk_bits,
                         const uint32_t *chunk_base, fwb_stream_t stream);
+/* scatter that leaves the nodes the solver does not update untouched (their values
+ * never change on the device; `dense` already holds them) */
+FWB_API int fwb_scatter_compact_keep(const double *compact, double *dense, int64_t n_nodes,
+                             const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                             fwb_stream_t stream);
+/* *count (device, caller-zeroed) += number of non-updated nodes whose value differs
+ * bitwise from `fill`: tells the host whether a later download may simply refill them */
+FWB_API int fwb_count_offfill(const double *dense, double fill, int64_t n_nodes,
+                      const uint32_t *chunk_bits, unsigned long long *count,
+                      fwb_stream_t stream);
 /* weights AoS dense (*shape, K) <-> compact SoA [K][ld] (user-supplied
  * Stencil results in, `model.weights` out) */
 FWB_API int fwb_weights_pack(const double *dense_aos, double *compact_soa, int K, int64_t ld,
