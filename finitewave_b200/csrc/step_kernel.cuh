@@ -150,6 +150,21 @@ struct StateIO {
     int64_t stride;
     __device__ __forceinline__ double ld(int q) const { return ld_stream(base + (int64_t)q * stride); }
     __device__ __forceinline__ void st(int q, double v) const { st_stream(base + (int64_t)q * stride, v); }
+    // pull every row this node will read towards the SM without holding registers: the
+    // models with many state arrays load them where they are used (register budget), and
+    // would otherwise pay the full HBM latency at each of those points
+    template <uint32_t MASK> __device__ __forceinline__ void prefetch() const
+    {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+            if ((MASK >> q) & 1u) {
+#ifdef FWB_PREFETCH_L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)q * stride));
+#else
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (int64_t)q * stride));
+#endif
+            }
+    }
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
@@ -212,6 +227,9 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
         const double *__restrict__ u = P.u + n;
         const double *__restrict__ w = P.w + c;
         const int64_t ld = g.ld;
+#ifndef FWB_NO_PREFETCH
+        if (M::NS > 4) StateIO{P.state + c, ld}.template prefetch<M::READ_MASK>();
+#endif
 
         // diffusion: issue the 2K loads, then the left-to-right sum in slot order
         // (no FMA contraction: -fmad=false)
