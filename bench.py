@@ -234,6 +234,32 @@ def e2e_host_api(workload, steps_per_call, calls, scale=1.0):
             "launches": launches}
 
 
+def e2e_slabs(sim, info, steps_per_call, calls, dist, device):
+    """N > 1: every rank round-trips its slab (u, u_new, all state arrays) through pinned
+    host memory around each run of `steps_per_call` steps; max over ranks."""
+    import torch
+    bufs = sim.host_buffers()
+    sim.download_host(bufs)
+    per_call = sum(b.numel() * 8 for b in bufs.values())
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        sim.upload_host(bufs)
+        sim.run(steps_per_call)
+        sim.download_host(bufs)
+    torch.cuda.synchronize()
+    sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    nm = torch.tensor([info["n_myo"]], dtype=torch.float64, device=device)
+    dist.all_reduce(nm, op=dist.ReduceOp.SUM)
+    return {"value": float(nm.item()) * steps_per_call * calls / float(sec.item()), "unit": UNIT,
+            "h2d_bytes_per_step": per_call, "d2h_bytes_per_step": per_call,
+            "steps_per_call": steps_per_call, "calls": calls,
+            "api": "finitewave_b200.devrun.DeviceSimulation upload_host -> run -> download_host "
+                   "per rank (bytes are per rank and call); one e2e step = one call"}
+
+
 def run_b200(args):
     import torch
     if not torch.cuda.is_available():
@@ -245,6 +271,8 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: keep NCCL's banner / debug output off it
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from finitewave_b200 import workloads
 
@@ -289,6 +317,12 @@ def run_b200(args):
                      "kernel": "fwb::step_kernel (fused diffusion + ionic + trackers)",
                      "kernel_ms": kernel_ms},
     }
+    if world > 1 and not args.no_e2e:
+        try:
+            e2e = e2e_slabs(sim, info, args.e2e_steps, 2, dist, device)
+        except Exception as e:
+            e2e = {"error": repr(e)}
+        line["e2e"] = e2e
     del sim
     torch.cuda.empty_cache()
 

@@ -189,6 +189,31 @@ class DeviceSimulation:
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "fwb_scatter_compact")
         return out.cpu().numpy()
 
+    # ---- host round trip of the whole state (slab-local, stored range) -----------
+    def host_buffers(self):
+        """Pinned host arrays for download_host / upload_host: u, u_new and every state
+        variable over this simulation's stored range."""
+        from .engine import pinned_empty
+        return {name: pinned_empty(self.shape) for name in ["u", "u_new"] + self.state_names}
+
+    def download_host(self, bufs):
+        eng = self.engine
+        cur = eng.current()
+        bufs["u"].copy_(eng.ubuf[cur], non_blocking=True)
+        bufs["u_new"].copy_(eng.ubuf[cur ^ 1], non_blocking=True)
+        for slot, name in enumerate(self.state_names):
+            eng.download_state(slot, bufs[name], getattr(self.model, "init_" + name))
+        eng.synchronize()
+
+    def upload_host(self, bufs):
+        eng = self.engine
+        cur = eng.current()
+        eng.ubuf[cur].copy_(bufs["u"], non_blocking=True)
+        eng.ubuf[cur ^ 1].copy_(bufs["u_new"], non_blocking=True)
+        for slot, name in enumerate(self.state_names):
+            eng.upload_state(slot, bufs[name])
+        eng.synchronize()
+
     def collect(self):
         self.engine.synchronize()
         for tr in self.trackers:
