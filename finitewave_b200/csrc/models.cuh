@@ -213,6 +213,76 @@ template <> struct Model<FWB_MODEL_FENTON_KARMA> {
 };
 
 // ---------------------------------------------------------------------------
+// Bueno-Orovio minimal ventricular model -- cpuwave2D/model/bueno_orovio_2d.py:183-433
+// (point functions), :435-475 (ionic_kernel_2d); bueno_orovio_3d.py.  SURVEY 8f row f1.
+// state: v, w, s.  Time constants chosen by a threshold are pre-inverted pairs.
+// ---------------------------------------------------------------------------
+template <> struct Model<FWB_MODEL_BUENO_OROVIO> {
+    static constexpr int NS = 3, NP = 28, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = true;
+    static constexpr uint32_t READ_MASK = 0x7, WRITE_MASK = 0x7;
+    struct Consts {
+        double dt, u_o, u_u, theta_v, theta_w, theta_v_m, theta_o;
+        double tau_w1_m, tau_w21_m, k_w_m, u_w_m, tau_so1, tau_so21, k_so, u_so, k_s, u_s, w_inf_;
+        DivC tau_v1_m, tau_v2_m, tau_v_p, tau_w_p, tau_fi, tau_o1, tau_o2, tau_s1, tau_s2,
+            tau_si, tau_w_inf;
+    };
+    static bool derive(const double *p, double dt, Consts &c)
+    {
+        c.dt = dt; c.u_o = p[0]; c.u_u = p[1]; c.theta_v = p[2]; c.theta_w = p[3];
+        c.theta_v_m = p[4]; c.theta_o = p[5];
+        c.tau_v1_m = make_divc(p[6]); c.tau_v2_m = make_divc(p[7]); c.tau_v_p = make_divc(p[8]);
+        c.tau_w1_m = p[9]; c.tau_w21_m = p[10] - p[9]; c.k_w_m = p[11]; c.u_w_m = p[12];
+        c.tau_w_p = make_divc(p[13]); c.tau_fi = make_divc(p[14]);
+        c.tau_o1 = make_divc(p[15]); c.tau_o2 = make_divc(p[16]);
+        c.tau_so1 = p[17]; c.tau_so21 = p[18] - p[17]; c.k_so = p[19]; c.u_so = p[20];
+        c.tau_s1 = make_divc(p[21]); c.tau_s2 = make_divc(p[22]); c.k_s = p[23]; c.u_s = p[24];
+        c.tau_si = make_divc(p[25]); c.tau_w_inf = make_divc(p[26]); c.w_inf_ = p[27];
+        return divc_ok(c.tau_v1_m) && divc_ok(c.tau_v2_m) && divc_ok(c.tau_v_p) &&
+               divc_ok(c.tau_w_p) && divc_ok(c.tau_fi) && divc_ok(c.tau_o1) && divc_ok(c.tau_o2) &&
+               divc_ok(c.tau_s1) && divc_ok(c.tau_s2) && divc_ok(c.tau_si) && divc_ok(c.tau_w_inf);
+    }
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
+    {
+        const double dt = c.dt;
+        // calc_v :183-213 (calc_v_inf :411-421, calc_tau_v_m :330-345)
+        const double v_inf = (u < c.theta_v_m) ? 1.0 : 0.0;
+        double v = io.ld(0);
+        {
+            const double num = v_inf - v;
+            const double below = ((u - c.theta_v_m) < 0) ? divc(num, c.tau_v1_m) : divc(num, c.tau_v2_m);
+            v += dt * (((u - c.theta_v) < 0) ? below : divc(-v, c.tau_v_p));
+        }
+        io.st(0, v);
+        // calc_w :216-246 (calc_w_inf :424-433, calc_tau_w_m :348-362)
+        const double w_inf = ((u - c.theta_o) < 0) ? 1 - divc(u, c.tau_w_inf) : c.w_inf_;
+        const double tau_w_m = c.tau_w1_m + c.tau_w21_m * (1 + tanh(c.k_w_m * (u - c.u_w_m))) * 0.5;
+        double w = io.ld(1);
+        w += dt * (((u - c.theta_w) < 0) ? (w_inf - w) / tau_w_m : divc(-w, c.tau_w_p));
+        io.st(1, w);
+        // calc_s :249-270 (calc_tau_s :381-393)
+        double s = io.ld(2);
+        {
+            const double num = dt * ((1 + tanh(c.k_s * (u - c.u_s))) * 0.5 - s);
+            s += ((u - c.theta_w) < 0) ? divc(num, c.tau_s1) : divc(num, c.tau_s2);
+        }
+        io.st(2, s);
+        // calc_Jfi :273-289, calc_Jso :292-310 (calc_tau_o :396-408, calc_tau_so :365-378),
+        // calc_Jsi :313-327
+        const double Hv = ((u - c.theta_v) >= 0) ? 1.0 : 0.0;
+        const double Hw = ((u - c.theta_w) >= 0) ? 1.0 : 0.0;
+        const double J_fi = divc(-v * Hv * (u - c.theta_v) * (c.u_u - u), c.tau_fi);
+        const double tau_so = c.tau_so1 + c.tau_so21 * (1 + tanh(c.k_so * (u - c.u_so))) * 0.5;
+        const double o_num = (u - c.u_o) * (1 - Hw);
+        const double J_so = (((u - c.theta_o) < 0) ? divc(o_num, c.tau_o1) : divc(o_num, c.tau_o2)) +
+                            Hw / tau_so;
+        const double J_si = divc(-Hw * w * s, c.tau_si);
+        un += dt * (-J_fi - J_so - J_si);
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Luo-Rudy 1991 -- cpuwave2D/model/luo_rudy91_2d.py:158-443, :446-510;
 // luo_rudy91_3d.py:63-132.  Gates are forward Euler (calc_gating_var :158-182),
 // I_Na uses the new m,h,j, I_si the old d,f, I_K the old x.

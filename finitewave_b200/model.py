@@ -459,6 +459,34 @@ class FentonKarma2D(CardiacModel):
         self.init_u, self.init_v, self.init_w = 0.0, 1.0, 1.0
 
 
+class BuenoOrovio2D(CardiacModel):
+    """bueno_orovio_2d.py:13-181 (minimal ventricular model)"""
+    _MODEL, _DIM = "bueno_orovio", 2
+    _PARAMS = ("u_o", "u_u", "theta_v", "theta_w", "theta_v_m", "theta_o", "tau_v1_m",
+               "tau_v2_m", "tau_v_p", "tau_w1_m", "tau_w2_m", "k_w_m", "u_w_m", "tau_w_p",
+               "tau_fi", "tau_o1", "tau_o2", "tau_so1", "tau_so2", "k_so", "u_so", "tau_s1",
+               "tau_s2", "k_s", "u_s", "tau_si", "tau_w_inf", "w_inf_")
+    _STATE = ("v", "w", "s")
+
+    def __init__(self):
+        super().__init__()
+        self.v = np.ndarray
+        self.w = np.ndarray
+        self.s = np.ndarray
+        self.D_model = 1.
+        self.state_vars = ["u", "v", "w", "s"]
+        self.npfloat = 'float64'
+        self.u_o, self.u_u = 0.0, 1.55
+        self.theta_v, self.theta_w, self.theta_v_m, self.theta_o = 0.3, 0.13, 0.006, 0.006
+        self.tau_v1_m, self.tau_v2_m, self.tau_v_p = 60, 1150, 1.4506
+        self.tau_w1_m, self.tau_w2_m, self.k_w_m, self.u_w_m, self.tau_w_p = 60, 15, 65, 0.03, 200
+        self.tau_fi, self.tau_o1, self.tau_o2 = 0.11, 400, 6
+        self.tau_so1, self.tau_so2, self.k_so, self.u_so = 30.0181, 0.9957, 2.0458, 0.65
+        self.tau_s1, self.tau_s2, self.k_s, self.u_s = 2.7342, 16, 2.0994, 0.9087
+        self.tau_si, self.tau_w_inf, self.w_inf_ = 1.8875, 0.07, 0.94
+        self.init_u, self.init_v, self.init_w, self.init_s = 0.0, 1.0, 1.0, 0.0
+
+
 class LuoRudy912D(CardiacModel):
     """luo_rudy91_2d.py:12-156"""
     _MODEL, _DIM = "luo_rudy91", 2
@@ -537,5 +565,6 @@ AlievPanfilov3D = _as_3d(AlievPanfilov2D, "AlievPanfilov3D")
 Barkley3D = _as_3d(Barkley2D, "Barkley3D")
 MitchellSchaeffer3D = _as_3d(MitchellSchaeffer2D, "MitchellSchaeffer3D")
 FentonKarma3D = _as_3d(FentonKarma2D, "FentonKarma3D")
+BuenoOrovio3D = _as_3d(BuenoOrovio2D, "BuenoOrovio3D")
 LuoRudy913D = _as_3d(LuoRudy912D, "LuoRudy913D")
 TP063D = _as_3d(TP062D, "TP063D")

@@ -22,6 +22,7 @@ MODEL_CLASS = {
     "barkley": "Barkley",
     "mitchell_schaeffer": "MitchellSchaeffer",
     "fenton_karma": "FentonKarma",
+    "bueno_orovio": "BuenoOrovio",
     "luo_rudy91": "LuoRudy91",
     "tp06": "TP06",
 }
@@ -31,6 +32,7 @@ STATE_VARS = {
     "barkley": ["u", "v"],
     "mitchell_schaeffer": ["u", "h"],
     "fenton_karma": ["u", "v", "w"],
+    "bueno_orovio": ["u", "v", "w", "s"],
     "luo_rudy91": ["u", "m", "h", "j", "d", "f", "x", "cai"],
     "tp06": ["u", "cai", "casr", "cass", "nai", "Ki", "m", "h", "j", "xr1", "xr2",
              "xs", "r", "s", "d", "f", "f2", "fcass", "rr", "oo"],
@@ -236,6 +238,23 @@ def make_cases():
         stims=[dict(kind="current_coord", t=0, value=100, duration=1,
                     box=[1, 3, 1, 4, 1, 4])],
         trackers=[dict(kind="action_potential", cell_ind=[4, 2, 2], step=1)]))
+
+    # Bueno-Orovio 2D iso, current stimulus (test_models_2d.py protocol) + spiral S2
+    cases.append(dict(
+        name="bo2d_iso_current", model="bueno_orovio", shape=[40, 30],
+        dt=0.01, dr=0.25, t_max=10,
+        stims=[dict(kind="current_coord", t=0, value=5, duration=0.5, box=[0, 4, 0, 30]),
+               dict(kind="voltage_coord", t=6, value=1, box=[0, 20, 0, 30])],
+        trackers=[dict(kind="multi_variable", cell_ind=[20, 15], step=5, vars=["u", "v", "w", "s"])]))
+
+    # Bueno-Orovio 3D aniso + fibrosis, non-default parameter
+    cases.append(dict(
+        name="bo3d_aniso_fib", model="bueno_orovio", shape=[14, 12, 10],
+        dt=0.01, dr=0.25, t_max=8, params=dict(tau_si=2.0),
+        mesh=random_fibrosis([14, 12, 10], 0.2, 12),
+        fibers=rotating_fibers_3d([14, 12, 10]),
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 4, 0, 12, 0, 10])],
+        trackers=[dict(kind="activation_time", threshold=0.3, step=1)]))
 
     # AP 2D aniso, non-default parameters and initial conditions
     cases.append(dict(

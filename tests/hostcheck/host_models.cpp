@@ -45,6 +45,7 @@ int fwb_host_ionic(int model, double *u_new, const double *u, double *const *st,
     case FWB_MODEL_FENTON_KARMA: run<FWB_MODEL_FENTON_KARMA>(u_new, u, st, n, dt, p); return 0;
     case FWB_MODEL_LUO_RUDY91: run<FWB_MODEL_LUO_RUDY91>(u_new, u, st, n, dt, p); return 0;
     case FWB_MODEL_TP06: run<FWB_MODEL_TP06>(u_new, u, st, n, dt, p); return 0;
+    case FWB_MODEL_BUENO_OROVIO: run<FWB_MODEL_BUENO_OROVIO>(u_new, u, st, n, dt, p); return 0;
     }
     return -1;
 }

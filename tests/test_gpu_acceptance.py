@@ -67,6 +67,7 @@ MODELS = [("AlievPanfilov", 5, 0.5, 80, 60, (1.0, 0.1), (0.0, 0.01), 0.1, (20, 2
           ("Barkley", 5, 0.1, 80, 60, (1.0, 0.1), (0.0, 0.01), 0.1, (1, 4)),
           ("MitchellSchaeffer", 5, 0.5, 1000, 1000, (0.95, 0.1), (0.0, 0.01), 0.1, (250, 350)),
           ("FentonKarma", 5, 0.5, 1000, 1000, (1.0, 0.1), (0.0, 0.01), 0.1, (100, 200)),
+          ("BuenoOrovio", 5, 0.5, 1000, 1000, (1.4, 0.1), (0.0, 0.01), 0.1, (200, 300)),
           ("LuoRudy91", 100, 1, 1000, 1000, None, None, -70, (350, 400)),
           ("TP06", 100, 1, 1000, 1000, None, None, -70, (280, 320))]
 

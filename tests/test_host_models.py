@@ -21,7 +21,7 @@ ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "tests" / "hostcheck" / "host_models.cpp"
 SO = ROOT / "tests" / "hostcheck" / "libhost_models.so"
 MODEL_IDS = {"aliev_panfilov": 0, "barkley": 1, "mitchell_schaeffer": 2, "fenton_karma": 3,
-             "luo_rudy91": 4, "tp06": 5}
+             "luo_rudy91": 4, "tp06": 5, "bueno_orovio": 6}
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -45,7 +45,8 @@ def _random_node_states(model, n, rng):
         u[: n // 8] = rng.uniform(-41.0, -39.0, n // 8)     # around the h/j branch
     else:
         u = rng.uniform(-0.1, 1.1, n)
-        u[: n // 8] = rng.uniform(0.12, 0.14, n // 8)       # around u_gate / u_c
+        u[: n // 8] = rng.uniform(0.12, 0.14, n // 8)       # around u_gate / u_c / theta_w
+        u[n // 8: n // 4] = rng.uniform(0.0, 0.012, n // 8)  # around theta_o / theta_v_m
     states = []
     for name in spec["state"]:
         init = spec["init"][name]
@@ -100,7 +101,7 @@ def test_param_order_matches_oracle_tables():
     finitewave_b200.model must be the oracle's (= the reference's kernel call order)."""
     from finitewave_b200 import model as m
     for cls in (m.AlievPanfilov2D, m.Barkley2D, m.MitchellSchaeffer2D, m.FentonKarma2D,
-                m.LuoRudy912D, m.TP062D):
+                m.BuenoOrovio2D, m.LuoRudy912D, m.TP062D):
         spec = oracle.MODELS[cls._MODEL]
         assert list(cls._PARAMS) == list(spec["params"]), cls.__name__
         assert list(cls._STATE) == list(spec["state"]), cls.__name__
