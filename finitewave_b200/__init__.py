@@ -13,7 +13,7 @@ entry raises ``FwbError``.
 from ._lib import FwbError
 from .hooks import Command, CommandSequence, StateLoader, StateSaver, StateSaverCollection
 from .model import (AlievPanfilov2D, AlievPanfilov3D, Barkley2D, Barkley3D, BuenoOrovio2D,
-                    BuenoOrovio3D, CardiacModel,
+                    BuenoOrovio3D, CardiacModel, Courtemanche2D, Courtemanche3D,
                     FentonKarma2D, FentonKarma3D, LuoRudy912D, LuoRudy913D,
                     MitchellSchaeffer2D, MitchellSchaeffer3D, TP062D, TP063D)
 from .stencil import (AsymmetricStencil2D, AsymmetricStencil3D, IsotropicStencil2D,

@@ -20,7 +20,7 @@ BUILD = PKG / "_build"
 LIB = PKG / "libfinitewave_b200.so"
 
 SOURCES = ["sim.cu", "aux_kernels.cu", "weights.cu", "halo.cu", "step_nomodel.cu", "step_ap.cu",
-           "step_barkley.cu", "step_ms.cu", "step_fk.cu", "step_bo.cu", "step_lr91.cu", "step_tp06.cu"]
+           "step_barkley.cu", "step_ms.cu", "step_fk.cu", "step_bo.cu", "step_lr91.cu", "step_tp06.cu", "step_court.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -12,7 +12,7 @@ namespace fwb {
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 constexpr int MAX_PARAMS = 64;
-constexpr int MAX_STATE = 19;
+constexpr int MAX_STATE = 21;
 
 // thread-local last error (fwb_last_error)
 void set_error(const char *fmt, ...);

@@ -49,12 +49,14 @@ namespace fwb {
 //   eu(x)  exp of an affine function of u   (|x| < 700 follows from |u| < 300)
 //   en(x)  exp of a non-positive, state-dependent argument (Rush-Larsen factors)
 //   ec(x)  exp of any state-dependent argument
-//   dv(a, b)  a / b for b = 1 + exp(.)
+//   dv(a, b)  a / b for b = const + exp(.) >= ~1e-2 (normal, with a normal reciprocal)
+//   p15(x)    x^1.5
 struct LibMath {
     FWB_HD static double eu(double x) { return exp(x); }
     FWB_HD static double en(double x) { return exp(x); }
     FWB_HD static double ec(double x) { return exp(x); }
     FWB_HD static double dv(double a, double b) { return a / b; }
+    FWB_HD static double p15(double x) { return pow(x, 1.5); }
 };
 struct FastMath {
     FWB_HD static double eu(double x) { return fexp(x); }
@@ -66,6 +68,7 @@ struct FastMath {
         const double q = a * y;
         return fma(fma(-b, q, a), y, q);
     }
+    FWB_HD static double p15(double x) { return x * sqrt(x); }   // x^1.5, x > 0
 };
 constexpr double FAST_MATH_U_LIMIT = 300.0;
 
@@ -649,6 +652,220 @@ template <> struct Model<FWB_MODEL_TP06> {
             io.st(2, (sqrt(bcss * bcss + 4 * ccss) - bcss) * 0.5);   // == / 2
         }
         // calc_cai :875-925 is dead: cai keeps its old value (:1098)
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Courtemanche 1998 human atrial model -- cpuwave2D/model/courtemanche_2d.py:180-567
+// (point functions), :569-641 (kernel); courtemanche_3d.py:60-163.  SURVEY 8f row f1.
+// state slots (model.state_vars without u):
+//   0 nai 1 ki 2 cai 3 caup 4 carel 5 m 6 h 7 j_ 8 d 9 f 10 oa 11 oi 12 ua 13 ui
+//   14 xr 15 xs 16 fca 17 irel 18 vrel 19 urel 20 wrel
+// Reference quirks kept: the kernel's xs/xr parameters are bound to model.xr/model.xs
+// (slot 14 is the I_Ks gate, slot 15 the I_Kr gate); calc_ikr ignores the gkr parameter.
+// ---------------------------------------------------------------------------
+template <> struct Model<FWB_MODEL_COURTEMANCHE> {
+    static constexpr int NS = 21, NP = 39, MIN_BLOCKS = 4;
+    static constexpr bool USE_TMA = false;
+    static constexpr uint32_t READ_MASK = 0x1fffff, WRITE_MASK = 0x1fffff;
+    struct Consts {
+        double dt, gna, gnab, gk1, gks, gto, gcal, gcab, gkur_coeff, F, ibk, cao, nao, ko;
+        double RT_F, RT_2F, kq10, kmnai, ko_kmko, inakmax, nak_s, inacamax, nao3, ncx_t12, ksatncx;
+        double ipcamax, krel, iupmax, kup, Vrel, Vup, Vrel_Vup, Fn_a, Fn_b;
+        double trpn_k, kmtrpn, cmdn_k, kmcmdn, csqn_k, kmcsqn;
+        DivC RT, caupmax, FVj, FVj2, Vj;
+    };
+    static bool derive(const double *p, double dt, Consts &c)
+    {
+        const double F = p[9], T = p[10], R = p[11], Vj = p[13], Vup = p[14], Vrel = p[15],
+                     nao = p[18], ko = p[19], kmko = p[23], kmnancx = p[24], kmcancx = p[25];
+        c.dt = dt; c.gna = p[0]; c.gnab = p[1]; c.gk1 = p[2]; c.gks = p[4]; c.gto = p[5];
+        c.gcal = p[6]; c.gcab = p[7]; c.gkur_coeff = p[8]; c.F = F; c.ibk = p[16];
+        c.cao = p[17]; c.nao = nao; c.ko = ko;
+        c.RT_F = R * T / F; c.RT_2F = R * T / (2 * F); c.RT = make_divc(R * T);
+        c.kq10 = p[38]; c.kmnai = p[22]; c.ko_kmko = ko / (ko + kmko); c.inakmax = p[34];
+        c.nak_s = (1 / 7.0) * (exp(nao / 67.3) - 1);
+        c.inacamax = p[33]; c.nao3 = nao * (nao * nao);
+        c.ncx_t12 = ((kmnancx * (kmnancx * kmnancx)) + c.nao3) * (kmcancx + p[17]);
+        c.ksatncx = p[26];
+        c.ipcamax = p[35]; c.krel = p[36]; c.iupmax = p[37]; c.kup = p[21];
+        c.Vrel = Vrel; c.Vup = Vup; c.Vrel_Vup = Vrel / Vup;
+        c.Fn_a = 1e-12 * Vrel; c.Fn_b = (5 * 1e-13) / F;
+        c.trpn_k = p[30] * p[28]; c.kmtrpn = p[28]; c.cmdn_k = p[31] * p[27]; c.kmcmdn = p[27];
+        c.csqn_k = p[32] * p[29]; c.kmcsqn = p[29];
+        c.caupmax = make_divc(p[20]); c.FVj = make_divc(F * Vj); c.FVj2 = make_divc(2 * F * Vj);
+        c.Vj = make_divc(Vj);
+        return divc_ok(c.RT) && divc_ok(c.caupmax) && divc_ok(c.FVj) && divc_ok(c.FVj2) &&
+               divc_ok(c.Vj);
+    }
+    // calc_gating_variable :187-189
+    template <class E> FWB_HD static double gate(double x, double x_inf, double tau_x, double dt)
+    {
+        return x_inf - (x_inf - x) * E::en(-dt / tau_x);
+    }
+    template <class IO>
+    FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
+    {
+#ifdef __CUDA_ARCH__
+        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
+        else
+#endif
+            ionic_impl<IO, LibMath>(u, un, io, c);
+    }
+    template <class IO, class E>
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
+    {
+        const double dt = c.dt;
+        const double nai = io.ld(0), ki = io.ld(1), cai = io.ld(2);
+        // calc_equilibrum_potentials :246-251
+        const double ena = c.RT_F * log(c.nao / nai);
+        const double ek = c.RT_F * log(c.ko / ki);
+        const double eca = c.RT_2F * log(c.cao / cai);
+        // calc_gating_m :259-271, calc_gating_h :274-285, calc_gating_j :288-299, calc_ina :254
+        double ina;
+        {
+            double am;
+            if (u == -47.13) am = 3.2;
+            else am = 0.32 * (u + 47.13) / (1 - E::eu(-0.1 * (u + 47.13)));
+            const double bm = 0.08 * E::eu(FWB_DIVK(-u, 11.));
+            const double m = gate<E>(io.ld(5), am / (am + bm), 1 / (am + bm), dt);
+            double ah, bh, aj, bj;
+            if (u >= -40) {
+                ah = 0;
+                bh = E::dv(1., 0.13 * (1 + E::eu(FWB_DIVK(-(u + 10.66), 11.1))));
+                aj = 0;
+                bj = E::dv(0.3 * E::eu(-0.0000002535 * u), 1 + E::eu(-0.1 * (u + 32)));
+            } else {
+                ah = 0.135 * E::eu(FWB_DIVK(-(80 + u), 6.8));
+                bh = 3.56 * E::eu(0.079 * u) + 310000 * E::eu(0.35 * u);
+                aj = E::dv((-127140 * E::eu(0.2444 * u) - 0.00003474 * E::eu(-0.04391 * u)) *
+                               (u + 37.78),
+                           1 + E::eu(0.311 * (u + 79.23)));
+                bj = E::dv(0.1212 * E::eu(-0.01052 * u), 1 + E::eu(-0.1378 * (u + 40.14)));
+            }
+            const double h = gate<E>(io.ld(6), ah / (ah + bh), 1 / (ah + bh), dt);
+            const double j_inf = aj / (aj + bj), tau_j = 1 / (aj + bj);
+            const double j = j_inf - (j_inf - io.ld(7)) * E::en(-dt / tau_j);
+            io.st(5, m); io.st(6, h); io.st(7, j);
+            ina = c.gna * (m * (m * m)) * h * j * (u - ena);
+        }
+        const double ik1 = c.gk1 * (u - ek) / (1 + E::eu(0.07 * (u + 80)));   // :302-304
+        // calc_ito :307-325 and calc_ikur :328-347 (share ao/bo)
+        double ito, ikur;
+        {
+            const double ao = E::dv(0.65, E::eu(FWB_DIVK(-(u + 10), 8.5)) + E::eu(FWB_DIVK(-(u - 30), 59.0)));
+            const double bo = E::dv(0.65, 2.5 + E::eu(FWB_DIVK(u + 82, 17.0)));
+            const double tau_o = 1 / (c.kq10 * (ao + bo));
+            const double o_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 20.47), 17.54)));
+            const double aoi = E::dv(1., 18.53 + E::eu(FWB_DIVK(u + 113.7, 10.95)));
+            const double boi = E::dv(1., 35.56 + E::eu(FWB_DIVK(-(u + 1.26), 7.44)));
+            const double tau_oi = 1 / (c.kq10 * (aoi + boi));
+            const double oi_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u + 43.1, 5.3)));
+            const double oa = gate<E>(io.ld(10), o_inf, tau_o, dt);
+            const double oi = gate<E>(io.ld(11), oi_inf, tau_oi, dt);
+            io.st(10, oa); io.st(11, oi);
+            ito = c.gto * (oa * (oa * oa)) * oi * (u - ek);
+
+            const double gkur = 0.005 + E::dv(0.05, 1 + E::eu(FWB_DIVK(-(u - 15), 13.0)));
+            const double tau_ua = tau_o;           // aua == ao, bua == bo (:330-332)
+            const double ua_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 30.3), 9.6)));
+            const double aui = E::dv(1., 21 + E::eu(FWB_DIVK(-(u - 185), 28.0)));
+            const double bui = E::eu(FWB_DIVK(u - 158, 16.0));
+            const double tau_ui = 1 / (c.kq10 * (aui + bui));
+            const double ui_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u - 99.45, 27.48)));
+            const double ua = gate<E>(io.ld(12), ua_inf, tau_ua, dt);
+            const double ui = gate<E>(io.ld(13), ui_inf, tau_ui, dt);
+            io.st(12, ua); io.st(13, ui);
+            ikur = c.gkur_coeff * gkur * (ua * (ua * ua)) * ui * (u - ek);
+        }
+        // calc_ikr :350-362 -- gate stored in slot 15 (model.xs), gkr fixed at 0.0294
+        double ikr;
+        {
+            const double axr = 0.0003 * (u + 14.1) / (1 - E::eu(FWB_DIVK(-(u + 14.1), 5.)));
+            const double bxr = 0.000073898 * (u - 3.3328) / (E::eu(FWB_DIVK(u - 3.3328, 5.1237)) - 1);
+            const double tau_xr = 1 / (axr + bxr);
+            const double xr_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 14.1), 6.5)));
+            const double xr = gate<E>(io.ld(15), xr_inf, tau_xr, dt);
+            io.st(15, xr);
+            ikr = E::dv(0.0294 * xr * (u - ek), 1 + E::eu(FWB_DIVK(u + 15, 22.4)));
+        }
+        // calc_iks :365-376 -- gate stored in slot 14 (model.xr)
+        double iks;
+        {
+            const double axs = 0.00004 * (u - 19.9) / (1 - E::eu(FWB_DIVK(-(u - 19.9), 17.)));
+            const double bxs = 0.000035 * (u - 19.9) / (E::eu(FWB_DIVK(u - 19.9, 9.)) - 1);
+            const double tau_xs = 1 / (2 * (axs + bxs));
+            const double xs_inf = 1 / sqrt(1 + E::eu(FWB_DIVK(-(u - 19.9), 12.7)));
+            const double xs = gate<E>(io.ld(14), xs_inf, tau_xs, dt);
+            io.st(14, xs);
+            iks = c.gks * (xs * xs) * (u - ek);
+        }
+        // calc_ical :379-396
+        double ical;
+        {
+            const double e10 = E::eu(FWB_DIVK(-(u + 10), 6.24));
+            const double tau_d = (1 - e10) / (0.035 * (u + 10) * (1 + e10));
+            const double d_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 10), 8.0)));
+            const double tau_f = 9 / (0.0197 * E::eu(-(0.0337 * 0.0337) * ((u + 10) * (u + 10))) + 0.02);
+            const double f_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u + 28, 6.9)));
+            const double fca_inf = 1 / (1 + FWB_DIVK(cai, 0.00035));
+            const double d = gate<E>(io.ld(8), d_inf, tau_d, dt);
+            const double f = gate<E>(io.ld(9), f_inf, tau_f, dt);
+            const double fca = gate<E>(io.ld(16), fca_inf, 2, dt);
+            io.st(8, d); io.st(9, f); io.st(16, fca);
+            ical = c.gcal * d * f * fca * (u - 65);
+        }
+        // calc_inak :399-404, calc_inaca :407-423
+        const double Fu = c.F * u;
+        const double fnak = 1 / (1 + 0.1245 * E::eu(divc(-0.1 * Fu, c.RT)) +
+                                 0.0365 * c.nak_s * E::eu(divc(-Fu, c.RT)));
+        const double inak = c.inakmax * fnak * (1 / (1 + E::p15(c.kmnai / nai))) * c.ko_kmko;
+        double inaca;
+        {
+            const double exp_term = E::eu(divc(0.35 * Fu, c.RT));
+            const double exp_rev_term = E::eu(divc((0.35 - 1) * Fu, c.RT));
+            const double numerator = c.inacamax * (exp_term * (nai * (nai * nai)) * c.cao -
+                                                   exp_rev_term * c.nao3 * cai);
+            inaca = numerator / (c.ncx_t12 * (1 + c.ksatncx * exp_rev_term));
+        }
+        const double ibca = c.gcab * (u - eca);               // :426-428
+        const double ibna = c.gnab * (u - ena);               // :431-433
+        const double ipca = c.ipcamax * cai / (cai + 0.0005); // :436-438
+        // membrane potential and the two concentrations that need no SR fluxes
+        un -= dt * (ina + ik1 + ito + ikur + ikr + iks + ical + ipca + inak + inaca + ibna + ibca);
+        io.st(0, nai + dt * divc(-3 * inak - 3 * inaca - ibna - ina, c.FVj));               // :207-210
+        io.st(1, ki + dt * divc(2 * inak - ik1 - ito - ikur - ikr - iks - c.ibk, c.FVj));    // :213-216
+        // calc_irel :441-462
+        const double caup = io.ld(3), carel = io.ld(4);
+        double irel;
+        {
+            const double Fn = c.Fn_a * io.ld(17) - c.Fn_b * (0.5 * ical - 0.2 * inaca);
+            const double eFn = E::ec(FWB_DIVK(-(Fn - 3.4175e-13), 13.67e-16));
+            const double u_inf = 1 / (1 + eFn);
+            const double tau_v = 1.91 + 2.09 / (1 + eFn);
+            const double v_inf = 1 - 1 / (1 + E::ec(FWB_DIVK(-(Fn - 6.835e-14), 13.67e-16)));
+            const double e79 = E::eu(FWB_DIVK(-(u - 7.9), 5.0));
+            const double tau_w = 6 * (1 - e79) / ((1 + 0.3 * e79) * (u - 7.9));
+            const double w_inf = 1 - E::dv(1., 1 + E::eu(FWB_DIVK(-(u - 40), 17.0)));
+            const double urel = gate<E>(io.ld(19), u_inf, 8, dt);
+            const double vrel = gate<E>(io.ld(18), v_inf, tau_v, dt);
+            const double wrel = gate<E>(io.ld(20), w_inf, tau_w, dt);
+            irel = c.krel * (urel * urel) * vrel * wrel * (carel - cai);
+            io.st(17, irel); io.st(19, urel); io.st(18, vrel); io.st(20, wrel);
+        }
+        const double itr = FWB_DIVK(caup - carel, 180.);       // :465-468
+        const double iup = c.iupmax / (1 + (c.kup / cai));     // :471-473
+        const double iupleak = divc(caup, c.caupmax) * c.iupmax;   // :476-478
+        io.st(3, caup + dt * (iup - iupleak - itr * c.Vrel_Vup));                           // :226-229
+        {
+            const double B1 = divc(2 * inaca - ipca - ical - ibca, c.FVj2) +
+                              divc(c.Vup * (iupleak - iup) + irel * c.Vrel, c.Vj);
+            const double B2 = 1 + c.trpn_k / ((cai + c.kmtrpn) * (cai + c.kmtrpn)) +
+                              c.cmdn_k / ((cai + c.kmcmdn) * (cai + c.kmcmdn));
+            io.st(2, cai + dt * (B1 / B2));                                                  // :219-224
+        }
+        io.st(4, carel + dt * ((itr - irel) /
+                               (1 + c.csqn_k / ((carel + c.kmcsqn) * (carel + c.kmcsqn)))));  // :232-235
     }
 };
 

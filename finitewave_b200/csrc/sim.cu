@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char *what)
 }
 
 extern const ModelEntry g_entry_aliev_panfilov, g_entry_barkley, g_entry_mitchell_schaeffer,
-    g_entry_fenton_karma, g_entry_luo_rudy91, g_entry_tp06, g_entry_bueno_orovio, g_entry_nomodel;
+    g_entry_fenton_karma, g_entry_luo_rudy91, g_entry_tp06, g_entry_bueno_orovio, g_entry_courtemanche, g_entry_nomodel;
 
 const ModelEntry *model_entry(int model)
 {
@@ -47,6 +47,7 @@ const ModelEntry *model_entry(int model)
     case FWB_MODEL_LUO_RUDY91: return &g_entry_luo_rudy91;
     case FWB_MODEL_TP06: return &g_entry_tp06;
     case FWB_MODEL_BUENO_OROVIO: return &g_entry_bueno_orovio;
+    case FWB_MODEL_COURTEMANCHE: return &g_entry_courtemanche;
     case FWB_N_MODELS: return &g_entry_nomodel;
     default: return nullptr;
     }

@@ -72,7 +72,7 @@ class DeviceSimulation:
         eng.ubuf[0].fill_(float(model.init_u))
         eng.ubuf[1].fill_(float(model.init_u) if model._INIT_U_NEW else 0.0)
         for slot, name in enumerate(self.state_names):
-            eng.fill_state(slot, getattr(model, "init_" + name))
+            eng.fill_state(slot, model._init_value(name))
         eng.create_sim(_lib.MODEL_IDS[model._MODEL], model._param_vector(), self.dt)
         if self.slow_offset:
             _lib.check(eng.L.fwb_sim_set_slow_offset(eng.sim, self.slow_offset))
@@ -183,7 +183,7 @@ class DeviceSimulation:
         out = torch.empty(self.shape, dtype=torch.float64, device=eng.device)
         _lib.check(eng.L.fwb_scatter_compact(
             ctypes.c_void_p(eng.state[self.state_names.index(name)].data_ptr()),
-            ctypes.c_void_p(out.data_ptr()), float(getattr(self.model, "init_" + name)),
+            ctypes.c_void_p(out.data_ptr()), float(self.model._init_value(name)),
             eng.n_nodes, ctypes.c_void_p(eng.chunk_bits.data_ptr()),
             ctypes.c_void_p(eng.chunk_base.data_ptr()),
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "fwb_scatter_compact")
@@ -202,7 +202,7 @@ class DeviceSimulation:
         bufs["u"].copy_(eng.ubuf[cur], non_blocking=True)
         bufs["u_new"].copy_(eng.ubuf[cur ^ 1], non_blocking=True)
         for slot, name in enumerate(self.state_names):
-            eng.download_state(slot, bufs[name], getattr(self.model, "init_" + name))
+            eng.download_state(slot, bufs[name], self.model._init_value(name))
         eng.synchronize()
 
     def upload_host(self, bufs):

@@ -89,6 +89,11 @@ class CardiacModel:
         return copy.deepcopy(self)
 
     # ------------------------------------------------------------------ setup
+    def _init_value(self, name):
+        """init_<var> of a state attribute (Courtemanche's `j_` array is filled from
+        `init_j`, courtemanche_2d.py:126)."""
+        return getattr(self, "init_" + name.rstrip("_"))
+
     def _alloc_host(self, shape, value):
         a = pinned_empty(shape).numpy()
         a[...] = value
@@ -118,7 +123,7 @@ class CardiacModel:
         if self._INIT_U_NEW:
             self.u_new[...] = self.init_u
         for name in self._STATE:
-            self.__dict__[name] = self._alloc_host(shape, getattr(self, "init_" + name))
+            self.__dict__[name] = self._alloc_host(shape, self._init_value(name))
         self._uploaded = False
 
     def compute_weights(self):
@@ -183,7 +188,7 @@ class CardiacModel:
         eng.upload_dense(cur, self._host_array("u"))
         eng.upload_dense(cur ^ 1, self._host_array("u_new"))
         for slot, name in enumerate(self._STATE):
-            eng.upload_state(slot, self._host_array(name), fill=getattr(self, "init_" + name))
+            eng.upload_state(slot, self._host_array(name), fill=self._init_value(name))
         eng.synchronize()
         # state rows only exist for updated nodes; where the host arrays hold something
         # else than init_* on the other nodes, downloads must preserve it
@@ -243,7 +248,7 @@ class CardiacModel:
                 host = np.array(host, dtype=np.float64, order="C") if keep else \
                     np.empty(eng.shape, dtype=np.float64)
                 self.__dict__[name] = host
-            eng.download_state(slot, host, getattr(self, "init_" + name), keep=keep)
+            eng.download_state(slot, host, self._init_value(name), keep=keep)
         eng.synchronize()
 
     # ------------------------------------------------------------------ the loop
@@ -487,6 +492,47 @@ class BuenoOrovio2D(CardiacModel):
         self.init_u, self.init_v, self.init_w, self.init_s = 0.0, 1.0, 1.0, 0.0
 
 
+class Courtemanche2D(CardiacModel):
+    """courtemanche_2d.py:12-178 (human atrial model)"""
+    _MODEL, _DIM = "courtemanche", 2
+    _PARAMS = ("gna", "gnab", "gk1", "gkr", "gks", "gto", "gcal", "gcab", "gkur_coeff", "F", "T",
+               "R", "Vc", "Vj", "Vup", "Vrel", "ibk", "cao", "nao", "ko", "caupmax", "kup",
+               "kmnai", "kmko", "kmnancx", "kmcancx", "ksatncx", "kmcmdn", "kmtrpn", "kmcsqn",
+               "trpnmax", "cmdnmax", "csqnmax", "inacamax", "inakmax", "ipcamax", "krel",
+               "iupmax", "kq10")
+    _STATE = ("nai", "ki", "cai", "caup", "carel", "m", "h", "j_", "d", "f", "oa", "oi", "ua",
+              "ui", "xr", "xs", "fca", "irel", "vrel", "urel", "wrel")
+    _INIT_U_NEW = True
+
+    def __init__(self):
+        super().__init__()
+        self.D_model = 0.154
+        self.state_vars = ["u"] + list(self._STATE)
+        self.npfloat = 'float64'
+        self.gna, self.gnab, self.gk1, self.gkr, self.gks = 7.8, 0.000674, 0.09, 0.0294, 0.129
+        self.gto, self.gcal, self.gcab, self.gkur_coeff = 0.1652, 0.1238, 0.00113, 1
+        self.F, self.T, self.R = 96485.0, 310.0, 8314.0
+        self.Vc = 20100
+        self.Vj = self.Vc * 0.68
+        self.Vup = self.Vj * 0.06 * 0.92
+        self.Vrel = self.Vj * 0.06 * 0.08
+        self.ibk, self.cao, self.nao, self.ko = 0.0, 1.8, 140, 5.4
+        self.caupmax, self.kup, self.kmnai, self.kmko = 15, 0.00092, 10, 1.5
+        self.kmnancx, self.kmcancx, self.ksatncx = 87.5, 1.38, 0.1
+        self.kmcmdn, self.kmtrpn, self.kmcsqn = 0.00238, 0.0005, 0.8
+        self.trpnmax, self.cmdnmax, self.csqnmax = 0.07, 0.05, 10.0
+        self.inacamax, self.inakmax, self.ipcamax = 1600, 0.6, 0.275
+        self.krel, self.iupmax, self.kq10 = 30, 0.005, 3
+        self.init_u = -84.5
+        self.init_nai, self.init_ki, self.init_cai = 11.2, 139, 0.000102
+        self.init_caup, self.init_carel = 1.6, 1.1
+        self.init_m, self.init_h, self.init_j = 0.00291, 0.965, 0.978
+        self.init_d, self.init_f = 0.000137, 0.999837
+        self.init_oa, self.init_oi, self.init_ua, self.init_ui = 0.000592, 0.9992, 0.003519, 0.9987
+        self.init_xs, self.init_xr, self.init_fca = 0.0187, 0.0000329, 0.775
+        self.init_irel, self.init_vrel, self.init_urel, self.init_wrel = 0, 1, 0, 0.9
+
+
 class LuoRudy912D(CardiacModel):
     """luo_rudy91_2d.py:12-156"""
     _MODEL, _DIM = "luo_rudy91", 2
@@ -566,5 +612,6 @@ Barkley3D = _as_3d(Barkley2D, "Barkley3D")
 MitchellSchaeffer3D = _as_3d(MitchellSchaeffer2D, "MitchellSchaeffer3D")
 FentonKarma3D = _as_3d(FentonKarma2D, "FentonKarma3D")
 BuenoOrovio3D = _as_3d(BuenoOrovio2D, "BuenoOrovio3D")
+Courtemanche3D = _as_3d(Courtemanche2D, "Courtemanche3D")
 LuoRudy913D = _as_3d(LuoRudy912D, "LuoRudy913D")
 TP063D = _as_3d(TP062D, "TP063D")

@@ -64,7 +64,8 @@ extern "C" {
 #define FWB_MODEL_LUO_RUDY91         4  /* state: m,h,j,d,f,x,cai  params(15): gna,gsi,gk,gk1,gkp,gb,ko,ki,nai,nao,cao,R,T,F,PR_NaK */
 #define FWB_MODEL_TP06               5  /* state: cai,casr,cass,nai,Ki,m,h,j,xr1,xr2,xs,r,s,d,f,f2,fcass,rr,oo  params(49): tp06_2d.py:204-218 order */
 #define FWB_MODEL_BUENO_OROVIO       6  /* state: v,w,s        params(28): bueno_orovio_2d.py:170-178 order */
-#define FWB_N_MODELS                 7
+#define FWB_MODEL_COURTEMANCHE       7  /* state: nai,ki,cai,caup,carel,m,h,j_,d,f,oa,oi,ua,ui,xr,xs,fca,irel,vrel,urel,wrel  params(39): courtemanche_2d.py:157-168 order */
+#define FWB_N_MODELS                 8
 
 /* stencils; K = 5/9 (2D) or 7/19 (3D); slot order = the reference's */
 #define FWB_STENCIL_ISO   0

@@ -23,6 +23,7 @@ MODEL_CLASS = {
     "mitchell_schaeffer": "MitchellSchaeffer",
     "fenton_karma": "FentonKarma",
     "bueno_orovio": "BuenoOrovio",
+    "courtemanche": "Courtemanche",
     "luo_rudy91": "LuoRudy91",
     "tp06": "TP06",
 }
@@ -33,6 +34,8 @@ STATE_VARS = {
     "mitchell_schaeffer": ["u", "h"],
     "fenton_karma": ["u", "v", "w"],
     "bueno_orovio": ["u", "v", "w", "s"],
+    "courtemanche": ["u", "nai", "ki", "cai", "caup", "carel", "m", "h", "j_", "d", "f", "oa",
+                     "oi", "ua", "ui", "xr", "xs", "fca", "irel", "vrel", "urel", "wrel"],
     "luo_rudy91": ["u", "m", "h", "j", "d", "f", "x", "cai"],
     "tp06": ["u", "cai", "casr", "cass", "nai", "Ki", "m", "h", "j", "xr1", "xr2",
              "xs", "r", "s", "d", "f", "f2", "fcass", "rr", "oo"],
@@ -256,6 +259,22 @@ def make_cases():
         stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 4, 0, 12, 0, 10])],
         trackers=[dict(kind="activation_time", threshold=0.3, step=1)]))
 
+    # Courtemanche 2D iso, current stimulus (test_models_2d.py protocol)
+    cases.append(dict(
+        name="court2d_iso_current", model="courtemanche", shape=[16, 9],
+        dt=0.01, dr=0.25, t_max=10,
+        stims=[dict(kind="current_coord", t=0, value=100, duration=1, box=[0, 3, 0, 9])],
+        trackers=[dict(kind="action_potential", cell_ind=[8, 4], step=10)]))
+
+    # Courtemanche 3D aniso + fibrosis
+    cases.append(dict(
+        name="court3d_aniso_fib", model="courtemanche", shape=[12, 10, 8],
+        dt=0.01, dr=0.25, t_max=8,
+        mesh=random_fibrosis([12, 10, 8], 0.2, 13),
+        fibers=rotating_fibers_3d([12, 10, 8]),
+        stims=[dict(kind="voltage_coord", t=0, value=-20, box=[0, 4, 0, 10, 0, 8])],
+        trackers=[dict(kind="activation_time", step=1)]))
+
     # AP 2D aniso, non-default parameters and initial conditions
     cases.append(dict(
         name="ap2d_aniso_params", model="aliev_panfilov", shape=[37, 45],
@@ -300,7 +319,7 @@ def build_model(fw, case):
     for k, v in case.get("params", {}).items():
         setattr(model, k, v)
     for k, v in case.get("init", {}).items():
-        setattr(model, "init_" + k, v)
+        setattr(model, "init_" + k.rstrip("_"), v)
     if "D_model" in case:
         model.D_model = case["D_model"]
     model.cardiac_tissue = tissue

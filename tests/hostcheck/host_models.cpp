@@ -46,6 +46,7 @@ int fwb_host_ionic(int model, double *u_new, const double *u, double *const *st,
     case FWB_MODEL_LUO_RUDY91: run<FWB_MODEL_LUO_RUDY91>(u_new, u, st, n, dt, p); return 0;
     case FWB_MODEL_TP06: run<FWB_MODEL_TP06>(u_new, u, st, n, dt, p); return 0;
     case FWB_MODEL_BUENO_OROVIO: run<FWB_MODEL_BUENO_OROVIO>(u_new, u, st, n, dt, p); return 0;
+    case FWB_MODEL_COURTEMANCHE: run<FWB_MODEL_COURTEMANCHE>(u_new, u, st, n, dt, p); return 0;
     }
     return -1;
 }

@@ -54,9 +54,9 @@ def test_library_is_sm100a_only():
 
 def test_model_tables(L):
     assert L.fwb_version() == 100
-    assert [L.fwb_model_n_state(m) for m in range(7)] == [1, 1, 1, 2, 7, 19, 3]
-    assert [L.fwb_model_n_params(m) for m in range(7)] == [5, 3, 5, 11, 15, 49, 28]
-    assert L.fwb_model_n_state(7) < 0 and L.fwb_model_n_state(-1) < 0
+    assert [L.fwb_model_n_state(m) for m in range(8)] == [1, 1, 1, 2, 7, 19, 3, 21]
+    assert [L.fwb_model_n_params(m) for m in range(8)] == [5, 3, 5, 11, 15, 49, 28, 39]
+    assert L.fwb_model_n_state(8) < 0 and L.fwb_model_n_state(-1) < 0
     assert [L.fwb_stencil_k(d, s) for d in (2, 3) for s in (0, 1)] == [5, 9, 7, 19]
     assert L.fwb_stencil_k(4, 0) < 0
     # TP06: cai (slot 0) is never written, oo (slot 18) never read

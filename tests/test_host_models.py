@@ -21,7 +21,7 @@ ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "tests" / "hostcheck" / "host_models.cpp"
 SO = ROOT / "tests" / "hostcheck" / "libhost_models.so"
 MODEL_IDS = {"aliev_panfilov": 0, "barkley": 1, "mitchell_schaeffer": 2, "fenton_karma": 3,
-             "luo_rudy91": 4, "tp06": 5, "bueno_orovio": 6}
+             "luo_rudy91": 4, "tp06": 5, "bueno_orovio": 6, "courtemanche": 7}
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -40,7 +40,7 @@ def _random_node_states(model, n, rng):
     """u and state values spread over the ranges a simulation visits (both sides of
     every branch threshold)."""
     spec = oracle.MODELS[model]
-    if model in ("luo_rudy91", "tp06"):
+    if model in ("luo_rudy91", "tp06", "courtemanche"):
         u = rng.uniform(-95.0, 45.0, n)
         u[: n // 8] = rng.uniform(-41.0, -39.0, n // 8)     # around the h/j branch
     else:
@@ -50,13 +50,19 @@ def _random_node_states(model, n, rng):
     states = []
     for name in spec["state"]:
         init = spec["init"][name]
-        if name in ("cai", "cass"):
+        if model == "courtemanche" and name in ("caup", "carel"):
+            s = rng.uniform(0.5, 3.0, n)
+        elif model == "courtemanche" and name == "nai":
+            s = rng.uniform(9.0, 13.0, n)
+        elif model == "courtemanche" and name == "irel":
+            s = rng.uniform(0.0, 0.05, n)
+        elif name in ("cai", "cass"):
             s = rng.uniform(5e-5, 2e-3, n)
         elif name == "casr":
             s = rng.uniform(0.3, 4.0, n)
         elif name in ("nai",):
             s = rng.uniform(7.0, 11.0, n)
-        elif name in ("Ki",):
+        elif name in ("Ki", "ki"):
             s = rng.uniform(130.0, 142.0, n)
         else:
             s = rng.uniform(0.0, 1.0, n)
@@ -101,7 +107,7 @@ def test_param_order_matches_oracle_tables():
     finitewave_b200.model must be the oracle's (= the reference's kernel call order)."""
     from finitewave_b200 import model as m
     for cls in (m.AlievPanfilov2D, m.Barkley2D, m.MitchellSchaeffer2D, m.FentonKarma2D,
-                m.BuenoOrovio2D, m.LuoRudy912D, m.TP062D):
+                m.BuenoOrovio2D, m.Courtemanche2D, m.LuoRudy912D, m.TP062D):
         spec = oracle.MODELS[cls._MODEL]
         assert list(cls._PARAMS) == list(spec["params"]), cls.__name__
         assert list(cls._STATE) == list(spec["state"]), cls.__name__
@@ -109,7 +115,7 @@ def test_param_order_matches_oracle_tables():
         for k, v in spec["params"].items():
             assert float(getattr(obj, k)) == float(v), (cls.__name__, k)
         for k, v in spec["init"].items():
-            assert float(getattr(obj, "init_" + k)) == float(v), (cls.__name__, k)
+            assert float(getattr(obj, "init_" + k.rstrip("_"))) == float(v), (cls.__name__, k)
         assert obj.D_model == spec["D_model"]
 
 
