@@ -40,38 +40,6 @@
 
 namespace fwb {
 
-// Math policies of the two FP64-issue-bound models (LR91, TP06).  LibMath is the
-// reference statement (library exp, IEEE division); it is what the host transcription
-// check compiles and what the device uses for nodes whose potential is outside
-// (-300, 300) mV.  FastMath is the device's normal path: table-driven exp (fexp.cuh),
-// and the division fast path without its special-operand test where the denominator
-// is 1 + exp(.) >= 1.
-//   eu(x)  exp of an affine function of u   (|x| < 700 follows from |u| < 300)
-//   en(x)  exp of a non-positive, state-dependent argument (Rush-Larsen factors)
-//   ec(x)  exp of any state-dependent argument
-//   dv(a, b)  a / b for b = const + exp(.) >= ~1e-2 (normal, with a normal reciprocal)
-//   p15(x)    x^1.5
-struct LibMath {
-    FWB_HD static double eu(double x) { return exp(x); }
-    FWB_HD static double en(double x) { return exp(x); }
-    FWB_HD static double ec(double x) { return exp(x); }
-    FWB_HD static double dv(double a, double b) { return a / b; }
-    FWB_HD static double p15(double x) { return pow(x, 1.5); }
-};
-struct FastMath {
-    FWB_HD static double eu(double x) { return fexp(x); }
-    FWB_HD static double en(double x) { return fexp_neg(x); }
-    FWB_HD static double ec(double x) { return fexp_clamped(x); }
-    FWB_HD static double dv(double a, double b)
-    {
-        const double y = frcp(b);
-        const double q = a * y;
-        return fma(fma(-b, q, a), y, q);
-    }
-    FWB_HD static double p15(double x) { return x * sqrt(x); }   // x^1.5, x > 0
-};
-constexpr double FAST_MATH_U_LIMIT = 300.0;
-
 // divisor known on the host: the value and its correctly rounded reciprocal
 struct DivC {
     double c, rc;
@@ -90,8 +58,52 @@ FWB_HD double divc(double x, const DivC &d)
     const double r = fma(-q, d.c, x);
     return fma(r, d.rc, q);
 }
+
+// Math policies of the two FP64-issue-bound models (LR91, TP06).  LibMath is the
+// reference statement (library exp, IEEE division); it is what the host transcription
+// check compiles and what the device uses for nodes whose potential is outside
+// (-300, 300) mV.  FastMath is the device's normal path: table-driven exp (fexp.cuh),
+// and the division fast path without its special-operand test where the denominator
+// is 1 + exp(.) >= 1.
+//   eu(x)  exp of an affine function of u   (|x| < 700 follows from |u| < 300)
+//   en(x)  exp of a non-positive, state-dependent argument (Rush-Larsen factors)
+//   ec(x)  exp of any state-dependent argument
+//   dv(a, b)  a / b for b = const + exp(.) >= ~1e-2 (normal, with a normal reciprocal)
+//   p15(x)    x^1.5
+//   dk(x, d)  x / d.c for a host constant (literal or parameter)
+struct LibMath {
+    FWB_HD static double eu(double x) { return exp(x); }
+    FWB_HD static double en(double x) { return exp(x); }
+    FWB_HD static double ec(double x) { return exp(x); }
+    FWB_HD static double dv(double a, double b) { return a / b; }
+    FWB_HD static double p15(double x) { return pow(x, 1.5); }
+    FWB_HD static double dk(double x, const DivC &d) { return divc(x, d); }
+    static constexpr bool FUSE_RATE = false;
+};
+struct FastMath {
+    FWB_HD static double eu(double x) { return fexp(x); }
+    FWB_HD static double en(double x) { return fexp_neg(x); }
+    FWB_HD static double ec(double x) { return fexp_clamped(x); }
+    FWB_HD static double dv(double a, double b)
+    {
+        const double y = frcp(b);
+        if (a == 1.0) return y;               // folded at compile time for literal numerators
+        const double q = a * y;
+        return fma(fma(-b, q, a), y, q);
+    }
+    FWB_HD static double p15(double x) { return x * sqrt(x); }   // x^1.5, x > 0
+    // x / constant as one multiplication by the rounded reciprocal (<= 1 ulp off the
+    // quotient; the exact 3-instruction divc() stays on the LibMath path)
+    FWB_HD static double dk(double x, const DivC &d) { return x * d.rc; }
+    static constexpr bool FUSE_RATE = true;
+};
+constexpr double FAST_MATH_U_LIMIT = 300.0;
+
 // x / k for a literal k (the reciprocal is folded at compile time)
 #define FWB_DIVK(x, k) ::fwb::divc((x), ::fwb::DivC{(k), 1.0 / (k)})
+// the same through a math policy E (LR91 / TP06 / Courtemanche): exact on LibMath, one
+// multiplication on FastMath
+#define FWB_EDIVK(x, k) E::dk((x), ::fwb::DivC{(k), 1.0 / (k)})
 
 // every DivC of a Consts block must be usable (parameter finite and non-zero)
 inline bool divc_ok(const DivC &d) { return d.rc == d.rc && d.rc != 0.0 && (d.rc - d.rc) == 0.0; }
@@ -334,10 +346,10 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         // calc_ina :185-241
         double alpha_h = 0, beta_h = 0, beta_J = 0, alpha_J = 0;
         if (u >= -40.) {
-            beta_h = 1. / (0.13 * (1 + E::eu(FWB_DIVK(u + 10.66, -11.1))));
+            beta_h = 1. / (0.13 * (1 + E::eu(FWB_EDIVK(u + 10.66, -11.1))));
             beta_J = E::dv(0.3 * E::eu(-2.535 * 1e-07 * u), 1 + E::eu(-0.1 * (u + 32)));
         } else {
-            alpha_h = 0.135 * E::eu(FWB_DIVK(80 + u, -6.8));
+            alpha_h = 0.135 * E::eu(FWB_EDIVK(80 + u, -6.8));
             beta_h = 3.56 * E::eu(0.079 * u) + 3.1 * 1e5 * E::eu(0.35 * u);
             beta_J = E::dv(0.1212 * E::eu(-0.01052 * u), 1 + E::eu(-0.1378 * (u + 40.14)));
             alpha_J = E::dv((-1.2714 * 1e5 * E::eu(0.2444 * u) - 3.474 * 1e-5 * E::eu(-0.04391 * u)) *
@@ -345,7 +357,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
                             1 + E::eu(0.311 * (u + 79.23)));
         }
         const double alpha_m = 0.32 * (u + 47.13) / (1 - E::eu(-0.1 * (u + 47.13)));
-        const double beta_m = 0.08 * E::eu(FWB_DIVK(-u, 11.));
+        const double beta_m = 0.08 * E::eu(FWB_EDIVK(-u, 11.));
         const double m = gate(io.ld(0), dt, alpha_m, beta_m);
         const double h = gate(io.ld(1), dt, alpha_h, beta_h);
         const double j = gate(io.ld(2), dt, alpha_J, beta_J);
@@ -383,7 +395,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
                                (1 + E::eu(-0.5143 * (u - E_K1 + 4.753)));
         const double K_1x = alpha_K1 / (alpha_K1 + beta_K1);
         const double ik1 = c.G_K1 * K_1x * (u - E_K1);
-        const double K_p = E::dv(1., 1 + E::eu(FWB_DIVK(7.488 - u, 5.98)));
+        const double K_p = E::dv(1., 1 + E::eu(FWB_EDIVK(7.488 - u, 5.98)));
         const double ikp = c.gkp * K_p * (u - E_K1);
         const double ib = c.gb * (u + 59.87);
         const double ik1t = ik1 + ikp + ib;
@@ -449,6 +461,13 @@ template <> struct Model<FWB_MODEL_TP06> {
     {
         return inf - (inf - x) * E::en(-dt / tau);
     }
+    // the same for tau = 1 / rate (h and j gates, tp06_2d.py:296-309): the reference
+    // divides twice, -dt / (1.0 / rate); FastMath multiplies once
+    template <class E> FWB_HD static double rl_rate(double inf, double x, double dt, double rate)
+    {
+        if (E::FUSE_RATE) return inf - (inf - x) * E::en(-dt * rate);
+        return inf - (inf - x) * E::en(-dt / (1.0 / rate));
+    }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
@@ -475,33 +494,31 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ina :242-318
         double ina;
         {
-            const double alpha_m = E::dv(1., 1. + E::eu(FWB_DIVK(-60. - u, 5.)));
-            const double beta_m = E::dv(0.1, 1. + E::eu(FWB_DIVK(u + 35., 5.))) +
-                                  E::dv(0.10, 1. + E::eu(FWB_DIVK(u - 50., 200.)));
+            const double alpha_m = E::dv(1., 1. + E::eu(FWB_EDIVK(-60. - u, 5.)));
+            const double beta_m = E::dv(0.1, 1. + E::eu(FWB_EDIVK(u + 35., 5.))) +
+                                  E::dv(0.10, 1. + E::eu(FWB_EDIVK(u - 50., 200.)));
             const double tau_m = alpha_m * beta_m;
-            const double em = 1. + E::eu(FWB_DIVK(-56.86 - u, 9.03));
+            const double em = 1. + E::eu(FWB_EDIVK(-56.86 - u, 9.03));
             const double m_inf = E::dv(1., em * em);
             double alpha_h, beta_h, alpha_j, beta_j;
             if (u >= -40.) {
                 alpha_h = 0.;
-                beta_h = E::dv(0.77, 0.13 * (1. + E::eu(FWB_DIVK(-(u + 10.66), 11.1))));
+                beta_h = E::dv(0.77, 0.13 * (1. + E::eu(FWB_EDIVK(-(u + 10.66), 11.1))));
                 alpha_j = 0.;
                 beta_j = E::dv(0.6 * E::eu(0.057 * u), 1. + E::eu(-0.1 * (u + 32.)));
             } else {
-                alpha_h = 0.057 * E::eu(FWB_DIVK(-(u + 80.), 6.8));
+                alpha_h = 0.057 * E::eu(FWB_EDIVK(-(u + 80.), 6.8));
                 beta_h = 2.7 * E::eu(0.079 * u) + 3.1e5 * E::eu(0.3485 * u);
                 alpha_j = E::dv((-2.5428e4 * E::eu(0.2444 * u) - 6.948e-6 * E::eu(-0.04391 * u)) *
                                     (u + 37.78),
                                 1. + E::eu(0.311 * (u + 79.23)));
                 beta_j = E::dv(0.02424 * E::eu(-0.01052 * u), 1. + E::eu(-0.1378 * (u + 40.14)));
             }
-            const double tau_h = 1.0 / (alpha_h + beta_h);
-            const double eh = 1. + E::eu(FWB_DIVK(u + 71.55, 7.43));
+            const double eh = 1. + E::eu(FWB_EDIVK(u + 71.55, 7.43));
             const double h_inf = E::dv(1., eh * eh);
-            const double tau_j = 1.0 / (alpha_j + beta_j);
             const double m = rl<E>(m_inf, io.ld(5), dt, tau_m);
-            const double h = rl<E>(h_inf, io.ld(6), dt, tau_h);
-            const double j = rl<E>(h_inf, io.ld(7), dt, tau_j);
+            const double h = rl_rate<E>(h_inf, io.ld(6), dt, alpha_h + beta_h);   // tau_h = 1/(..)
+            const double j = rl_rate<E>(h_inf, io.ld(7), dt, alpha_j + beta_j);   // tau_j = 1/(..)
             io.st(5, m); io.st(6, h); io.st(7, j);
             ina = c.gna * m * m * m * h * j * (u - Ena);
         }
@@ -510,34 +527,34 @@ template <> struct Model<FWB_MODEL_TP06> {
         const double cass = io.ld(2);
         double ical;
         {
-            const double d_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-8 - u, 7.5)));
-            const double Ad = E::dv(1.4, 1. + E::eu(FWB_DIVK(-35 - u, 13.))) + 0.25;
-            const double Bd = E::dv(1.4, 1. + E::eu(FWB_DIVK(u + 5, 5.)));
-            const double Cd = E::dv(1., 1. + E::eu(FWB_DIVK(50 - u, 20.)));
+            const double d_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(-8 - u, 7.5)));
+            const double Ad = E::dv(1.4, 1. + E::eu(FWB_EDIVK(-35 - u, 13.))) + 0.25;
+            const double Bd = E::dv(1.4, 1. + E::eu(FWB_EDIVK(u + 5, 5.)));
+            const double Cd = E::dv(1., 1. + E::eu(FWB_EDIVK(50 - u, 20.)));
             const double tau_d = Ad * Bd + Cd;
             const double d = rl<E>(d_inf, io.ld(13), dt, tau_d);
             io.st(13, d);
-            const double f_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u + 20, 7.)));
-            const double Af = 1102.5 * E::eu(FWB_DIVK(-(u + 27) * (u + 27), 225.));
-            const double Bf = E::dv(200., 1 + E::eu(FWB_DIVK(13 - u, 10.)));
-            const double e30 = E::eu(FWB_DIVK(u + 30, 10.));
+            const double f_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(u + 20, 7.)));
+            const double Af = 1102.5 * E::eu(FWB_EDIVK(-(u + 27) * (u + 27), 225.));
+            const double Bf = E::dv(200., 1 + E::eu(FWB_EDIVK(13 - u, 10.)));
+            const double e30 = E::eu(FWB_EDIVK(u + 30, 10.));
             const double Cf = E::dv(180., 1 + e30) + 20;
             const double tau_f = Af + Bf + Cf;
             const double f = rl<E>(f_inf, io.ld(14), dt, tau_f);
             io.st(14, f);
-            const double f2_inf = E::dv(0.67, 1. + E::eu(FWB_DIVK(u + 35, 7.))) + 0.33;
-            const double Af2 = 600 * E::eu(FWB_DIVK(-(u + 25) * (u + 25), 170.));
-            const double Bf2 = E::dv(31., 1. + E::eu(FWB_DIVK(25 - u, 10.)));
+            const double f2_inf = E::dv(0.67, 1. + E::eu(FWB_EDIVK(u + 35, 7.))) + 0.33;
+            const double Af2 = 600 * E::eu(FWB_EDIVK(-(u + 25) * (u + 25), 170.));
+            const double Bf2 = E::dv(31., 1. + E::eu(FWB_EDIVK(25 - u, 10.)));
             const double Cf2 = E::dv(16., 1. + e30);
             const double tau_f2 = Af2 + Bf2 + Cf2;
             const double f2 = rl<E>(f2_inf, io.ld(15), dt, tau_f2);
             io.st(15, f2);
-            const double cq = 1 + FWB_DIVK(cass, 0.05) * FWB_DIVK(cass, 0.05);
+            const double cq = 1 + FWB_EDIVK(cass, 0.05) * FWB_EDIVK(cass, 0.05);
             const double fcass_inf = E::dv(0.6, cq) + 0.4;
             const double tau_fcass = E::dv(80., cq) + 2.;
             const double fcass = rl<E>(fcass_inf, io.ld(16), dt, tau_fcass);
             io.st(16, fcass);
-            const double e2 = E::eu(divc(2 * (u - 15) * c.F, c.RT));
+            const double e2 = E::eu(E::dk(2 * (u - 15) * c.F, c.RT));
             ical = c.gcal * d * f * f2 * fcass * 4 * (u - 15) * c.FF_RT *
                    (0.25 * e2 * cass - c.cao) / (e2 - 1.);
         }
@@ -545,11 +562,11 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ito :383-413
         double ito;
         {
-            const double r_inf = E::dv(1., 1. + E::eu(FWB_DIVK(20 - u, 6.)));
-            const double s_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u + 20, 5.)));
-            const double tau_r = 9.5 * E::eu(FWB_DIVK(-(u + 40.) * (u + 40.), 1800.)) + 0.8;
-            const double tau_s = 85. * E::eu(FWB_DIVK(-(u + 45.) * (u + 45.), 320.)) +
-                                 E::dv(5., 1. + E::eu(FWB_DIVK(u - 20., 5.))) + 3.;
+            const double r_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(20 - u, 6.)));
+            const double s_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(u + 20, 5.)));
+            const double tau_r = 9.5 * E::eu(FWB_EDIVK(-(u + 40.) * (u + 40.), 1800.)) + 0.8;
+            const double tau_s = 85. * E::eu(FWB_EDIVK(-(u + 45.) * (u + 45.), 320.)) +
+                                 E::dv(5., 1. + E::eu(FWB_EDIVK(u - 20., 5.))) + 3.;
             const double sg = rl<E>(s_inf, io.ld(12), dt, tau_s);
             const double r = rl<E>(r_inf, io.ld(11), dt, tau_r);
             io.st(11, r); io.st(12, sg);
@@ -559,13 +576,13 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_ikr :416-452
         double ikr;
         {
-            const double xr1_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-26. - u, 7.)));
-            const double axr1 = E::dv(450., 1. + E::eu(FWB_DIVK(-45. - u, 10.)));
-            const double bxr1 = E::dv(6., 1. + E::eu(FWB_DIVK(u - (-30.), 11.5)));
+            const double xr1_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(-26. - u, 7.)));
+            const double axr1 = E::dv(450., 1. + E::eu(FWB_EDIVK(-45. - u, 10.)));
+            const double bxr1 = E::dv(6., 1. + E::eu(FWB_EDIVK(u - (-30.), 11.5)));
             const double tau_xr1 = axr1 * bxr1;
-            const double xr2_inf = E::dv(1., 1. + E::eu(FWB_DIVK(u - (-88.), 24.)));
-            const double axr2 = E::dv(3., 1. + E::eu(FWB_DIVK(-60. - u, 20.)));
-            const double bxr2 = E::dv(1.12, 1. + E::eu(FWB_DIVK(u - 60., 20.)));
+            const double xr2_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(u - (-88.), 24.)));
+            const double axr2 = E::dv(3., 1. + E::eu(FWB_EDIVK(-60. - u, 20.)));
+            const double bxr2 = E::dv(1.12, 1. + E::eu(FWB_EDIVK(u - 60., 20.)));
             const double tau_xr2 = axr2 * bxr2;
             const double xr1 = rl<E>(xr1_inf, io.ld(8), dt, tau_xr1);
             const double xr2 = rl<E>(xr2_inf, io.ld(9), dt, tau_xr2);
@@ -576,9 +593,9 @@ template <> struct Model<FWB_MODEL_TP06> {
         // calc_iks :455-485
         double iks;
         {
-            const double xs_inf = E::dv(1., 1. + E::eu(FWB_DIVK(-5. - u, 14.)));
-            const double Axs = (1400. / (sqrt(1. + E::eu(FWB_DIVK(5. - u, 6.)))));
-            const double Bxs = E::dv(1., 1. + E::eu(FWB_DIVK(u - 35., 15.)));
+            const double xs_inf = E::dv(1., 1. + E::eu(FWB_EDIVK(-5. - u, 14.)));
+            const double Axs = (1400. / (sqrt(1. + E::eu(FWB_EDIVK(5. - u, 6.)))));
+            const double Bxs = E::dv(1., 1. + E::eu(FWB_EDIVK(u - 35., 15.)));
             const double tau_xs = Axs * Bxs + 80;
             const double xs = rl<E>(xs_inf, io.ld(10), dt, tau_xs);
             io.st(10, xs);
@@ -592,17 +609,17 @@ template <> struct Model<FWB_MODEL_TP06> {
         const double rec_iK1 = ak1 / (ak1 + bk1);
         const double ik1 = c.gk1 * rec_iK1 * (u - Ek);
         // calc_inaca :517-565
-        const double e_nm1 = E::eu(divc(c.n_m1 * u * c.F, c.RT));
+        const double e_nm1 = E::eu(E::dk(c.n_m1 * u * c.F, c.RT));
         const double inaca = c.inaca_pref * (1. / (1 + c.ksat * e_nm1)) *
-                             (E::eu(divc(c.n_ * u * c.F, c.RT)) * nai * nai * nai * c.cao -
+                             (E::eu(E::dk(c.n_ * u * c.F, c.RT)) * nai * nai * nai * c.cao -
                               e_nm1 * c.nao * c.nao * c.nao * cai * 2.5);
         // calc_inak :568-604
-        const double rec_iNaK = E::dv(1., 1. + 0.1245 * E::eu(divc(-0.1 * u * c.F, c.RT)) +
-                                              0.0353 * E::eu(divc(-u * c.F, c.RT)));
+        const double rec_iNaK = E::dv(1., 1. + 0.1245 * E::eu(E::dk(-0.1 * u * c.F, c.RT)) +
+                                              0.0353 * E::eu(E::dk(-u * c.F, c.RT)));
         const double inak = c.knak_pref * (nai / (nai + c.KmNa)) * rec_iNaK;
         // calc_ipca :607-627, calc_ipk :630-653, calc_ibna :656-675, calc_ibca :678-697
         const double ipca = c.gpca * cai / (c.KpCa + cai);
-        const double rec_ipK = E::dv(1., 1. + E::eu(FWB_DIVK(25 - u, 5.98)));
+        const double rec_ipK = E::dv(1., 1. + E::eu(FWB_EDIVK(25 - u, 5.98)));
         const double ipk = c.gpk * rec_ipK * (u - Ek);
         const double ibna = c.gbna * (u - Ena);
         const double ibca = c.gbca * (u - Eca);
@@ -727,16 +744,16 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
             double am;
             if (u == -47.13) am = 3.2;
             else am = 0.32 * (u + 47.13) / (1 - E::eu(-0.1 * (u + 47.13)));
-            const double bm = 0.08 * E::eu(FWB_DIVK(-u, 11.));
+            const double bm = 0.08 * E::eu(FWB_EDIVK(-u, 11.));
             const double m = gate<E>(io.ld(5), am / (am + bm), 1 / (am + bm), dt);
             double ah, bh, aj, bj;
             if (u >= -40) {
                 ah = 0;
-                bh = E::dv(1., 0.13 * (1 + E::eu(FWB_DIVK(-(u + 10.66), 11.1))));
+                bh = E::dv(1., 0.13 * (1 + E::eu(FWB_EDIVK(-(u + 10.66), 11.1))));
                 aj = 0;
                 bj = E::dv(0.3 * E::eu(-0.0000002535 * u), 1 + E::eu(-0.1 * (u + 32)));
             } else {
-                ah = 0.135 * E::eu(FWB_DIVK(-(80 + u), 6.8));
+                ah = 0.135 * E::eu(FWB_EDIVK(-(80 + u), 6.8));
                 bh = 3.56 * E::eu(0.079 * u) + 310000 * E::eu(0.35 * u);
                 aj = E::dv((-127140 * E::eu(0.2444 * u) - 0.00003474 * E::eu(-0.04391 * u)) *
                                (u + 37.78),
@@ -753,26 +770,26 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         // calc_ito :307-325 and calc_ikur :328-347 (share ao/bo)
         double ito, ikur;
         {
-            const double ao = E::dv(0.65, E::eu(FWB_DIVK(-(u + 10), 8.5)) + E::eu(FWB_DIVK(-(u - 30), 59.0)));
-            const double bo = E::dv(0.65, 2.5 + E::eu(FWB_DIVK(u + 82, 17.0)));
+            const double ao = E::dv(0.65, E::eu(FWB_EDIVK(-(u + 10), 8.5)) + E::eu(FWB_EDIVK(-(u - 30), 59.0)));
+            const double bo = E::dv(0.65, 2.5 + E::eu(FWB_EDIVK(u + 82, 17.0)));
             const double tau_o = 1 / (c.kq10 * (ao + bo));
-            const double o_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 20.47), 17.54)));
-            const double aoi = E::dv(1., 18.53 + E::eu(FWB_DIVK(u + 113.7, 10.95)));
-            const double boi = E::dv(1., 35.56 + E::eu(FWB_DIVK(-(u + 1.26), 7.44)));
+            const double o_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(-(u + 20.47), 17.54)));
+            const double aoi = E::dv(1., 18.53 + E::eu(FWB_EDIVK(u + 113.7, 10.95)));
+            const double boi = E::dv(1., 35.56 + E::eu(FWB_EDIVK(-(u + 1.26), 7.44)));
             const double tau_oi = 1 / (c.kq10 * (aoi + boi));
-            const double oi_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u + 43.1, 5.3)));
+            const double oi_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(u + 43.1, 5.3)));
             const double oa = gate<E>(io.ld(10), o_inf, tau_o, dt);
             const double oi = gate<E>(io.ld(11), oi_inf, tau_oi, dt);
             io.st(10, oa); io.st(11, oi);
             ito = c.gto * (oa * (oa * oa)) * oi * (u - ek);
 
-            const double gkur = 0.005 + E::dv(0.05, 1 + E::eu(FWB_DIVK(-(u - 15), 13.0)));
+            const double gkur = 0.005 + E::dv(0.05, 1 + E::eu(FWB_EDIVK(-(u - 15), 13.0)));
             const double tau_ua = tau_o;           // aua == ao, bua == bo (:330-332)
-            const double ua_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 30.3), 9.6)));
-            const double aui = E::dv(1., 21 + E::eu(FWB_DIVK(-(u - 185), 28.0)));
-            const double bui = E::eu(FWB_DIVK(u - 158, 16.0));
+            const double ua_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(-(u + 30.3), 9.6)));
+            const double aui = E::dv(1., 21 + E::eu(FWB_EDIVK(-(u - 185), 28.0)));
+            const double bui = E::eu(FWB_EDIVK(u - 158, 16.0));
             const double tau_ui = 1 / (c.kq10 * (aui + bui));
-            const double ui_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u - 99.45, 27.48)));
+            const double ui_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(u - 99.45, 27.48)));
             const double ua = gate<E>(io.ld(12), ua_inf, tau_ua, dt);
             const double ui = gate<E>(io.ld(13), ui_inf, tau_ui, dt);
             io.st(12, ua); io.st(13, ui);
@@ -781,21 +798,21 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         // calc_ikr :350-362 -- gate stored in slot 15 (model.xs), gkr fixed at 0.0294
         double ikr;
         {
-            const double axr = 0.0003 * (u + 14.1) / (1 - E::eu(FWB_DIVK(-(u + 14.1), 5.)));
-            const double bxr = 0.000073898 * (u - 3.3328) / (E::eu(FWB_DIVK(u - 3.3328, 5.1237)) - 1);
+            const double axr = 0.0003 * (u + 14.1) / (1 - E::eu(FWB_EDIVK(-(u + 14.1), 5.)));
+            const double bxr = 0.000073898 * (u - 3.3328) / (E::eu(FWB_EDIVK(u - 3.3328, 5.1237)) - 1);
             const double tau_xr = 1 / (axr + bxr);
-            const double xr_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 14.1), 6.5)));
+            const double xr_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(-(u + 14.1), 6.5)));
             const double xr = gate<E>(io.ld(15), xr_inf, tau_xr, dt);
             io.st(15, xr);
-            ikr = E::dv(0.0294 * xr * (u - ek), 1 + E::eu(FWB_DIVK(u + 15, 22.4)));
+            ikr = E::dv(0.0294 * xr * (u - ek), 1 + E::eu(FWB_EDIVK(u + 15, 22.4)));
         }
         // calc_iks :365-376 -- gate stored in slot 14 (model.xr)
         double iks;
         {
-            const double axs = 0.00004 * (u - 19.9) / (1 - E::eu(FWB_DIVK(-(u - 19.9), 17.)));
-            const double bxs = 0.000035 * (u - 19.9) / (E::eu(FWB_DIVK(u - 19.9, 9.)) - 1);
+            const double axs = 0.00004 * (u - 19.9) / (1 - E::eu(FWB_EDIVK(-(u - 19.9), 17.)));
+            const double bxs = 0.000035 * (u - 19.9) / (E::eu(FWB_EDIVK(u - 19.9, 9.)) - 1);
             const double tau_xs = 1 / (2 * (axs + bxs));
-            const double xs_inf = 1 / sqrt(1 + E::eu(FWB_DIVK(-(u - 19.9), 12.7)));
+            const double xs_inf = 1 / sqrt(1 + E::eu(FWB_EDIVK(-(u - 19.9), 12.7)));
             const double xs = gate<E>(io.ld(14), xs_inf, tau_xs, dt);
             io.st(14, xs);
             iks = c.gks * (xs * xs) * (u - ek);
@@ -803,12 +820,12 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         // calc_ical :379-396
         double ical;
         {
-            const double e10 = E::eu(FWB_DIVK(-(u + 10), 6.24));
+            const double e10 = E::eu(FWB_EDIVK(-(u + 10), 6.24));
             const double tau_d = (1 - e10) / (0.035 * (u + 10) * (1 + e10));
-            const double d_inf = E::dv(1., 1 + E::eu(FWB_DIVK(-(u + 10), 8.0)));
+            const double d_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(-(u + 10), 8.0)));
             const double tau_f = 9 / (0.0197 * E::eu(-(0.0337 * 0.0337) * ((u + 10) * (u + 10))) + 0.02);
-            const double f_inf = E::dv(1., 1 + E::eu(FWB_DIVK(u + 28, 6.9)));
-            const double fca_inf = 1 / (1 + FWB_DIVK(cai, 0.00035));
+            const double f_inf = E::dv(1., 1 + E::eu(FWB_EDIVK(u + 28, 6.9)));
+            const double fca_inf = 1 / (1 + FWB_EDIVK(cai, 0.00035));
             const double d = gate<E>(io.ld(8), d_inf, tau_d, dt);
             const double f = gate<E>(io.ld(9), f_inf, tau_f, dt);
             const double fca = gate<E>(io.ld(16), fca_inf, 2, dt);
@@ -817,13 +834,13 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         }
         // calc_inak :399-404, calc_inaca :407-423
         const double Fu = c.F * u;
-        const double fnak = 1 / (1 + 0.1245 * E::eu(divc(-0.1 * Fu, c.RT)) +
-                                 0.0365 * c.nak_s * E::eu(divc(-Fu, c.RT)));
+        const double fnak = 1 / (1 + 0.1245 * E::eu(E::dk(-0.1 * Fu, c.RT)) +
+                                 0.0365 * c.nak_s * E::eu(E::dk(-Fu, c.RT)));
         const double inak = c.inakmax * fnak * (1 / (1 + E::p15(c.kmnai / nai))) * c.ko_kmko;
         double inaca;
         {
-            const double exp_term = E::eu(divc(0.35 * Fu, c.RT));
-            const double exp_rev_term = E::eu(divc((0.35 - 1) * Fu, c.RT));
+            const double exp_term = E::eu(E::dk(0.35 * Fu, c.RT));
+            const double exp_rev_term = E::eu(E::dk((0.35 - 1) * Fu, c.RT));
             const double numerator = c.inacamax * (exp_term * (nai * (nai * nai)) * c.cao -
                                                    exp_rev_term * c.nao3 * cai);
             inaca = numerator / (c.ncx_t12 * (1 + c.ksatncx * exp_rev_term));
@@ -833,33 +850,33 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         const double ipca = c.ipcamax * cai / (cai + 0.0005); // :436-438
         // membrane potential and the two concentrations that need no SR fluxes
         un -= dt * (ina + ik1 + ito + ikur + ikr + iks + ical + ipca + inak + inaca + ibna + ibca);
-        io.st(0, nai + dt * divc(-3 * inak - 3 * inaca - ibna - ina, c.FVj));               // :207-210
-        io.st(1, ki + dt * divc(2 * inak - ik1 - ito - ikur - ikr - iks - c.ibk, c.FVj));    // :213-216
+        io.st(0, nai + dt * E::dk(-3 * inak - 3 * inaca - ibna - ina, c.FVj));               // :207-210
+        io.st(1, ki + dt * E::dk(2 * inak - ik1 - ito - ikur - ikr - iks - c.ibk, c.FVj));    // :213-216
         // calc_irel :441-462
         const double caup = io.ld(3), carel = io.ld(4);
         double irel;
         {
             const double Fn = c.Fn_a * io.ld(17) - c.Fn_b * (0.5 * ical - 0.2 * inaca);
-            const double eFn = E::ec(FWB_DIVK(-(Fn - 3.4175e-13), 13.67e-16));
+            const double eFn = E::ec(FWB_EDIVK(-(Fn - 3.4175e-13), 13.67e-16));
             const double u_inf = 1 / (1 + eFn);
             const double tau_v = 1.91 + 2.09 / (1 + eFn);
-            const double v_inf = 1 - 1 / (1 + E::ec(FWB_DIVK(-(Fn - 6.835e-14), 13.67e-16)));
-            const double e79 = E::eu(FWB_DIVK(-(u - 7.9), 5.0));
+            const double v_inf = 1 - 1 / (1 + E::ec(FWB_EDIVK(-(Fn - 6.835e-14), 13.67e-16)));
+            const double e79 = E::eu(FWB_EDIVK(-(u - 7.9), 5.0));
             const double tau_w = 6 * (1 - e79) / ((1 + 0.3 * e79) * (u - 7.9));
-            const double w_inf = 1 - E::dv(1., 1 + E::eu(FWB_DIVK(-(u - 40), 17.0)));
+            const double w_inf = 1 - E::dv(1., 1 + E::eu(FWB_EDIVK(-(u - 40), 17.0)));
             const double urel = gate<E>(io.ld(19), u_inf, 8, dt);
             const double vrel = gate<E>(io.ld(18), v_inf, tau_v, dt);
             const double wrel = gate<E>(io.ld(20), w_inf, tau_w, dt);
             irel = c.krel * (urel * urel) * vrel * wrel * (carel - cai);
             io.st(17, irel); io.st(19, urel); io.st(18, vrel); io.st(20, wrel);
         }
-        const double itr = FWB_DIVK(caup - carel, 180.);       // :465-468
+        const double itr = FWB_EDIVK(caup - carel, 180.);       // :465-468
         const double iup = c.iupmax / (1 + (c.kup / cai));     // :471-473
-        const double iupleak = divc(caup, c.caupmax) * c.iupmax;   // :476-478
+        const double iupleak = E::dk(caup, c.caupmax) * c.iupmax;   // :476-478
         io.st(3, caup + dt * (iup - iupleak - itr * c.Vrel_Vup));                           // :226-229
         {
-            const double B1 = divc(2 * inaca - ipca - ical - ibca, c.FVj2) +
-                              divc(c.Vup * (iupleak - iup) + irel * c.Vrel, c.Vj);
+            const double B1 = E::dk(2 * inaca - ipca - ical - ibca, c.FVj2) +
+                              E::dk(c.Vup * (iupleak - iup) + irel * c.Vrel, c.Vj);
             const double B2 = 1 + c.trpn_k / ((cai + c.kmtrpn) * (cai + c.kmtrpn)) +
                               c.cmdn_k / ((cai + c.kmcmdn) * (cai + c.kmcmdn));
             io.st(2, cai + dt * (B1 / B2));                                                  // :219-224

@@ -144,6 +144,53 @@ template <> struct Stencil<3, FWB_STENCIL_ANISO> {
 
 #ifdef __CUDACC__
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+constexpr int tma_popc(uint32_t m) { return m ? (int)(m & 1u) + tma_popc(m >> 1) : 0; }
+// position of state slot q among the staged (read) slots
+constexpr int tma_slot(uint32_t mask, int q) { return tma_popc(mask & ((1u << q) - 1u)); }
+// q-th staged slot -> state slot
+__host__ __device__ constexpr int tma_nth(uint32_t mask, int n)
+{
+    int q = 0;
+    for (; q < 32; ++q)
+        if ((mask >> q) & 1u) { if (n == 0) break; --n; }
+    return q;
+}
+
+// Models with many state arrays (LR91, TP06, Courtemanche) cannot hold their state in
+// registers and load it where it is used -- each such load would pay the full HBM latency
+// in the middle of the FP64 work.  Instead every thread starts asynchronous copies
+// (cp.async -> LDGSTS, no registers held) of its node's state values into its own column
+// of a shared-memory block at the top of the kernel; they land while the warp waits for
+// the stencil operands anyway, and the model then reads them at shared-memory latency.
+// A thread only ever reads the column it filled itself, so no block barrier is needed.
+// Measured on B200 (C5, TP06): 6.15 G upd/s staged vs 6.42 with the L1 prefetch below, so
+// the staged path is opt-in (-DFWB_STAGE_STATE) until the FP64 work per node shrinks.
+#ifdef FWB_STAGE_STATE
+template <class M> constexpr bool stage_state() { return M::NS > 4; }
+#else
+template <class M> constexpr bool stage_state() { return false; }
+#endif
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+template <class M> struct StateIOStaged {
+    const double *sm;     // this thread's column of the staged rows [NSR][BLOCK_THREADS]
+    double *gp;           // this node's column in the global compact state
+    int64_t stride;
+    __device__ __forceinline__ double ld(int q) const { return sm[tma_slot(M::READ_MASK, q) * BLOCK_THREADS]; }
+    __device__ __forceinline__ void st(int q, double v) const { st_stream(gp + (int64_t)q * stride, v); }
+};
+
 // state accessor of one node: slot q lives at state[q * ld + c]
 struct StateIO {
     double *base;
@@ -188,6 +235,9 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     const Grid &g = P.g;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    constexpr bool STAGE = stage_state<M>();
+    constexpr int NSR = STAGE ? tma_popc(M::READ_MASK) : 1;
+    __shared__ double staged[STAGE ? NSR : 1][STAGE ? BLOCK_THREADS : 1];
 
     // which slab boundary (if any) this block belongs to
     const HaloSide *side = nullptr;
@@ -227,9 +277,16 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
         const double *__restrict__ u = P.u + n;
         const double *__restrict__ w = P.w + c;
         const int64_t ld = g.ld;
+        if constexpr (STAGE) {
+#pragma unroll
+            for (int q = 0; q < NSR; ++q)
+                cp_async8(&staged[q][threadIdx.x],
+                          P.state + (int64_t)tma_nth(M::READ_MASK, q) * ld + c);
+        } else {
 #ifndef FWB_NO_PREFETCH
-        if (M::NS > 4) StateIO{P.state + c, ld}.template prefetch<M::READ_MASK>();
+            if (M::NS > 4) StateIO{P.state + c, ld}.template prefetch<M::READ_MASK>();
 #endif
+        }
 
         // diffusion: issue the 2K loads, then the left-to-right sum in slot order
         // (no FMA contraction: -fmad=false)
@@ -257,8 +314,14 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 
         if (TRACK) diff = acc - uc;
 
-        StateIO io{P.state + c, ld};
-        M::ionic(uc, acc, io, A.c);
+        if constexpr (STAGE) {
+            cp_async_wait_all();
+            StateIOStaged<M> io{&staged[0][threadIdx.x], P.state + c, ld};
+            M::ionic(uc, acc, io, A.c);
+        } else {
+            StateIO io{P.state + c, ld};
+            M::ionic(uc, acc, io, A.c);
+        }
 
         P.u_new[n] = acc;
         if (HALO && side) side->peer_dst[n - side->first] = acc;
@@ -327,10 +390,6 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 // ---------------------------------------------------------------------------
 // step_kernel_tma: persistent, TMA-fed variant (see the header comment)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -361,18 +420,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
-}
-
-constexpr int tma_popc(uint32_t m) { return m ? (int)(m & 1u) + tma_popc(m >> 1) : 0; }
-// position of state slot q among the staged (read) slots
-constexpr int tma_slot(uint32_t mask, int q) { return tma_popc(mask & ((1u << q) - 1u)); }
-// q-th staged slot -> state slot
-__host__ __device__ constexpr int tma_nth(uint32_t mask, int n)
-{
-    int q = 0;
-    for (; q < 32; ++q)
-        if ((mask >> q) & 1u) { if (n == 0) break; --n; }
-    return q;
 }
 
 constexpr int TMA_SEG = 258;   // doubles per staged row: 256 nodes + 16-B alignment slack
