@@ -58,3 +58,27 @@ void fwb_host_fexp(const double *x, double *out, int64_t n, int mode)
     for (int64_t i = 0; i < n; ++i)
         out[i] = mode == 0 ? fwb::fexp(x[i]) : mode == 1 ? fwb::fexp_neg(x[i]) : fwb::fexp_clamped(x[i]);
 }
+
+// host build of TP06's rearranged device path (Model<TP06>::ionic_fast) for comparison
+// with the reference statement (ionic_impl<LibMath>) on the same node states
+extern "C" __attribute__((visibility("default")))
+int fwb_host_tp06_fast(double *u_new, const double *u, double *const *st, int64_t n, double dt,
+                       const double *p)
+{
+    using M = Model<FWB_MODEL_TP06>;
+    M::Consts c;
+    if (!M::derive(p, dt, c)) return -1;
+    struct IO {
+        double *const *arr;
+        int64_t i;
+        double ld(int q) const { return (M::READ_MASK >> q) & 1 ? arr[q][i] : -12345.0; }
+        void st(int q, double v) const { arr[q][i] = (M::WRITE_MASK >> q) & 1 ? v : -54321.0; }
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        IO io{st, i};
+        double un = u_new[i];
+        M::ionic_fast(u[i], un, io, c);
+        u_new[i] = un;
+    }
+    return 0;
+}

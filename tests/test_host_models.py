@@ -102,6 +102,42 @@ def test_models_header_matches_oracle_bitwise(hostlib, model, dt):
         assert np.array_equal(a, b), f"{name} differs: {np.max(np.abs(a - b)):.3e}"
 
 
+def test_tp06_fast_path_matches_reference_statement(hostlib):
+    """Model<TP06>::ionic_fast (the device's path for |u| < 300 mV: shared exponentials,
+    one reciprocal per gate, branch-free divisions) is an algebraic rearrangement of the
+    reference statement: one step from the same node states agrees to rounding level."""
+    rng = np.random.default_rng(3)
+    n = 200000
+    spec = oracle.MODELS["tp06"]
+    u, st = _random_node_states("tp06", n, rng)
+    u[-n // 10:] = rng.uniform(-290.0, 290.0, n // 10)       # the whole guarded range
+    pvec = np.array([float(v) for v in spec["params"].values()], dtype=np.float64)
+    diff = rng.uniform(-1, 1, n) * 0.01 + u
+    for dt in (0.01, 0.001):
+        outs = []
+        for fn, extra in ((hostlib.fwb_host_ionic, (MODEL_IDS["tp06"],)),
+                          (hostlib.fwb_host_tp06_fast, ())):
+            un = diff.copy()
+            s2 = [s.copy() for s in st]
+            arr = (c_double_p * len(s2))(*[s.ctypes.data_as(c_double_p) for s in s2])
+            rc = fn(*extra, un.ctypes.data_as(c_double_p), u.ctypes.data_as(c_double_p), arr,
+                    ctypes.c_int64(n), ctypes.c_double(dt), pvec.ctypes.data_as(c_double_p))
+            assert rc == 0
+            outs.append((un, s2))
+        (un_r, st_r), (un_f, st_f) = outs
+        # the step's increments (what the rearrangement computes) agree to 1e-11 relative
+        # to the increment scale; the values themselves to ~1e-14
+        du = np.abs(un_r - diff)
+        err = np.abs(un_f - un_r) / np.maximum(np.abs(un_r), 1.0)
+        assert err.max() < 2e-13, ("u_new", err.max(), int(err.argmax()), u[err.argmax()])
+        for name, a, b, s0 in zip(spec["state"], st_f, st_r, st):
+            if name == "cai":
+                assert np.array_equal(a, s0)
+                continue
+            err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+            assert err.max() < 2e-12, (name, err.max(), int(err.argmax()), u[err.argmax()])
+
+
 def test_param_order_matches_oracle_tables():
     """The device parameter vectors are indexed by position: the attribute order in
     finitewave_b200.model must be the oracle's (= the reference's kernel call order)."""
