@@ -35,6 +35,7 @@
 // (NVLink), and the last of them to finish raises the neighbour's flag for the
 // next step.  Interior blocks never wait: the exchange overlaps the interior.
 #pragma once
+#include <stdlib.h>
 #include "fwb_common.cuh"
 #include "models.cuh"
 
@@ -162,32 +163,61 @@ __host__ __device__ constexpr int tma_nth(uint32_t mask, int n)
 
 // Models with many state arrays (LR91, TP06, Courtemanche) cannot hold their state in
 // registers and load it where it is used -- each such load would pay the full HBM latency
-// in the middle of the FP64 work.  Instead every thread starts asynchronous copies
-// (cp.async -> LDGSTS, no registers held) of its node's state values into its own column
-// of a shared-memory block at the top of the kernel; they land while the warp waits for
-// the stencil operands anyway, and the model then reads them at shared-memory latency.
-// A thread only ever reads the column it filled itself, so no block barrier is needed.
-// Measured on B200 (C5, TP06): 6.15 G upd/s staged vs 6.42 with the L1 prefetch below, so
-// the staged path is opt-in (-DFWB_STAGE_STATE) until the FP64 work per node shrinks.
-#ifdef FWB_STAGE_STATE
-template <class M> constexpr bool stage_state() { return M::NS > 4; }
-#else
+// in the middle of the FP64 work.  With the tile-ordered compact layout a tile's state rows
+// are contiguous, so one thread of the block fetches them with TMA bulk copies into shared
+// memory while all threads wait for the stencil operands anyway; the model then reads its
+// state at shared-memory latency (step_kernel<..., STAGED = true>).
+#ifdef FWB_NO_STAGE
 template <class M> constexpr bool stage_state() { return false; }
+#else
+template <class M> constexpr bool stage_state() { return M::NS > 4; }
 #endif
-__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all()
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
 {
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    const uint32_t a = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(phase)
+            : "memory");
+    } while (!ok);
 }
-template <class M> struct StateIOStaged {
-    const double *sm;     // this thread's column of the staged rows [NSR][BLOCK_THREADS]
+// global -> shared bulk copy (TMA, 1-D); bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int TMA_SEG = 258;   // doubles per staged row: 256 nodes + 16-B alignment slack
+
+// state accessor of the TMA kernel: reads from the staged rows, writes to global
+template <class M> struct StateIOTma {
+    const double *sm;     // this node's column in the staged state rows
     double *gp;           // this node's column in the global compact state
     int64_t stride;
-    __device__ __forceinline__ double ld(int q) const { return sm[tma_slot(M::READ_MASK, q) * BLOCK_THREADS]; }
+    // (__popc of a constant folds; the constexpr recursion of tma_slot() does not when q
+    // only becomes a constant after inlining, and costs a 150-instruction loop per load)
+    __device__ __forceinline__ double ld(int q) const
+    {
+        return sm[__popc(M::READ_MASK & ((1u << q) - 1u)) * TMA_SEG];
+    }
     __device__ __forceinline__ void st(int q, double v) const { st_stream(gp + (int64_t)q * stride, v); }
 };
 
@@ -195,7 +225,11 @@ template <class M> struct StateIOStaged {
 struct StateIO {
     double *base;
     int64_t stride;
+#ifdef FWB_STATE_LD_CA
+    __device__ __forceinline__ double ld(int q) const { return base[(int64_t)q * stride]; }
+#else
     __device__ __forceinline__ double ld(int q) const { return ld_stream(base + (int64_t)q * stride); }
+#endif
     __device__ __forceinline__ void st(int q, double v) const { st_stream(base + (int64_t)q * stride, v); }
     // pull every row this node will read towards the SM without holding registers: the
     // models with many state arrays load them where they are used (register budget), and
@@ -225,7 +259,7 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class M, int DIM, int ST, bool TRACK, bool HALO>
+template <class M, int DIM, int ST, bool TRACK, bool HALO, bool STAGED = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, M::MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs<M> A)
 {
@@ -235,9 +269,31 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     const Grid &g = P.g;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    constexpr bool STAGE = stage_state<M>();
-    constexpr int NSR = STAGE ? tma_popc(M::READ_MASK) : 1;
-    __shared__ double staged[STAGE ? NSR : 1][STAGE ? BLOCK_THREADS : 1];
+    constexpr int NSR = tma_popc(M::READ_MASK);
+    __shared__ __align__(128) double staged[STAGED ? NSR * TMA_SEG : 2];
+    __shared__ uint64_t staged_full;
+    if (STAGED) {
+        // (requires P.tile_base / P.records: block b owns tile b = compact range
+        // [tile_base[b], tile_base[b + 1]))
+        if (threadIdx.x == 0) {
+            mbar_init(&staged_full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t c0 = __ldg(P.tile_base + blockIdx.x), c1 = __ldg(P.tile_base + blockIdx.x + 1);
+            const uint32_t c0a = c0 & ~1u;
+            const unsigned bytes = c1 > c0 ? (((c1 - c0a) + 1u) & ~1u) * 8u : 0u;
+            mbar_arrive_expect_tx(&staged_full, bytes * NSR);
+            if (bytes) {
+#pragma unroll
+                for (int q = 0; q < NSR; ++q)
+                    tma_load_1d(staged + q * TMA_SEG,
+                                P.state + (int64_t)tma_nth(M::READ_MASK, q) * g.ld + c0a, bytes,
+                                &staged_full);
+            }
+        }
+    }
 
     // which slab boundary (if any) this block belongs to
     const HaloSide *side = nullptr;
@@ -255,10 +311,21 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
         }
     }
 
+    // the warp's work record {chunk, bits, compact base, .}: one 16-B load when the engine
+    // built the records (tile-ordered layout), else three dependent loads
     const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-    const int64_t chunk = slot < g.n_work ? (int64_t)__ldg(g.worklist + slot) : -1;
-    uint32_t bits = 0;
-    if (chunk >= 0) bits = __ldg(g.chunk_bits + chunk);
+    int64_t chunk = -1;
+    uint32_t bits = 0, cbase = 0, tbase = 0;
+    if (slot < g.n_work) {
+        if (STAGED || P.records) {
+            const uint4 rec = __ldg(P.records + slot);
+            chunk = (int64_t)(int32_t)rec.x;
+            if (chunk >= 0) { bits = rec.y; cbase = rec.z; tbase = rec.w; }
+        } else {
+            chunk = (int64_t)__ldg(g.worklist + slot);
+            if (chunk >= 0) { bits = __ldg(g.chunk_bits + chunk); cbase = __ldg(g.chunk_base + chunk); }
+        }
+    }
 
     const int64_t n = chunk * 32 + lane;
     const bool myo = (bits >> lane) & 1u;
@@ -272,19 +339,20 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     }
 
     if (myo) {
-        const int64_t c = (int64_t)__ldg(g.chunk_base + chunk) +
-                          __popc(bits & ((1u << lane) - 1u));
+        const int64_t c = (int64_t)cbase + __popc(bits & ((1u << lane) - 1u));
         const double *__restrict__ u = P.u + n;
         const double *__restrict__ w = P.w + c;
         const int64_t ld = g.ld;
-        if constexpr (STAGE) {
-#pragma unroll
-            for (int q = 0; q < NSR; ++q)
-                cp_async8(&staged[q][threadIdx.x],
-                          P.state + (int64_t)tma_nth(M::READ_MASK, q) * ld + c);
-        } else {
+        if constexpr (!STAGED) {
 #ifndef FWB_NO_PREFETCH
             if (M::NS > 4) StateIO{P.state + c, ld}.template prefetch<M::READ_MASK>();
+#endif
+#ifdef FWB_PREFETCH_W
+            if (M::NS > 4) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(w + (int64_t)k * ld));
+            }
 #endif
         }
 
@@ -299,7 +367,11 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
             // boundary blocks of a slab read ghost values a peer GPU wrote during the
             // previous step: they must not come from the non-coherent path
             un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
+#ifdef FWB_PREFETCH_W
+            wn[k] = (M::NS > 4) ? *w : ld_stream(w);
+#else
             wn[k] = ld_stream(w);
+#endif
             w += ld;
         }
         double acc = mul(un[0], wn[0]);
@@ -314,9 +386,9 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 
         if (TRACK) diff = acc - uc;
 
-        if constexpr (STAGE) {
-            cp_async_wait_all();
-            StateIOStaged<M> io{&staged[0][threadIdx.x], P.state + c, ld};
+        if constexpr (STAGED) {
+            mbar_wait(&staged_full, 0);
+            StateIOTma<M> io{staged + (c - (int64_t)(tbase & ~1u)), P.state + c, ld};
             M::ionic(uc, acc, io, A.c);
         } else {
             StateIO io{P.state + c, ld};
@@ -390,40 +462,6 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 // ---------------------------------------------------------------------------
 // step_kernel_tma: persistent, TMA-fed variant (see the header comment)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
-{
-    const uint32_t a = smem_u32(bar);
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(a), "r"(phase)
-            : "memory");
-    } while (!ok);
-}
-// global -> shared bulk copy (TMA, 1-D); bytes % 16 == 0, both addresses 16-B aligned
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-constexpr int TMA_SEG = 258;   // doubles per staged row: 256 nodes + 16-B alignment slack
-
 constexpr int TMA_REC_BYTES = WARPS_PER_BLOCK * 16;   // the tile's 8 work records
 
 template <class M, int K> struct TmaCfg {
@@ -434,15 +472,6 @@ template <class M, int K> struct TmaCfg {
     static constexpr size_t STAGE = (size_t)NARR * TMA_SEG * sizeof(double) + TMA_REC_BYTES;
     static constexpr size_t SMEM = NSTAGE * STAGE + 64;
     static constexpr int BLOCKS = SMEM * 4 <= 224 * 1024 ? 4 : (SMEM * 3 <= 224 * 1024 ? 3 : 2);
-};
-
-// state accessor of the TMA kernel: reads from the staged rows, writes to global
-template <class M> struct StateIOTma {
-    const double *sm;     // this node's column in the staged state rows
-    double *gp;           // this node's column in the global compact state
-    int64_t stride;
-    __device__ __forceinline__ double ld(int q) const { return sm[tma_slot(M::READ_MASK, q) * TMA_SEG]; }
-    __device__ __forceinline__ void st(int q, double v) const { st_stream(gp + (int64_t)q * stride, v); }
 };
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
@@ -601,6 +630,21 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
     const int64_t blocks = step_blocks(k.g);
     if (blocks <= 0) return 0;
+    static int carve = -2;
+    if (carve == -2) {
+        const char *e = getenv("FWB_CARVEOUT");          // experiment: L1 / shared split
+        carve = e ? atoi(e) : -1;
+        if (carve >= 0)
+            cudaFuncSetAttribute(step_kernel<M, DIM, ST, TRACK, HALO>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    if constexpr (stage_state<M>()) {
+        if (k.tile_base && k.records) {
+            step_kernel<M, DIM, ST, TRACK, HALO, true><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
+            FWB_KERNEL_CHECK("step_kernel (staged)");
+            return 0;
+        }
+    }
     step_kernel<M, DIM, ST, TRACK, HALO><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
     FWB_KERNEL_CHECK("step_kernel");
     return 0;

@@ -1,0 +1,1 @@
+bash scripts/gpu_prof_one.sh c5 r1_e
