@@ -172,6 +172,11 @@ template <class M> constexpr bool stage_state() { return false; }
 #else
 template <class M> constexpr bool stage_state() { return M::NS > 4; }
 #endif
+#ifdef FWB_NO_STAGE_W
+template <class M> constexpr bool stage_weights() { return false; }
+#else
+template <class M> constexpr bool stage_weights() { return true; }
+#endif
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
@@ -205,6 +210,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
         : "memory");
 }
 
+constexpr int TMA_REC_BYTES = WARPS_PER_BLOCK * 16;   // the tile's 8 work records
 constexpr int TMA_SEG = 258;   // doubles per staged row: 256 nodes + 16-B alignment slack
 
 // state accessor of the TMA kernel: reads from the staged rows, writes to global
@@ -259,8 +265,19 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class M, int DIM, int ST, bool TRACK, bool HALO, bool STAGED = false>
-__global__ void __launch_bounds__(BLOCK_THREADS, M::MIN_BLOCKS)
+// STAGED: 0 = every operand through LDG; 1 = the tile's state rows by TMA into shared memory;
+// 2 = state rows AND weight rows (3 blocks per SM: 76 KB each).  1 and 2 need the tile-ordered
+// compact layout (P.tile_base / P.records): block b owns tile b = compact range
+// [tile_base[b], tile_base[b + 1]).
+template <class M, int K, int STAGED> struct StageCfg {
+    static constexpr int NSR = tma_popc(M::READ_MASK);
+    static constexpr int ROWS = STAGED == 2 ? K + NSR : (STAGED == 1 ? NSR : 0);
+    static constexpr size_t SMEM = (size_t)ROWS * TMA_SEG * sizeof(double);
+    static constexpr int BLOCKS = STAGED == 2 ? (M::MIN_BLOCKS < 3 ? M::MIN_BLOCKS : 3) : M::MIN_BLOCKS;
+};
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO, int STAGED = 0>
+__global__ void __launch_bounds__(BLOCK_THREADS, (StageCfg<M, Stencil<DIM, ST>::K, STAGED>::BLOCKS))
 step_kernel(const __grid_constant__ StepArgs<M> A)
 {
     using S = Stencil<DIM, ST>;
@@ -270,13 +287,14 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int NSR = tma_popc(M::READ_MASK);
-    __shared__ __align__(128) double staged[STAGED ? NSR * TMA_SEG : 2];
-    __shared__ uint64_t staged_full;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    double *const staged_w = reinterpret_cast<double *>(dyn_smem);              // [K][TMA_SEG] (mode 2)
+    double *const staged = staged_w + (STAGED == 2 ? K * TMA_SEG : 0);          // [NSR][TMA_SEG]
+    __shared__ uint64_t staged_full[2];                                         // state, weights
     if (STAGED) {
-        // (requires P.tile_base / P.records: block b owns tile b = compact range
-        // [tile_base[b], tile_base[b + 1]))
         if (threadIdx.x == 0) {
-            mbar_init(&staged_full, 1);
+            mbar_init(&staged_full[0], 1);
+            mbar_init(&staged_full[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
@@ -284,13 +302,22 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
             const uint32_t c0 = __ldg(P.tile_base + blockIdx.x), c1 = __ldg(P.tile_base + blockIdx.x + 1);
             const uint32_t c0a = c0 & ~1u;
             const unsigned bytes = c1 > c0 ? (((c1 - c0a) + 1u) & ~1u) * 8u : 0u;
-            mbar_arrive_expect_tx(&staged_full, bytes * NSR);
+            if (STAGED == 2) {
+                mbar_arrive_expect_tx(&staged_full[1], bytes * K);
+                if (bytes) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        tma_load_1d(staged_w + k * TMA_SEG, P.w + (int64_t)k * g.ld + c0a, bytes,
+                                    &staged_full[1]);
+                }
+            }
+            mbar_arrive_expect_tx(&staged_full[0], bytes * NSR);
             if (bytes) {
 #pragma unroll
                 for (int q = 0; q < NSR; ++q)
                     tma_load_1d(staged + q * TMA_SEG,
                                 P.state + (int64_t)tma_nth(M::READ_MASK, q) * g.ld + c0a, bytes,
-                                &staged_full);
+                                &staged_full[0]);
             }
         }
     }
@@ -343,16 +370,9 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
         const double *__restrict__ u = P.u + n;
         const double *__restrict__ w = P.w + c;
         const int64_t ld = g.ld;
-        if constexpr (!STAGED) {
+        if constexpr (STAGED == 0) {
 #ifndef FWB_NO_PREFETCH
             if (M::NS > 4) StateIO{P.state + c, ld}.template prefetch<M::READ_MASK>();
-#endif
-#ifdef FWB_PREFETCH_W
-            if (M::NS > 4) {
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(w + (int64_t)k * ld));
-            }
 #endif
         }
 
@@ -367,12 +387,14 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
             // boundary blocks of a slab read ghost values a peer GPU wrote during the
             // previous step: they must not come from the non-coherent path
             un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
-#ifdef FWB_PREFETCH_W
-            wn[k] = (M::NS > 4) ? *w : ld_stream(w);
-#else
-            wn[k] = ld_stream(w);
-#endif
+            if (STAGED != 2) wn[k] = ld_stream(w);
             w += ld;
+        }
+        if (STAGED == 2) {
+            mbar_wait(&staged_full[1], 0);
+            const double *sw = staged_w + (c - (int64_t)(tbase & ~1u));
+#pragma unroll
+            for (int k = 0; k < K; ++k) wn[k] = sw[k * TMA_SEG];
         }
         double acc = mul(un[0], wn[0]);
 #pragma unroll
@@ -386,8 +408,8 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 
         if (TRACK) diff = acc - uc;
 
-        if constexpr (STAGED) {
-            mbar_wait(&staged_full, 0);
+        if constexpr (STAGED != 0) {
+            mbar_wait(&staged_full[0], 0);
             StateIOTma<M> io{staged + (c - (int64_t)(tbase & ~1u)), P.state + c, ld};
             M::ionic(uc, acc, io, A.c);
         } else {
@@ -462,7 +484,6 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 // ---------------------------------------------------------------------------
 // step_kernel_tma: persistent, TMA-fed variant (see the header comment)
 // ---------------------------------------------------------------------------
-constexpr int TMA_REC_BYTES = WARPS_PER_BLOCK * 16;   // the tile's 8 work records
 
 template <class M, int K> struct TmaCfg {
     static constexpr int NSR = tma_popc(M::READ_MASK);
@@ -620,6 +641,7 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
     }
 }
 
+
 inline int64_t step_blocks(const Grid &g) { return (g.n_work + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
@@ -640,7 +662,24 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     }
     if constexpr (stage_state<M>()) {
         if (k.tile_base && k.records) {
-            step_kernel<M, DIM, ST, TRACK, HALO, true><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
+            // everything by TMA when three such blocks fit an SM and no ECG sample is due
+            // (its reduction buffer would cost the third block); else the state rows only
+            constexpr int K = Stencil<DIM, ST>::K;
+            constexpr bool FULL = !TRACK && stage_weights<M>() &&
+                                  3 * (StageCfg<M, K, 2>::SMEM + 1024 + 64) <= 228 * 1024;
+            if constexpr (FULL) {
+                auto kern = step_kernel<M, DIM, ST, TRACK, HALO, 2>;
+                static bool attr = false;
+                if (!attr) {
+                    FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)StageCfg<M, K, 2>::SMEM));
+                    attr = true;
+                }
+                kern<<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 2>::SMEM, s>>>(a);
+            } else {
+                step_kernel<M, DIM, ST, TRACK, HALO, 1>
+                    <<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 1>::SMEM, s>>>(a);
+            }
             FWB_KERNEL_CHECK("step_kernel (staged)");
             return 0;
         }
@@ -686,6 +725,7 @@ static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
 static int launch_pick(const StepCommon &k, const void *consts, cudaStream_t s)
 {
+
     if constexpr (M::USE_TMA) {
         if (k.tile_base && !k.do_ecg) return launch_tma<M, DIM, ST, TRACK, HALO>(k, consts, s);
     }
