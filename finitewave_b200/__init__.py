@@ -17,7 +17,7 @@ from .model import (AlievPanfilov2D, AlievPanfilov3D, Barkley2D, Barkley3D, Buen
                     FentonKarma2D, FentonKarma3D, LuoRudy912D, LuoRudy913D,
                     MitchellSchaeffer2D, MitchellSchaeffer3D, TP062D, TP063D)
 from .stencil import (AsymmetricStencil2D, AsymmetricStencil3D, IsotropicStencil2D,
-                      IsotropicStencil3D, Stencil)
+                      IsotropicStencil3D, Stencil, SymmetricStencil2D)
 from .stimulation import (Stim, StimCurrent, StimCurrentArea2D, StimCurrentArea3D,
                           StimCurrentCoord2D, StimCurrentCoord3D, StimCurrentMatrix2D,
                           StimCurrentMatrix3D, StimSequence, StimVoltage, StimVoltageCoord2D,

@@ -16,7 +16,7 @@ _lib = None
 MODEL_IDS = {"aliev_panfilov": 0, "barkley": 1, "mitchell_schaeffer": 2, "fenton_karma": 3,
              "luo_rudy91": 4, "tp06": 5, "bueno_orovio": 6,
              "courtemanche": 7}
-STENCIL_ISO, STENCIL_ANISO = 0, 1
+STENCIL_ISO, STENCIL_ANISO, STENCIL_SYM = 0, 1, 2
 STIM_VOLTAGE, STIM_CURRENT, STIM_VOLTAGE_LIST = 0, 1, 2
 
 

@@ -151,7 +151,7 @@ extern "C" uint32_t fwb_model_write_mask(int model)
 }
 extern "C" int fwb_stencil_k(int dim, int stencil)
 {
-    if (dim == 2) return stencil == FWB_STENCIL_ISO ? 5 : stencil == FWB_STENCIL_ANISO ? 9 : FWB_E_ARG;
+    if (dim == 2) return stencil == FWB_STENCIL_ISO ? 5 : (stencil == FWB_STENCIL_ANISO || stencil == FWB_STENCIL_SYM) ? 9 : FWB_E_ARG;
     if (dim == 3) return stencil == FWB_STENCIL_ISO ? 7 : stencil == FWB_STENCIL_ANISO ? 19 : FWB_E_ARG;
     return FWB_E_ARG;
 }

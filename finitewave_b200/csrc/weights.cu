@@ -281,6 +281,80 @@ __global__ void __launch_bounds__(BLOCK_THREADS) weights_aniso_kernel(const __gr
     }
 }
 
+// ---- symmetric 2D ---------------------------------------
+// SymmetricStencil2D: cpuwave2D/stencil/symmetric_stencil_2d.py -- cell-centred tensor
+// (compute_half_step_diffusion :68-118), corner weights of one cell (compute_components
+// :121-151), the four cells around a node in the reference's accumulation order (njit
+// compute_weights :160-250), scaling by the SCALAR D_model * dt / dr**2 (:61-62).
+struct Quad { double w[4]; };
+
+__device__ __forceinline__ Quad sym_components(double d_xx, double d_xy, double d_yx, double d_yy,
+                                               int m0, int m1, int m2, int m3, double qx, double qy)
+{
+    Quad r;
+    if (m0 + m1 + m2 + m3 < 3) {
+        r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.0;
+        return r;
+    }
+    const double qdx = add(mul(qx, d_xx), mul(qy, d_yx));
+    const double qdy = add(mul(qx, d_xy), mul(qy, d_yy));
+    const double w0 = sub(mul(dvd((double)(-m0), (double)(m0 + m1)), qdx),
+                          mul(dvd((double)m0, (double)(m0 + m2)), qdy));
+    const double w1 = add(mul(dvd((double)(-m1), (double)(m0 + m1)), qdx),
+                          mul(dvd((double)m1, (double)(m1 + m3)), qdy));
+    const double w2 = sub(mul(dvd((double)m2, (double)(m2 + m3)), qdx),
+                          mul(dvd((double)m2, (double)(m0 + m2)), qdy));
+    const double w3 = add(mul(dvd((double)m3, (double)(m2 + m3)), qdx),
+                          mul(dvd((double)m3, (double)(m1 + m3)), qdy));
+    r.w[0] = mul(0.5, w0); r.w[1] = mul(0.5, w1); r.w[2] = mul(0.5, w2); r.w[3] = mul(0.5, w3);
+    return r;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS) weights_sym2d_kernel(const __grid_constant__ WArgs A)
+{
+    const Grid &g = A.g;
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (chunk >= g.n_chunks) return;
+    const uint32_t bits = g.chunk_bits[chunk];
+    if (!((bits >> lane) & 1u)) return;
+    const int64_t n = chunk * 32 + lane;
+    const int64_t c = (int64_t)g.chunk_base[chunk] + __popc(bits & ((1u << lane) - 1u));
+    const int64_t sI = g.s_row;
+    Aniso<2> X{A, n};
+    // tensor component (a, b) of the cell whose lower corner is `node`
+    auto cell = [&](int64_t node, int a, int b) {
+        return mul(0.25, add(add(add(X.Dc(node, a, b), X.Dc(node + sI, a, b)),
+                                 X.Dc(node + 1, a, b)), X.Dc(node + sI + 1, a, b)));
+    };
+    auto comp = [&](int64_t node, double qx, double qy, int m0, int m1, int m2, int m3) {
+        return sym_components(cell(node, 0, 0), cell(node, 0, 1), cell(node, 1, 0),
+                              cell(node, 1, 1), m0, m1, m2, m3, qx, qy);
+    };
+#define M2(di, dj) X.m((di) * sI + (dj))
+    double w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = 0.0;
+    Quad q;
+    q = comp(n - sI - 1, -1.0, -1.0, M2(-1, -1), M2(-1, 0), M2(0, -1), M2(0, 0));   // (i-1/2, j-1/2)
+    ACC_ADD(0, q.w[0]); ACC_ADD(1, q.w[1]); ACC_ADD(3, q.w[2]); ACC_ADD(4, q.w[3]);
+    q = comp(n - sI, -1.0, 1.0, M2(-1, 0), M2(-1, 1), M2(0, 0), M2(0, 1));          // (i-1/2, j+1/2)
+    ACC_ADD(1, q.w[0]); ACC_ADD(2, q.w[1]); ACC_ADD(4, q.w[2]); ACC_ADD(5, q.w[3]);
+    q = comp(n - 1, 1.0, -1.0, M2(0, -1), M2(0, 0), M2(1, -1), M2(1, 0));           // (i+1/2, j-1/2)
+    ACC_ADD(3, q.w[0]); ACC_ADD(4, q.w[1]); ACC_ADD(6, q.w[2]); ACC_ADD(7, q.w[3]);
+    q = comp(n, 1.0, 1.0, M2(0, 0), M2(0, 1), M2(1, 0), M2(1, 1));                  // (i+1/2, j+1/2)
+    ACC_ADD(4, q.w[0]); ACC_ADD(5, q.w[1]); ACC_ADD(7, q.w[2]); ACC_ADD(8, q.w[3]);
+#undef M2
+    const double sc = dvd(mul(A.D_model, A.dt), A.dr2);
+    double *out = A.w + c;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double v = mul(w[k], sc);
+        if (k == 4) v = add(v, 1.0);
+        out[(int64_t)k * g.ld] = v;
+    }
+}
+
 }  // namespace fwb
 
 using namespace fwb;
@@ -296,7 +370,11 @@ extern "C" int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
         set_error("fwb_compute_weights: bad argument");
         return FWB_E_ARG;
     }
-    if (stencil == FWB_STENCIL_ANISO && !fibers) {
+    if (stencil == FWB_STENCIL_SYM && dim != 2) {
+        set_error("fwb_compute_weights: the symmetric stencil is 2D only");
+        return FWB_E_ARG;
+    }
+    if ((stencil == FWB_STENCIL_ANISO || stencil == FWB_STENCIL_SYM) && !fibers) {
         set_error("Fibers must be provided for anisotropic diffusion.");
         return FWB_E_ARG;
     }
@@ -314,6 +392,8 @@ extern "C" int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
     } else if (stencil == FWB_STENCIL_ANISO) {
         if (dim == 2) weights_aniso_kernel<2><<<blocks, BLOCK_THREADS, 0, s>>>(A);
         else weights_aniso_kernel<3><<<blocks, BLOCK_THREADS, 0, s>>>(A);
+    } else if (stencil == FWB_STENCIL_SYM) {
+        weights_sym2d_kernel<<<blocks, BLOCK_THREADS, 0, s>>>(A);
     } else {
         set_error("fwb_compute_weights: unknown stencil %d", stencil);
         return FWB_E_ARG;

@@ -172,7 +172,9 @@ class Engine:
     # ---- weights --------------------------------------------------------
     def compute_weights(self, stencil, conductivity, fibers, D_al, D_ac, D_model, dt, dr):
         dev = self.device
-        self.stencil = stencil
+        # the symmetric stencil only differs in its weights: the step applies them with the
+        # 9-point kernel (the reference reuses diffusion_kernel_2d_aniso)
+        self.stencil = _lib.STENCIL_ANISO if stencil == _lib.STENCIL_SYM else stencil
         self.K = self.L.fwb_stencil_k(self.dim, stencil)
         self.weights = torch.empty((self.K, self.ld), dtype=torch.float64, device=dev)
         cond_t, cond_s = None, 1.0

@@ -69,10 +69,10 @@ class _BuiltinStencil(Stencil):
         if np.dtype(model.npfloat) != np.float64:
             raise NotImplementedError("finitewave_b200 computes in float64 only")
         eng = model._engine_for(cardiac_tissue)
-        if self._KIND == _lib.STENCIL_ANISO and cardiac_tissue.fibers is None:
+        if self._KIND != _lib.STENCIL_ISO and cardiac_tissue.fibers is None:
             raise ValueError("Fibers must be provided for anisotropic diffusion.")
         eng.compute_weights(self._KIND, cardiac_tissue.conductivity,
-                            cardiac_tissue.fibers if self._KIND == _lib.STENCIL_ANISO else None,
+                            cardiac_tissue.fibers if self._KIND != _lib.STENCIL_ISO else None,
                             getattr(self, "D_al", 1), getattr(self, "D_ac", 1 / 9),
                             model.D_model, model.dt, model.dr)
         return DeviceWeights(eng)
@@ -81,6 +81,8 @@ class _BuiltinStencil(Stencil):
         """Callable with the reference's signature ``(u_new, u, w, indexes)`` running
         the device diffusion apply (fwb_diffuse) on host arrays."""
         kind, dim = self._KIND, self._DIM
+        if kind == _lib.STENCIL_SYM:
+            kind = _lib.STENCIL_ANISO
 
         def diffusion_kernel(u_new, u, w, indexes):
             from .hostcall import diffuse_host
@@ -110,3 +112,10 @@ class AsymmetricStencil2D(_BuiltinStencil):
 class AsymmetricStencil3D(AsymmetricStencil2D):
     """19-point (faces + 12 edges), slot order of asymmetric_stencil_3d.py:26-44."""
     _KIND, _DIM = _lib.STENCIL_ANISO, 3
+
+
+class SymmetricStencil2D(AsymmetricStencil2D):
+    """Cell-centred 9-point scheme (cpuwave2D/stencil/symmetric_stencil_2d.py:7-66); same
+    slot order and apply kernel as AsymmetricStencil2D, only the weights differ.  Never
+    auto-selected: assign ``model.stencil = SymmetricStencil2D()``."""
+    _KIND, _DIM = _lib.STENCIL_SYM, 2

@@ -70,6 +70,10 @@ extern "C" {
 /* stencils; K = 5/9 (2D) or 7/19 (3D); slot order = the reference's */
 #define FWB_STENCIL_ISO   0
 #define FWB_STENCIL_ANISO 1
+/* weights only (fwb_compute_weights, 2D): SymmetricStencil2D,
+ * finitewave/cpuwave2D/stencil/symmetric_stencil_2d.py; the step applies them with the
+ * 9-point kernel, i.e. as FWB_STENCIL_ANISO (the reference reuses diffusion_kernel_2d_aniso) */
+#define FWB_STENCIL_SYM   2
 
 /* stimulus modes */
 #define FWB_STIM_VOLTAGE      0   /* u = value                 (StimVoltage*)  */

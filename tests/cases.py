@@ -284,6 +284,24 @@ def make_cases():
         stims=[dict(kind="voltage_coord", t=0.1, value=1, box=[1, 36, 1, 4])],
         trackers=[dict(kind="activation_time", threshold=0.5, step=7, start_time=0.5,
                        end_time=3.0)]))
+    # SymmetricStencil2D: cell-centred 9-point weights, random fibres,
+    # fibrosis and a conductivity map; the apply kernel is the asymmetric 9-point one
+    rng = np.random.default_rng(21)
+    cases.append(dict(
+        name="ap2d_sym_fib", model="aliev_panfilov", shape=[40, 36],
+        dt=0.01, dr=0.25, t_max=5, stencil="sym",
+        mesh=random_fibrosis([40, 36], 0.2, 22),
+        fibers=random_fibers([40, 36], 23),
+        conductivity=0.4 + 0.6 * rng.random([40, 36]),
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 40, 0, 5])],
+        trackers=[dict(kind="activation_time", threshold=0.5, step=1)]))
+    # the same stencil with uniform fibres on FK (scalar conductivity)
+    cases.append(dict(
+        name="fk2d_sym_uniform", model="fenton_karma", shape=[32, 30],
+        dt=0.01, dr=0.25, t_max=4, stencil="sym",
+        fibers=uniform_fibers_2d([32, 30], 0.3 * np.pi),
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 5, 0, 30])],
+        trackers=[dict(kind="action_potential", cell_ind=[16, 15], step=2)]))
     return cases
 
 
@@ -323,6 +341,8 @@ def build_model(fw, case):
     if "D_model" in case:
         model.D_model = case["D_model"]
     model.cardiac_tissue = tissue
+    if case.get("stencil") == "sym":
+        model.stencil = fw.SymmetricStencil2D()
 
     seq = fw.StimSequence()
     for s in case.get("stims", []):
