@@ -26,7 +26,9 @@ from .stimulation import (Stim, StimCurrent, StimCurrentArea2D, StimCurrentArea3
 from .tissue import CardiacTissue, CardiacTissue2D, CardiacTissue3D
 from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker,
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,
-                      ECG3DTracker, MultiVariable2DTracker, MultiVariable3DTracker, Tracker,
-                      TrackerSequence, Variable2DTracker, Variable3DTracker)
+                      ECG3DTracker, LocalActivationTime2DTracker, LocalActivationTime3DTracker,
+                      MultiVariable2DTracker, MultiVariable3DTracker, Period2DTracker,
+                      Period3DTracker, Tracker, TrackerSequence, Variable2DTracker,
+                      Variable3DTracker)
 
 __version__ = "0.1.0"

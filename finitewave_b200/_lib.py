@@ -89,6 +89,9 @@ def _sig(L):
     L.fwb_sim_set_halo.argtypes = [p, p, p, p, c_int64, p, c_int64, p, p, c_int64, p, c_int64]
     L.fwb_sim_set_slow_offset.argtypes = [p, c_int64]
     L.fwb_sim_halo_sync.argtypes = [p]
+    L.fwb_lat_cross.argtypes = [p, c_int64, c_double, p, p, p, p, p]
+    L.fwb_lat_write.argtypes = [p, c_int64, c_double, p, p]
+    L.fwb_gather_u8.argtypes = [p, p, c_int64, p, p]
 
 
 def lib():

@@ -675,3 +675,77 @@ extern "C" int fwb_weights_unpack(const double *compact_soa, double *dense_aos, 
     FWB_KERNEL_CHECK("weights_unpack_kernel");
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// LocalActivationTime / Period trackers:
+// finitewave/cpuwave2D/tracker/local_activation_time_2d_tracker.py:58-90 (_track,
+// cross_threshold), period_2d_tracker.py:38-52.  Element-wise over every grid node.
+// ---------------------------------------------------------------------------
+namespace fwb {
+// cross = (u >= thr) & !activated; activated |= cross; then nodes with (u < thr) & activated
+// are re-armed (cross_threshold :71-90).  `layer` (may be NULL) is the tracker's current
+// activation layer: *flag is raised if a crossing node already holds a time in it (_track :66)
+__global__ void lat_cross_kernel(const double *u, int64_t n, double thr, uint8_t *activated,
+                                 uint8_t *cross, const double *layer, int *flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i < n) {
+        const double v = u[i];
+        const uint8_t a = activated[i];
+        const bool c = (v >= thr) && a == 0;
+        uint8_t a2 = c ? 1 : a;
+        if (v < thr && a2 == 1) a2 = 0;
+        activated[i] = a2;
+        cross[i] = c ? 1 : 0;
+        hit = c && layer && layer[i] > -1.0;
+    }
+    if (__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+// layer = where(cross, t, layer)   (_track :69)
+__global__ void lat_write_kernel(const uint8_t *cross, int64_t n, double t, double *layer)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && cross[i]) layer[i] = t;
+}
+__global__ void gather_u8_kernel(const uint8_t *src, const int64_t *idx, int64_t k, uint8_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) out[i] = src[idx[i]];
+}
+}  // namespace fwb
+
+extern "C" int fwb_lat_cross(const double *u, int64_t n_nodes, double threshold, uint8_t *activated,
+                             uint8_t *cross, const double *layer, int *flag, fwb_stream_t stream)
+{
+    if (!u || !activated || !cross || n_nodes < 0 || (layer && !flag)) {
+        set_error("fwb_lat_cross: bad argument");
+        return FWB_E_ARG;
+    }
+    if (n_nodes == 0) return 0;
+    fwb::lat_cross_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        u, n_nodes, threshold, activated, cross, layer, flag);
+    FWB_KERNEL_CHECK("lat_cross_kernel");
+    return 0;
+}
+
+extern "C" int fwb_lat_write(const uint8_t *cross, int64_t n_nodes, double t, double *layer,
+                             fwb_stream_t stream)
+{
+    if (!cross || !layer || n_nodes < 0) { set_error("fwb_lat_write: bad argument"); return FWB_E_ARG; }
+    if (n_nodes == 0) return 0;
+    fwb::lat_write_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        cross, n_nodes, t, layer);
+    FWB_KERNEL_CHECK("lat_write_kernel");
+    return 0;
+}
+
+extern "C" int fwb_gather_u8(const uint8_t *src, const int64_t *idx, int64_t k, uint8_t *out,
+                             fwb_stream_t stream)
+{
+    if (!src || !idx || !out || k < 0) { set_error("fwb_gather_u8: bad argument"); return FWB_E_ARG; }
+    if (k == 0) return 0;
+    fwb::gather_u8_kernel<<<(unsigned)((k + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src, idx, k, out);
+    FWB_KERNEL_CHECK("gather_u8_kernel");
+    return 0;
+}

@@ -273,7 +273,9 @@ class CardiacModel:
         native_stims = bool(self.stim_sequence) and self.stim_sequence.all_native()
         trackers = self.tracker_sequence.sequence if self.tracker_sequence else []
         native_tr = [tr for tr in trackers if getattr(tr, "_native", False)]
-        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)]
+        dev_tr = [tr for tr in trackers if getattr(tr, "_device_hook", False)]
+        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)
+                   and not getattr(tr, "_device_hook", False)]
         commands = self.command_sequence.sequence if self.command_sequence else []
         self._live = dict(stims=stims, native_stims=native_stims, native_tr=native_tr,
                           iters=iters, done=0)
@@ -297,17 +299,18 @@ class CardiacModel:
         while done < iters and not finished:
             # ---- plan: how many steps until the next host hook --------------------
             t_sim, step_sim, n = self.t, self.step, 0
-            hook_stim = hook_tracker = False
+            hook_stim = hook_tracker = hook_dev = False
             while done + n < iters and n < chunk_cap:
                 due_s = (not native_stims) and any(t_sim >= s.t and not s.passed for s in stims)
                 due_t = any(tr.gate(t_sim, step_sim) for tr in host_tr)
-                if (due_s or due_t) and n > 0:
+                due_d = any(tr.gate(t_sim, step_sim) for tr in dev_tr)
+                if (due_s or due_t or due_d) and n > 0:
                     break                  # run the n clean steps first
                 t_sim += self.dt
                 step_sim += 1
                 n += 1
-                if due_s or due_t:
-                    hook_stim, hook_tracker = due_s, due_t
+                if due_s or due_t or due_d:
+                    hook_stim, hook_tracker, hook_dev = due_s, due_t, due_d
                     break                  # this single step carries the hook
                 if self._post_hook_due(t_sim, step_sim, commands):
                     break
@@ -325,6 +328,13 @@ class CardiacModel:
             eng.set_time(self.t, self.step)
             eng.run(n)
             host_view_valid = False
+
+            # ---- mid-step device hook: trackers with their own device kernels; they see
+            # the step's pre-update potential (the buffer that was `u` before the swap)
+            if hook_dev:
+                for tr in dev_tr:
+                    if tr.gate(self.t, self.step):
+                        tr._track_device(eng, eng.ubuf[eng.current() ^ 1], self.t)
 
             # ---- mid-step host hook: user-defined trackers (pre-increment view) ------
             if hook_tracker:

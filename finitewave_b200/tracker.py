@@ -7,8 +7,11 @@ point samplers  cpuwave2D/tracker/{action_potential,multi_variable,variable}_2d_
 
 Native trackers (``_native = True``) are evaluated on the device inside the step
 runner -- activation time and ECG are fused into the step kernel -- and only
-their small outputs come back.  Any other Tracker subclass is a host hook: the
-model downloads ``state_vars`` before calling its ``_track()``.
+their small outputs come back.  Device-hook trackers (``_device_hook = True``:
+LocalActivationTime, Period) run their own small kernels on the device potential at
+their sample steps; nothing is downloaded until their output is read.  Any other
+Tracker subclass is a host hook: the model downloads ``state_vars`` before calling
+its ``_track()``.
 """
 import copy
 import ctypes
@@ -22,6 +25,7 @@ from ._lib import check
 
 class Tracker:
     _native = False
+    _device_hook = False
 
     def __init__(self):
         self.model = None
@@ -317,4 +321,152 @@ class Variable2DTracker(MultiVariable2DTracker):
 
 
 class Variable3DTracker(Variable2DTracker):
+    pass
+
+
+# ---- multi-activation trackers --------------------------------------
+class LocalActivationTime2DTracker(Tracker):
+    """Every threshold up-crossing of every node, in layers: a new layer is opened when a
+    crossing node already holds a time in the current one (reference
+    cpuwave2D/tracker/local_activation_time_2d_tracker.py:6-104).  Evaluated on the device
+    (fwb_lat_cross / fwb_lat_write); ``output`` has shape ``(n_layers, *shape)``."""
+    _device_hook = True
+
+    def __init__(self):
+        super().__init__()
+        self.act_t = []
+        self.threshold = -40
+        self.file_name = "local_act_time_2d"
+        self._activated = np.ndarray
+        self._dev = None
+
+    def initialize(self, model):
+        self.model = model
+        self.act_t = [-np.ones_like(self.model.u)]
+        self._activated = np.full(self.model.u.shape, 0, dtype=bool)
+        self._dev = None
+
+    # device state: created from the host attributes on first use, so that values the user
+    # assigned after initialize() are honoured
+    def _ensure_dev(self, engine):
+        if self._dev is not None and self._dev["device"] == engine.device:
+            return self._dev
+        dev = engine.device
+        n = engine.n_nodes
+        self._dev = dict(
+            device=dev,
+            activated=torch.from_numpy(np.ascontiguousarray(self._activated, dtype=np.uint8)
+                                       .reshape(-1)).to(dev),
+            cross=torch.zeros(n, dtype=torch.uint8, device=dev),
+            flag=torch.zeros(1, dtype=torch.int32, device=dev),
+            layers=[torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev)
+                    for a in self.act_t],
+            dirty=False)
+        return self._dev
+
+    def _track_device(self, engine, u, t):
+        d = self._ensure_dev(engine)
+        L, st = engine.L, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n = engine.n_nodes
+        check(L.fwb_lat_cross(ctypes.c_void_p(u.data_ptr()), n, float(self.threshold),
+                              ctypes.c_void_p(d["activated"].data_ptr()),
+                              ctypes.c_void_p(d["cross"].data_ptr()),
+                              ctypes.c_void_p(d["layers"][-1].data_ptr()),
+                              ctypes.c_void_p(d["flag"].data_ptr()), st), "fwb_lat_cross")
+        if int(d["flag"].item()):          # 4-byte read-back: does this sample open a layer?
+            d["layers"].append(torch.full((n,), -1.0, dtype=torch.float64, device=engine.device))
+            d["flag"].zero_()
+        check(L.fwb_lat_write(ctypes.c_void_p(d["cross"].data_ptr()), n, float(t),
+                              ctypes.c_void_p(d["layers"][-1].data_ptr()), st), "fwb_lat_write")
+        d["dirty"] = True
+
+    def _track(self):
+        eng = self.model._engine
+        self._track_device(eng, eng.ubuf[eng.current()], self.model.t)
+
+    def _collect(self, engine=None):
+        d = self._dev
+        if d is None or not d["dirty"]:
+            return
+        shape = self.model.u.shape
+        self.act_t = [a.cpu().numpy().reshape(shape) for a in d["layers"]]
+        self._activated = d["activated"].cpu().numpy().reshape(shape).astype(bool)
+        d["dirty"] = False
+
+    @property
+    def output(self):
+        self._collect()
+        return np.array(self.act_t)
+
+
+class LocalActivationTime3DTracker(LocalActivationTime2DTracker):
+    pass
+
+
+class Period2DTracker(LocalActivationTime2DTracker):
+    """Activation periods at detector cells (reference period_2d_tracker.py:9-86): the
+    crossing detector runs over the whole grid on the device, only the detector cells' bits
+    come back; ``output`` is a pandas DataFrame of the differences of successive activation
+    times per cell, ``act_t`` the layers ``(n_layers, n_cells)``."""
+
+    def __init__(self):
+        super().__init__()
+        self.cell_ind = []
+        self.file_name = "period"
+
+    def initialize(self, model):
+        super().initialize(model)
+        self.act_t = [-np.ones(len(np.atleast_2d(self.cell_ind)))]
+
+    def _ensure_dev(self, engine):
+        if self._dev is not None and self._dev["device"] == engine.device:
+            return self._dev
+        dev = engine.device
+        cells = np.atleast_2d(self.cell_ind)
+        flat = np.ravel_multi_index(tuple(cells.T), engine.shape)
+        self._dev = dict(
+            device=dev,
+            activated=torch.from_numpy(np.ascontiguousarray(self._activated, dtype=np.uint8)
+                                       .reshape(-1)).to(dev),
+            cross=torch.zeros(engine.n_nodes, dtype=torch.uint8, device=dev),
+            idx=torch.from_numpy(flat.astype(np.int64)).to(dev),
+            out=torch.zeros(len(flat), dtype=torch.uint8, device=dev),
+            dirty=False)
+        return self._dev
+
+    def _track_device(self, engine, u, t):
+        d = self._ensure_dev(engine)
+        L, st = engine.L, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(L.fwb_lat_cross(ctypes.c_void_p(u.data_ptr()), engine.n_nodes, float(self.threshold),
+                              ctypes.c_void_p(d["activated"].data_ptr()),
+                              ctypes.c_void_p(d["cross"].data_ptr()), None, None, st),
+              "fwb_lat_cross")
+        k = int(d["idx"].numel())
+        check(L.fwb_gather_u8(ctypes.c_void_p(d["cross"].data_ptr()),
+                              ctypes.c_void_p(d["idx"].data_ptr()), k,
+                              ctypes.c_void_p(d["out"].data_ptr()), st), "fwb_gather_u8")
+        cross = d["out"].cpu().numpy().astype(bool)
+        if np.any(self.act_t[-1][cross] > -1):
+            self.act_t.append(-np.ones(k))
+        self.act_t[-1] = np.where(cross, t, self.act_t[-1])
+        d["dirty"] = True
+
+    def _collect(self, engine=None):
+        d = self._dev
+        if d is None or not d["dirty"]:
+            return
+        self._activated = d["activated"].cpu().numpy().reshape(self.model.u.shape).astype(bool)
+        d["dirty"] = False
+
+    @property
+    def output(self):
+        import pandas as pd
+        lats = pd.DataFrame(np.array(self.act_t).T)
+        return lats.apply(lambda row: np.diff(row[row != -1]), axis=1)
+
+    def write(self):
+        self.output.to_csv(Path(self.path, self.file_name).with_suffix(".csv"))
+
+
+class Period3DTracker(Period2DTracker):
     pass

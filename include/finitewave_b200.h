@@ -188,6 +188,26 @@ FWB_API int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
                         int64_t ld, double *weights, fwb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * LocalActivationTime{2,3}DTracker / Period{2,3}DTracker on the device.
+ * Replace LocalActivationTime2DTracker.cross_threshold + _track
+ * (finitewave/cpuwave2D/tracker/local_activation_time_2d_tracker.py:58-90) and
+ * Period2DTracker._track (period_2d_tracker.py:38-52), which are numpy passes over model.u.
+ *   fwb_lat_cross  cross = (u >= threshold) & !activated; activated updated (armed again
+ *                  once u < threshold); if `layer` is given, *flag |= 1 when a crossing node
+ *                  already holds a time (> -1) in that layer (=> the caller opens a new layer)
+ *   fwb_lat_write  layer = where(cross, t, layer)
+ *   fwb_gather_u8  out[i] = src[idx[i]]  (the detector cells of the period tracker)
+ * All arrays are dense over the grid (n_nodes), device pointers; u is the pre-update
+ * potential of the sampled step.
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_lat_cross(const double *u, int64_t n_nodes, double threshold, uint8_t *activated,
+                  uint8_t *cross, const double *layer, int *flag, fwb_stream_t stream);
+FWB_API int fwb_lat_write(const uint8_t *cross, int64_t n_nodes, double t, double *layer,
+                  fwb_stream_t stream);
+FWB_API int fwb_gather_u8(const uint8_t *src, const int64_t *idx, int64_t k, uint8_t *out,
+                  fwb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * The simulation object: the fused per-time-step path.
  * Replaces, per step, CardiacModel.run's loop body
  * (finitewave/core/model/cardiac_model.py:164-189):

@@ -284,6 +284,25 @@ def make_cases():
         stims=[dict(kind="voltage_coord", t=0.1, value=1, box=[1, 36, 1, 4])],
         trackers=[dict(kind="activation_time", threshold=0.5, step=7, start_time=0.5,
                        end_time=3.0)]))
+    # LocalActivationTime + Period trackers on a re-entrant Barkley wave:
+    # S1-S2 spiral protocol so that nodes activate more than once (several layers)
+    cases.append(dict(
+        name="barkley2d_lat_period", model="barkley", shape=[40, 40],
+        dt=0.01, dr=0.25, t_max=20,
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 40, 0, 5]),
+               dict(kind="voltage_coord", t=3.1, value=1, box=[0, 20, 0, 40])],
+        trackers=[dict(kind="local_activation_time", threshold=0.5, step=2),
+                  dict(kind="period", threshold=0.5, step=1,
+                       cell_ind=[[10, 10], [20, 30], [30, 15]])]))
+    # the 3D classes, AP focal stimulus fired twice
+    cases.append(dict(
+        name="ap3d_lat_period", model="aliev_panfilov", shape=[14, 12, 10],
+        dt=0.01, dr=0.25, t_max=60,
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 3, 0, 12, 0, 10]),
+               dict(kind="voltage_coord", t=35, value=1, box=[0, 3, 0, 12, 0, 10])],
+        trackers=[dict(kind="local_activation_time", threshold=0.5, step=5),
+                  dict(kind="period", threshold=0.5, step=5, cell_ind=[[7, 6, 5], [12, 3, 8]])]))
+
     # SymmetricStencil2D: cell-centred 9-point weights, random fibres,
     # fibrosis and a conductivity map; the apply kernel is the asymmetric 9-point one
     rng = np.random.default_rng(21)
@@ -384,6 +403,15 @@ def build_model(fw, case):
             tr = getattr(fw, "MultiVariable" + sfx + "Tracker")()
             tr.cell_ind = t["cell_ind"]
             tr.var_list = list(t["vars"])
+        elif kind == "local_activation_time":
+            tr = getattr(fw, "LocalActivationTime" + sfx + "Tracker")()
+            if "threshold" in t:
+                tr.threshold = t["threshold"]
+        elif kind == "period":
+            tr = getattr(fw, "Period" + sfx + "Tracker")()
+            tr.cell_ind = t["cell_ind"]
+            if "threshold" in t:
+                tr.threshold = t["threshold"]
         else:
             raise ValueError(kind)
         for k in ("step", "start_time", "end_time"):
@@ -403,6 +431,10 @@ def collect_outputs(case, model, trackers):
         if t["kind"] == "multi_variable":
             for v in t["vars"]:
                 out[f"tracker{i}_{v}"] = np.array(tr.output[v], dtype=np.float64)
+        elif t["kind"] == "period":
+            # the layers (n_layers, n_cells); `output` is a DataFrame of their differences
+            tr.output
+            out[f"tracker{i}"] = np.array(tr.act_t, dtype=np.float64)
         else:
             out[f"tracker{i}"] = np.array(tr.output, dtype=np.float64)
     return out
