@@ -294,6 +294,41 @@ class Engine:
         _as_tensor(host_out).copy_(self.staging, non_blocking=True)
         # staging is reused by the next call on the same stream: ordering is by stream
 
+    # ---- asynchronous checkpoints ---------------------
+    def snapshot_async(self, fills):
+        """Snapshot u and every state row WITHOUT stalling the step loop.
+
+        On the compute stream: one device-to-device copy of u and one compact -> dense
+        scatter per state row into fresh snapshot buffers (HBM speed).  On a separate copy
+        stream, after an event: the device-to-host copies into pinned buffers.  Returns
+        (host_arrays, done_event): host_arrays[0] is u, [1 + slot] the state rows as dense
+        numpy arrays backed by pinned memory; they are valid once done_event has completed.
+        The step loop may continue as soon as this returns.  `fills[slot]` is the value of
+        the nodes the solver does not update (the model's init_* constant)."""
+        dev = self.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        snaps = [torch.empty(self.shape, dtype=torch.float64, device=dev)]
+        snaps[0].copy_(self.ubuf[self.current()], non_blocking=True)
+        for slot in range(self.n_state):
+            d = torch.empty(self.shape, dtype=torch.float64, device=dev)
+            check(self.L.fwb_scatter_compact(_ptr(self.state[slot]), _ptr(d), float(fills[slot]),
+                                             self.n_nodes, _ptr(self.chunk_bits),
+                                             _ptr(self.chunk_base), _stream()),
+                  "fwb_scatter_compact")
+            snaps.append(d)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        hosts = [torch.empty(self.shape, dtype=torch.float64, pin_memory=True) for _ in snaps]
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for h, d in zip(hosts, snaps):
+                h.copy_(d, non_blocking=True)
+                d.record_stream(self._copy_stream)   # freed only after the copy has run
+            done.record(self._copy_stream)
+        return [h.numpy() for h in hosts], done, hosts
+
     def fill_state(self, slot, value):
         self.state[slot].fill_(float(value))
 

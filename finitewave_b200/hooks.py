@@ -9,7 +9,15 @@ firing rules follow the reference so user scripts run unchanged:
                               finitewave/core/state/{state_saver,state_loader}.py
 The model synchronises ``model.__dict__[var]`` with the device around every hook
 (model.CardiacModel.run), so ``execute(model)`` / ``save()`` see plain numpy arrays.
+
+Checkpoints taken DURING a run (a StateSaver whose ``time`` lies before ``t_max``) do not
+stall the step loop: the model snapshots the device state on the compute
+stream, a copy stream moves the snapshot into pinned host memory, and a writer thread
+stores the ``.npy`` files (``AsyncCheckpointWriter``); the files are complete when ``run()``
+returns.  The final checkpoint (``time = -1``) is written from the arrays ``run()`` downloads
+anyway.
 """
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -84,6 +92,37 @@ class StateSaver:
 
     def _save_variable(self, var_path, var):
         np.save(var_path, var)
+
+
+class AsyncCheckpointWriter:
+    """Writer thread(s) of the checkpoints taken while the simulation keeps running."""
+
+    def __init__(self):
+        self.threads = []
+        self.errors = []
+
+    def submit(self, path, names, arrays, done_event, keepalive):
+        def work():
+            try:
+                done_event.synchronize()            # the device-to-host copies have landed
+                Path(path).mkdir(parents=True, exist_ok=True)
+                for name, a in zip(names, arrays):
+                    np.save(Path(path).joinpath(name + ".npy"), a)
+            except Exception as e:                  # re-raised by wait()
+                self.errors.append(e)
+            finally:
+                keepalive.clear()
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        self.threads.append(th)
+
+    def wait(self):
+        for th in self.threads:
+            th.join()
+        self.threads = []
+        if self.errors:
+            e, self.errors = self.errors[0], []
+            raise e
 
 
 class StateSaverCollection(StateSaver):

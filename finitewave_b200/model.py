@@ -361,10 +361,11 @@ class CardiacModel:
                     self._upload()           # commands may have edited anything
                     host_view_valid = True
                 if self.state_saver and self._saver_due(self.t):
-                    if not host_view_valid:
-                        self._download()
-                        host_view_valid = True
-                    self.state_saver.save()
+                    if not self._save_async(host_view_valid):
+                        if not host_view_valid:
+                            self._download()
+                            host_view_valid = True
+                        self.state_saver.save()
                 if self.check_termination():
                     if self.state_saver:
                         if not host_view_valid:
@@ -378,8 +379,37 @@ class CardiacModel:
         if not host_view_valid:
             self._download()
         self._collect_native()
+        if getattr(self, "_ckpt_writer", None) is not None:
+            self._ckpt_writer.wait()          # checkpoint files are complete on return
         self.gpu_launches = eng.launch_count() - launches0
         self._live = None
+
+    def _save_async(self, host_view_valid):
+        """Mid-run checkpoint without stalling the step loop.  Applies to
+        the built-in StateSaver class (a subclass may override how variables are written) when
+        the device holds the only current copy and no state array carries user values on
+        nodes the solver does not update.  Returns False to request the synchronous path."""
+        from .hooks import AsyncCheckpointWriter, StateSaver, StateSaverCollection
+        if host_view_valid or getattr(self, "async_checkpoints", True) is False:
+            return False
+        sv = self.state_saver
+        savers = list(sv.savers) if isinstance(sv, StateSaverCollection) else [sv]
+        due = [x for x in savers if x.due()]
+        if not due or any(type(x) is not StateSaver for x in due):
+            return False
+        if any(getattr(self, "_keep_offnodes", [])) or self.t >= self.t_max:
+            return False
+        if list(self.state_vars) != ["u"] + list(self._STATE):
+            return False
+        eng = self._engine
+        fills = [self._init_value(name) for name in self._STATE]
+        arrays, done, keep = eng.snapshot_async(fills)
+        if getattr(self, "_ckpt_writer", None) is None:
+            self._ckpt_writer = AsyncCheckpointWriter()
+        for x in due:
+            self._ckpt_writer.submit(x.path, list(self.state_vars), arrays, done, keep)
+            x.passed = True
+        return True
 
     def _saver_due(self, t):
         savers = getattr(self.state_saver, "savers", None)
