@@ -11,6 +11,8 @@ There is no CPU fallback: without the CUDA library or a CUDA device every comput
 entry raises ``FwbError``.
 """
 from ._lib import FwbError
+from .fibrosis import (Diffuse2DPattern, Diffuse3DPattern, FibrosisPattern, Structural2DPattern,
+                       Structural3DPattern)
 from .hooks import Command, CommandSequence, StateLoader, StateSaver, StateSaverCollection
 from .model import (AlievPanfilov2D, AlievPanfilov3D, Barkley2D, Barkley3D, BuenoOrovio2D,
                     BuenoOrovio3D, CardiacModel, Courtemanche2D, Courtemanche3D,

@@ -749,3 +749,85 @@ extern "C" int fwb_gather_u8(const uint8_t *src, const int64_t *idx, int64_t k, 
     FWB_KERNEL_CHECK("gather_u8_kernel");
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Fibrosis patterns on the device: Diffuse{2,3}DPattern and
+// Structural{2,3}DPattern (finitewave/cpuwave2D/fibrosis/diffuse_2d_pattern.py:63-87,
+// structural_2d_pattern.py:71-120, cpuwave3D/fibrosis/*.py).  Inside the box every node
+// (diffuse) or every block anchored at the box origin and clipped at its end (structural)
+// becomes 2 with probability `density` and 1 otherwise -- the box is overwritten, as in the
+// reference.  The reference draws from numpy's / random's global state; here the draw is a
+// hash of (seed, global block id), so a tissue is reproducible and identical however it is
+// cut into slabs.
+// ---------------------------------------------------------------------------
+namespace fwb {
+struct PatternArgs {
+    int dim;
+    int64_t shape[3];     // stored (local) shape, padded with 1
+    int64_t lo[3], hi[3]; // box in GLOBAL indices, half open
+    int64_t len[3];       // block edge lengths (1 = diffuse)
+    int64_t nb[3];        // blocks per axis
+    int64_t off[3];       // global index of local index 0 per axis (slab runs: slowest real axis)
+    double density;
+    unsigned long long seed;
+};
+__host__ __device__ inline double hash_u01(unsigned long long id, unsigned long long seed)
+{
+    unsigned long long h = id + seed * 0x9E3779B97F4A7C15ULL;     // splitmix64 finaliser
+    h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ULL;
+    h ^= h >> 27; h *= 0x94D049BB133111EBULL;
+    h ^= h >> 31;
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+__global__ void pattern_kernel(int8_t *mesh, const __grid_constant__ PatternArgs A)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = A.shape[0] * A.shape[1] * A.shape[2];
+    if (n >= total) return;
+    int64_t g[3];
+    g[2] = n % A.shape[2] + A.off[2];
+    g[1] = (n / A.shape[2]) % A.shape[1] + A.off[1];
+    g[0] = n / (A.shape[2] * A.shape[1]) + A.off[0];
+    int64_t b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (g[a] < A.lo[a] || g[a] >= A.hi[a]) return;
+        b[a] = (g[a] - A.lo[a]) / A.len[a];
+    }
+    const unsigned long long id = (unsigned long long)((b[0] * A.nb[1] + b[1]) * A.nb[2] + b[2]);
+    mesh[n] = hash_u01(id, A.seed) <= A.density ? 2 : 1;
+}
+}  // namespace fwb
+
+extern "C" int fwb_pattern_fibrosis(int8_t *mesh, int dim, const int64_t *shape, const int64_t *box,
+                                    const int64_t *block, double density, unsigned long long seed,
+                                    int64_t slow_offset, fwb_stream_t stream)
+{
+    if (!mesh || (dim != 2 && dim != 3) || !shape || !box || !block) {
+        set_error("fwb_pattern_fibrosis: bad argument");
+        return FWB_E_ARG;
+    }
+    fwb::PatternArgs A;
+    const int pad = 3 - dim;          // 2D grids are (1, n_i, n_j)
+    for (int a = 0; a < 3; ++a) { A.shape[a] = 1; A.lo[a] = 0; A.hi[a] = 1; A.len[a] = 1; }
+    for (int a = 0; a < dim; ++a) {
+        A.shape[a + pad] = shape[a];
+        A.lo[a + pad] = box[2 * a];
+        A.hi[a + pad] = box[2 * a + 1];
+        A.len[a + pad] = block[a];
+        if (block[a] < 1 || shape[a] < 0) { set_error("fwb_pattern_fibrosis: bad block / shape"); return FWB_E_ARG; }
+    }
+    for (int a = 0; a < 3; ++a) {
+        const int64_t ext = A.hi[a] > A.lo[a] ? A.hi[a] - A.lo[a] : 0;
+        A.nb[a] = (ext + A.len[a] - 1) / A.len[a];
+        if (A.nb[a] < 1) A.nb[a] = 1;
+    }
+    A.dim = dim; A.density = density; A.seed = seed;
+    A.off[0] = A.off[1] = A.off[2] = 0;
+    A.off[pad] = slow_offset;         // slabs are cut along the slowest real axis
+    const int64_t total = A.shape[0] * A.shape[1] * A.shape[2];
+    if (total == 0) return 0;
+    fwb::pattern_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mesh, A);
+    FWB_KERNEL_CHECK("pattern_kernel");
+    return 0;
+}

@@ -188,6 +188,24 @@ FWB_API int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
                         int64_t ld, double *weights, fwb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Fibrosis patterns on the device.  Replaces the numpy generators
+ * Diffuse{2,3}DPattern.generate / Structural{2,3}DPattern.generate
+ * (finitewave/cpuwave2D/fibrosis/diffuse_2d_pattern.py:63-87, structural_2d_pattern.py:71-120,
+ * finitewave/cpuwave3D/fibrosis/*.py) for meshes that only exist in device memory.
+ *   mesh         int8 (*shape), device; the box is overwritten with 1 / 2
+ *   box          2*dim global indices [x1, x2, y1, y2(, z1, z2)), half open
+ *   block        dim block edge lengths (all 1 = diffuse); blocks are anchored at the box
+ *                origin and clipped at its end
+ *   density      probability of a node / block being fibrotic
+ *   seed         the draw is a hash of (seed, global block id): reproducible and independent
+ *                of how the tissue is cut into slabs (the reference uses numpy's global state)
+ *   slow_offset  global index of local slice 0 of the slowest axis
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_pattern_fibrosis(int8_t *mesh, int dim, const int64_t *shape, const int64_t *box,
+                         const int64_t *block, double density, unsigned long long seed,
+                         int64_t slow_offset, fwb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * LocalActivationTime{2,3}DTracker / Period{2,3}DTracker on the device.
  * Replace LocalActivationTime2DTracker.cross_threshold + _track
  * (finitewave/cpuwave2D/tracker/local_activation_time_2d_tracker.py:58-90) and
