@@ -493,11 +493,7 @@ template <> struct Model<FWB_MODEL_TP06> {
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
 #ifdef __CUDA_ARCH__
-#ifdef FWB_TP06_POLICY_FAST
-        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
-#else
         if (fabs(u) < FAST_MATH_U_LIMIT) ionic_fast(u, un, io, c);
-#endif
         else
 #endif
             ionic_impl<IO, LibMath>(u, un, io, c);
@@ -522,22 +518,11 @@ template <> struct Model<FWB_MODEL_TP06> {
     {
         return fma(x - inf, fexp_fast_neg(-dt * rtau), inf);
     }
-    // state values are requested one gate ahead of their use (FWB_EARLY ... FWB_LATE): at
-    // ~13 cycles per issued instruction and warp, one gate's worth of FP64 work covers the
-    // HBM latency, at the price of one or two live registers
-#ifdef FWB_TP06_EARLY_LD
-#define FWB_EARLY(...) __VA_ARGS__
-#define FWB_LATE(var, q) var
-#else
-#define FWB_EARLY(...)
-#define FWB_LATE(var, q) io.ld(q)
-#endif
     template <class IO>
     FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c)
     {
         const double dt = c.dt;
         const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
-        FWB_EARLY(const double m0 = io.ld(5), h0 = io.ld(6), j0 = io.ld(7);)
         const double Ek = c.RTONF * (c.l_ko - log(Ki));
         const double Ena = c.RTONF * (c.l_nao - log(nai));
         const double Eks = c.RTONF * (c.l_kpn - log(fma(c.pKNa, nai, Ki)));
@@ -551,7 +536,6 @@ template <> struct Model<FWB_MODEL_TP06> {
         const double n24 = fexp_fast(u * (-1. / 24.)), n12 = n24 * n24, n6 = n12 * n12;
 
         // ---- I_Na (calc_ina :242-318)
-        FWB_EARLY(const double cass_e = io.ld(2), d0 = io.ld(13);)
         double ina;
         {
             const double A = g5 + c.km1;                  // alpha_m = g5 / A
@@ -576,19 +560,17 @@ template <> struct Model<FWB_MODEL_TP06> {
                 const double nb = 0.02424 * fexp_fast(-0.01052 * u);
                 rate_j = fma(na, b, nb * a) * frcp(a * b);
             }
-            const double m = rlf(m_inf, FWB_LATE(m0, 5), dt, rtau_m);
-            const double h = rlf(h_inf, FWB_LATE(h0, 6), dt, rate_h);
-            const double j = rlf(h_inf, FWB_LATE(j0, 7), dt, rate_j);
+            const double m = rlf(m_inf, io.ld(5), dt, rtau_m);
+            const double h = rlf(h_inf, io.ld(6), dt, rate_h);
+            const double j = rlf(h_inf, io.ld(7), dt, rate_j);
             io.st(5, m); io.st(6, h); io.st(7, j);
             ina = c.gna * m * m * m * h * j * (u - Ena);
         }
 
         // ---- I_CaL (calc_ical :321-380)
-        const double cass = FWB_LATE(cass_e, 2);
-        FWB_EARLY(const double s0 = io.ld(12), r0 = io.ld(11);)
+        const double cass = io.ld(2);
         double ical;
         {
-            FWB_EARLY(const double f0 = io.ld(14);)
             const double d_inf = g75 * frcp(g75 + c.kd1);
             const double A = 1. + fexp_fast((-35. - u) * (1. / 13.));   // Ad = 1.4 / A + 0.25
             const double B = fma(c.kd2, g5, 1.);                        // Bd = 1.4 / B
@@ -596,9 +578,8 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double P = fma(0.25, A, 1.4) * 1.4;                   // Ad Bd = P / (A B)
             const double AB = A * B;
             const double rtau_d = AB * Cn * frcp(fma(P, Cn, g20 * AB));
-            const double d = rlf(d_inf, FWB_LATE(d0, 13), dt, rtau_d);
+            const double d = rlf(d_inf, io.ld(13), dt, rtau_d);
             io.st(13, d);
-            FWB_EARLY(const double f20 = io.ld(15);)
 
             const double E30 = fma(c.kf3, g10, 1.);
             const double f_inf = frcp(fma(c.kf1, g7, 1.));
@@ -607,9 +588,8 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double Df = Bn * E30;                                 // Cf = 180 / E30 + 20
             const double Nf = fma(200. * g10, E30, 180. * Bn);
             const double rtau_f = Df * frcp(fma(Af + 20., Df, Nf));
-            const double f = rlf(f_inf, FWB_LATE(f0, 14), dt, rtau_f);
+            const double f = rlf(f_inf, io.ld(14), dt, rtau_f);
             io.st(14, f);
-            FWB_EARLY(const double fcass0 = io.ld(16);)
 
             const double f2_inf = fma(0.67, frcp(fma(c.kf4, g7, 1.)), 0.33);
             const double Af2 = 600. * fexp_fast(-(u + 25.) * (u + 25.) * (1. / 170.));
@@ -617,14 +597,14 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double Df2 = Bn2 * E30;                               // Cf2 = 16 / E30
             const double Nf2 = fma(31. * g10, E30, 16. * Bn2);
             const double rtau_f2 = Df2 * frcp(fma(Af2, Df2, Nf2));
-            const double f2 = rlf(f2_inf, FWB_LATE(f20, 15), dt, rtau_f2);
+            const double f2 = rlf(f2_inf, io.ld(15), dt, rtau_f2);
             io.st(15, f2);
 
             const double cs = cass * (1. / 0.05);
             const double cq = fma(cs, cs, 1.);
             const double fcass_inf = fma(0.6, frcp(cq), 0.4);
             const double rtau_fcass = cq * frcp(fma(2., cq, 80.));
-            const double fcass = rlf(fcass_inf, FWB_LATE(fcass0, 16), dt, rtau_fcass);
+            const double fcass = rlf(fcass_inf, io.ld(16), dt, rtau_fcass);
             io.st(16, fcass);
 
             const double e2 = fexp_fast(2. * (u - 15.) * c.F_RT);
@@ -633,7 +613,6 @@ template <> struct Model<FWB_MODEL_TP06> {
         }
 
         // ---- I_to (calc_ito :383-413)
-        FWB_EARLY(const double xr10 = io.ld(8), xr20 = io.ld(9);)
         double ito;
         {
             const double r_inf = frcp(fma(c.kr1, n6, 1.));
@@ -643,14 +622,13 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double G = fma(85., fexp_fast(-(u + 45.) * (u + 45.) * (1. / 320.)), 3.);
             const double S2 = fma(c.ks2, g5, 1.);                       // tau_s = G + 5 / S2
             const double rtau_s = S2 * frcp(fma(G, S2, 5.));
-            const double sg = rlf(s_inf, FWB_LATE(s0, 12), dt, rtau_s);
-            const double r = rlf(r_inf, FWB_LATE(r0, 11), dt, rtau_r);
+            const double sg = rlf(s_inf, io.ld(12), dt, rtau_s);
+            const double r = rlf(r_inf, io.ld(11), dt, rtau_r);
             io.st(11, r); io.st(12, sg);
             ito = c.gto * r * sg * (u - Ek);
         }
 
         // ---- I_Kr (calc_ikr :416-452)
-        FWB_EARLY(const double xs0 = io.ld(10);)
         double ikr;
         {
             const double xr1_inf = g7 * frcp(g7 + c.kx1);
@@ -660,8 +638,8 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double xr2_inf = n24 * frcp(n24 + c.kx3);
             // tau_xr2 = 3 g20 / (g20 + kx4) * 1.12 / (1 + kx5 g20)
             const double rtau_xr2 = (g20 + c.kx4) * fma(c.kx5, g20, 1.) * (i20 * (1. / 3.36));
-            const double xr1 = rlf(xr1_inf, FWB_LATE(xr10, 8), dt, rtau_xr1);
-            const double xr2 = rlf(xr2_inf, FWB_LATE(xr20, 9), dt, rtau_xr2);
+            const double xr1 = rlf(xr1_inf, io.ld(8), dt, rtau_xr1);
+            const double xr2 = rlf(xr2_inf, io.ld(9), dt, rtau_xr2);
             io.st(8, xr1); io.st(9, xr2);
             ikr = c.gkr_sqrt * xr1 * xr2 * (u - Ek);
         }
@@ -673,12 +651,11 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double sq = sqrt(fma(c.kxs2, n6, 1.));                // Axs = 1400 / sq
             const double sb = sq * fma(c.kxs3, g15, 1.);                // Bxs = 1 / (1 + kxs3 g15)
             const double rtau_xs = sb * frcp(fma(80., sb, 1400.));      // tau_xs = 1400 / sb + 80
-            const double xs = rlf(xs_inf, FWB_LATE(xs0, 10), dt, rtau_xs);
+            const double xs = rlf(xs_inf, io.ld(10), dt, rtau_xs);
             io.st(10, xs);
             iks = c.gks * xs * xs * (u - Eks);
         }
 
-        FWB_EARLY(const double casr_e = io.ld(1), rr0 = io.ld(17);)
         // ---- I_K1 (calc_ik1 :488-514): rec = ak1 / (ak1 + bk1), ak1 = 0.1 / a, bk1 = n / b
         const double y = u - Ek;
         double ik1;
@@ -717,11 +694,11 @@ template <> struct Model<FWB_MODEL_TP06> {
         un -= dt * (ikr + iks + ik1 + ito + ina + ibna + ical + ibca + inak + inaca + ipca + ipk);
 
         // ---- calcium handling (calc_irel :700-730 ... calc_cass :831-872)
-        const double casr = FWB_LATE(casr_e, 1);
+        const double casr = io.ld(1);
         const double cass2 = cass * cass;
         double irel;
         {
-            double rr = FWB_LATE(rr0, 17);
+            double rr = io.ld(17);
             const double casr2 = casr * casr;
             const double kCaSR = fma(-c.maxsr_m_minsr * casr2, frcp(casr2 + c.EC2), c.maxsr);
             const double k2 = c.k2_ * kCaSR;
@@ -751,9 +728,6 @@ template <> struct Model<FWB_MODEL_TP06> {
             io.st(2, (sqrt(fma(bcss, bcss, 4 * ccss)) - bcss) * 0.5);
         }
     }
-
-#undef FWB_EARLY
-#undef FWB_LATE
 
     template <class IO, class E>
     FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)

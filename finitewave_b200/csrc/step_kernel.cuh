@@ -14,12 +14,14 @@
 // so warps read contiguous, fully used lines even on 30 %-fibrotic or
 // shell-shaped tissues.  Neighbour values of u come from global memory through
 // L1 (read-only path); the work list's tile order makes the neighbour lines L1
-// hits.  State values are loaded where the model needs them and stored as soon
-// as they are final, which keeps the 19-state TP06 kernel at 2 blocks per SM.
+// hits.  State values are read where the model needs them and stored as soon
+// as they are final, which keeps the 19-state TP06 kernel at 64-80 registers.
 //
 // Two kernels implement this step:
-//   step_kernel      one block per tile, every operand through LDG (all models;
-//                    the compute-bound LR91 / TP06 always use it)
+//   step_kernel      one block per tile (all models; the FP64-bound LR91 / TP06 /
+//                    Courtemanche always use it).  STAGED = 0: every operand through LDG;
+//                    STAGED = 1 / 2: the tile's state rows (and weight rows) arrive by TMA
+//                    bulk copies in shared memory, so the FP64 work never waits on HBM
 //   step_kernel_tma  persistent blocks (grid = resident blocks of the GPU) that walk
 //                    the tile list; the tile's weight rows and state rows -- the
 //                    HBM streams, contiguous in the tile-ordered compact layout --
@@ -35,7 +37,6 @@
 // (NVLink), and the last of them to finish raises the neighbour's flag for the
 // next step.  Interior blocks never wait: the exchange overlaps the interior.
 #pragma once
-#include <stdlib.h>
 #include "fwb_common.cuh"
 #include "models.cuh"
 
@@ -166,7 +167,8 @@ __host__ __device__ constexpr int tma_nth(uint32_t mask, int n)
 // in the middle of the FP64 work.  With the tile-ordered compact layout a tile's state rows
 // are contiguous, so one thread of the block fetches them with TMA bulk copies into shared
 // memory while all threads wait for the stencil operands anyway; the model then reads its
-// state at shared-memory latency (step_kernel<..., STAGED = true>).
+// state at shared-memory latency (step_kernel<..., STAGED>).  The two switches exist for A/B
+// measurements (scripts/gpu_ab.sh).
 #ifdef FWB_NO_STAGE
 template <class M> constexpr bool stage_state() { return false; }
 #else
@@ -231,11 +233,7 @@ template <class M> struct StateIOTma {
 struct StateIO {
     double *base;
     int64_t stride;
-#ifdef FWB_STATE_LD_CA
-    __device__ __forceinline__ double ld(int q) const { return base[(int64_t)q * stride]; }
-#else
     __device__ __forceinline__ double ld(int q) const { return ld_stream(base + (int64_t)q * stride); }
-#endif
     __device__ __forceinline__ void st(int q, double v) const { st_stream(base + (int64_t)q * stride, v); }
     // pull every row this node will read towards the SM without holding registers: the
     // models with many state arrays load them where they are used (register budget), and
@@ -245,11 +243,7 @@ struct StateIO {
 #pragma unroll
         for (int q = 0; q < 32; ++q)
             if ((MASK >> q) & 1u) {
-#ifdef FWB_PREFETCH_L2
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)q * stride));
-#else
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (int64_t)q * stride));
-#endif
             }
     }
 };
@@ -652,38 +646,6 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
     const int64_t blocks = step_blocks(k.g);
     if (blocks <= 0) return 0;
-    static int carve = -2;
-    if (carve == -2) {
-        const char *e = getenv("FWB_CARVEOUT");          // experiment: L1 / shared split
-        carve = e ? atoi(e) : -1;
-        if (carve >= 0)
-            cudaFuncSetAttribute(step_kernel<M, DIM, ST, TRACK, HALO>,
-                                 cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
-    if constexpr (stage_state<M>()) {
-        if (k.tile_base && k.records) {
-            // everything by TMA when three such blocks fit an SM and no ECG sample is due
-            // (its reduction buffer would cost the third block); else the state rows only
-            constexpr int K = Stencil<DIM, ST>::K;
-            constexpr bool FULL = !TRACK && stage_weights<M>() &&
-                                  3 * (StageCfg<M, K, 2>::SMEM + 1024 + 64) <= 228 * 1024;
-            if constexpr (FULL) {
-                auto kern = step_kernel<M, DIM, ST, TRACK, HALO, 2>;
-                static bool attr = false;
-                if (!attr) {
-                    FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)StageCfg<M, K, 2>::SMEM));
-                    attr = true;
-                }
-                kern<<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 2>::SMEM, s>>>(a);
-            } else {
-                step_kernel<M, DIM, ST, TRACK, HALO, 1>
-                    <<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 1>::SMEM, s>>>(a);
-            }
-            FWB_KERNEL_CHECK("step_kernel (staged)");
-            return 0;
-        }
-    }
     step_kernel<M, DIM, ST, TRACK, HALO><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
     FWB_KERNEL_CHECK("step_kernel");
     return 0;
