@@ -302,3 +302,87 @@ def test_user_defined_tracker_and_stim_are_host_hooks(fw):
                        dict(kind="voltage_coord", t=1.0, value=0.9, box=[30, 34, 30, 34])])
     ref = oracle.simulate(case)
     assert np.array_equal(model.u, ref["u"]) and np.array_equal(model.v, ref["v"])
+
+
+# ---- the "next" rows, with the reference's own assertions -----------------------
+def test_local_activation_time_2d_tracker(fw):
+    """tests/test_trackers_2d.py:149-181: two waves -> two LAT layers, speeds in [1.5, 2]."""
+    model = cable_model(fw)
+    tracker = fw.LocalActivationTime2DTracker()
+    tracker.threshold, tracker.step, tracker.start_time = 0.5, 1, 0
+    seq = fw.TrackerSequence()
+    seq.add_tracker(tracker)
+    model.tracker_sequence = seq
+    model.stim_sequence.add_stim(fw.StimVoltageCoord2D(45, 1, 0, 5, 0, 10))
+    model.t_max = 50
+    model.run()
+    lats = tracker.output
+    assert lats is not None and len(lats) == 2, "Every cell should have two LAT values"
+    lat1, lat2 = lats[:, 10, 1]
+    assert lat1 < lat2
+    assert 1.5 <= 5 * model.dr / lat1 <= 2
+    assert 1.5 <= 5 * model.dr / (lat2 - 45) <= 2
+
+
+def test_local_activation_time_3d_tracker(fw):
+    """tests/test_trackers_3d.py (cable along the first axis): same assertions in 3D."""
+    tissue = fw.CardiacTissue3D([12, 3, 3])
+    seq = fw.StimSequence()
+    seq.add_stim(fw.StimCurrentCoord3D(0, 5, 0.5, 0, 5, 0, 3, 0, 3))
+    seq.add_stim(fw.StimVoltageCoord3D(45, 1, 0, 5, 0, 3, 0, 3))
+    model = fw.AlievPanfilov3D()
+    model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 50, False
+    model.cardiac_tissue, model.stim_sequence = tissue, seq
+    tracker = fw.LocalActivationTime3DTracker()
+    tracker.threshold, tracker.step = 0.5, 1
+    ts = fw.TrackerSequence()
+    ts.add_tracker(tracker)
+    model.tracker_sequence = ts
+    model.run()
+    lats = tracker.output
+    assert len(lats) == 2
+    lat1, lat2 = lats[:, 10, 1, 1]
+    assert 1.5 <= 5 * model.dr / lat1 <= 2 and 1.5 <= 5 * model.dr / (lat2 - 45) <= 2
+
+
+def test_spiral_wave_period_2d_tracker(fw):
+    """tests/test_trackers_2d.py:25-40, :234-258: Barkley spiral, detector periods 3.5 +- 0.2."""
+    ni = nj = 100
+    tissue = fw.CardiacTissue2D([ni, nj])
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, 1, 0, ni, 0, 3))
+    stims.add_stim(fw.StimVoltageCoord2D(5, 1, 0, ni // 2, 0, nj))
+    model = fw.Barkley2D()
+    model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 20, False
+    model.cardiac_tissue, model.stim_sequence = tissue, stims
+    tracker = fw.Period2DTracker()
+    tracker.cell_ind = np.array([[80, 80], [20, 70], [40, 10], [25, 90]])
+    tracker.threshold, tracker.start_time, tracker.step = 0.5, 10, 10
+    seq = fw.TrackerSequence()
+    seq.add_tracker(tracker)
+    model.tracker_sequence = seq
+    model.run()
+    periods = tracker.output
+    assert periods is not None and len(periods) > 0
+    mean = np.nanmean(np.array([np.mean(x) if len(x) > 0 else np.nan for x in periods]))
+    assert mean == pytest.approx(3.5, abs=0.2)
+
+
+def test_fibrosis_patterns_reference_assertions(fw):
+    """tests/test_fibrosis_2d.py, test_fibrosis_3d.py: shape, values in {1, 2}, density of the
+    sub-region within 0.01 (diffuse) / 0.05 (structural)."""
+    shape, (x1, x2, y1, y2) = (1000, 1000), (100, 900, 200, 800)
+    res = fw.Diffuse2DPattern(density=0.3, x1=x1, x2=x2, y1=y1, y2=y2).generate(shape=shape)
+    assert res.shape == shape and np.all(np.isin(res, [1, 2]))
+    assert abs(np.mean(res[x1:x2, y1:y2] == 2) - 0.3) < 0.01
+    res = fw.Structural2DPattern(density=0.4, length_i=5, length_j=4, x1=x1, x2=x2, y1=y1,
+                                 y2=y2).generate(shape=shape)
+    assert res.shape == shape and np.all(np.isin(res, [1, 2]))
+    assert abs(np.mean(res[x1:x2, y1:y2] == 2) - 0.4) < 0.05
+    shape3, box = (100, 100, 100), (10, 90, 20, 80, 30, 70)
+    res = fw.Diffuse3DPattern(*box, 0.3).generate(shape=shape3)
+    sub = res[box[0]:box[1], box[2]:box[3], box[4]:box[5]]
+    assert res.shape == shape3 and np.all(np.isin(res, [1, 2])) and abs(np.mean(sub == 2) - 0.3) < 0.01
+    res = fw.Structural3DPattern(*box, 0.4, 5, 4, 3).generate(shape=shape3)
+    sub = res[box[0]:box[1], box[2]:box[3], box[4]:box[5]]
+    assert np.all(np.isin(res, [1, 2])) and abs(np.mean(sub == 2) - 0.4) < 0.05
