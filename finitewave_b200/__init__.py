@@ -30,7 +30,7 @@ from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker,
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,
                       ECG3DTracker, LocalActivationTime2DTracker, LocalActivationTime3DTracker,
                       MultiVariable2DTracker, MultiVariable3DTracker, Period2DTracker,
-                      Period3DTracker, Tracker, TrackerSequence, Variable2DTracker,
-                      Variable3DTracker)
+                      Period3DTracker, SpiralWaveCore2DTracker, SpiralWaveCore3DTracker, Tracker,
+                      TrackerSequence, Variable2DTracker, Variable3DTracker)
 
 __version__ = "0.1.0"

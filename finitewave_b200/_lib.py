@@ -92,6 +92,7 @@ def _sig(L):
     L.fwb_lat_cross.argtypes = [p, c_int64, c_double, p, p, p, p, p]
     L.fwb_lat_write.argtypes = [p, c_int64, c_double, p, p]
     L.fwb_gather_u8.argtypes = [p, p, c_int64, p, p]
+    L.fwb_tip_scan.argtypes = [p, p, c_int, POINTER(c_int64), c_double, p, ctypes.c_uint, p, p]
     L.fwb_pattern_fibrosis.argtypes = [p, c_int, POINTER(c_int64), POINTER(c_int64),
                                        POINTER(c_int64), c_double, ctypes.c_uint64, c_int64, p]
 

@@ -831,3 +831,98 @@ extern "C" int fwb_pattern_fibrosis(int8_t *mesh, int dim, const int64_t *shape,
     FWB_KERNEL_CHECK("pattern_kernel");
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// SpiralWaveCore{2,3}DTracker:
+// finitewave/cpuwave2D/tracker/spiral_wave_core_2d_tracker.py:108-248 (_correct_tip_pos,
+// _apply_threshold, _track_tip_line), cpuwave3D/tracker/spiral_wave_core_3d_tracker.py:30-48
+// (one scan per slice of the LAST axis).  One thread per 2x2 cell; the arithmetic is the
+// reference's, operation by operation (the file is compiled without FMA contraction), so
+// the tip coordinates are bit-identical.  Output rows {x, y, cell key}; the key
+// ((k * n_i + i) * n_j + j) restores the reference's scan order on the host.
+// ---------------------------------------------------------------------------
+namespace fwb {
+struct TipArgs {
+    const double *u_prev, *u;
+    int64_t n_i, n_j, n_k;      // n_k = 1 in 2D
+    int64_t s_i, s_j;           // flat strides of axis i and j (2D: n_j, 1; 3D: n_j*n_k, n_k)
+    double thr;
+    double *out;                // [capacity][3]
+    unsigned *count;
+    unsigned capacity;
+};
+__device__ __forceinline__ int tip_threshold(const double *p, int64_t s_i, int64_t s_j, double thr)
+{
+    const double a = p[0], b = p[s_i], c = p[s_j], d = p[s_i + s_j];
+    if (a >= thr && (b < thr || c < thr || d < thr)) return 1;
+    if (a < thr && (b >= thr || c >= thr || d >= thr)) return 1;
+    return 0;
+}
+__global__ void tip_scan_kernel(const __grid_constant__ TipArgs A)
+{
+    constexpr int64_t delta = 5;                    // safety margin of _track_tip_line
+    const int64_t wi = A.n_i - 2 * delta, wj = A.n_j - 2 * delta;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi <= 0 || wj <= 0 || q >= wi * wj * A.n_k) return;
+    const int64_t j = q % wj + delta, i = (q / wj) % wi + delta, k = q / (wj * wi);
+    const int64_t n = i * A.s_i + j * A.s_j + k;    // the last axis has stride 1 in 3D;
+                                                    // in 2D n_k = 1, k = 0, s_j = 1
+    const double *u = A.u_prev + n, *v = A.u + n;
+    const int64_t si = A.s_i, sj = A.s_j;
+    if (tip_threshold(u, si, sj, A.thr) != 1 || tip_threshold(v, si, sj, A.thr) != 1) return;
+    const double thr = A.thr;
+    // _correct_tip_pos :124-170
+    const double AC = add(add(add(u[0], -u[sj]), u[si + sj]), -u[si]);
+    const double GC = add(u[sj], -u[0]);
+    const double BC = add(u[si], -u[0]);
+    const double DC = add(u[0], -thr);
+    const double AD = add(add(add(v[0], -v[sj]), v[si + sj]), -v[si]);
+    const double GD = add(v[sj], -v[0]);
+    const double BD = add(v[si], -v[0]);
+    const double DD = add(v[0], -thr);
+    const double Q = add(mul(BC, AD), -mul(BD, AC));
+    const double R = add(mul(GC, AD), -mul(GD, AC));
+    const double S = add(mul(DC, AD), -mul(DD, AC));
+    const double QOnR = __ddiv_rn(Q, R), SOnR = __ddiv_rn(S, R);
+    const double T = mul(AC, QOnR);
+    const double U = add(add(mul(AC, SOnR), -BC), mul(GC, QOnR));
+    const double V = add(mul(GC, SOnR), -DC);
+    const double disc = add(mul(U, U), -mul(mul(4., T), V));
+    if (disc < 0) return;
+    const double T2 = mul(2., T);
+    if (T2 == 0.) return;
+    const double sq = __dsqrt_rn(disc);
+    const double xn = __ddiv_rn(add(-U, -sq), T2), xp = __ddiv_rn(add(-U, sq), T2);
+    const double yn = add(mul(-QOnR, xn), -SOnR), yp = add(mul(-QOnR, xp), -SOnR);
+    double cx, cy;
+    if (0 <= xn && xn <= 1 && 0 <= yn && yn <= 1) { cx = xn; cy = yn; }
+    else if (0 <= xp && xp <= 1 && 0 <= yp && yp <= 1) { cx = xp; cy = yp; }
+    else return;
+    const unsigned slot = atomicAdd(A.count, 1u);
+    if (slot < A.capacity) {
+        A.out[3 * slot] = add((double)j, cy);        // out.append([j + correction[1], i + correction[0]])
+        A.out[3 * slot + 1] = add((double)i, cx);
+        A.out[3 * slot + 2] = (double)((k * A.n_i + i) * A.n_j + j);
+    }
+}
+}  // namespace fwb
+
+extern "C" int fwb_tip_scan(const double *u_prev, const double *u, int dim, const int64_t *shape,
+                            double threshold, double *out, unsigned capacity, unsigned *count,
+                            fwb_stream_t stream)
+{
+    if (!u_prev || !u || (dim != 2 && dim != 3) || !shape || !out || !count) {
+        set_error("fwb_tip_scan: bad argument");
+        return FWB_E_ARG;
+    }
+    fwb::TipArgs A;
+    A.u_prev = u_prev; A.u = u; A.thr = threshold; A.out = out; A.count = count; A.capacity = capacity;
+    A.n_i = shape[0]; A.n_j = shape[1]; A.n_k = dim == 3 ? shape[2] : 1;
+    A.s_i = A.n_j * A.n_k; A.s_j = A.n_k;
+    const int64_t wi = A.n_i - 10, wj = A.n_j - 10;
+    if (wi <= 0 || wj <= 0 || A.n_k <= 0) return 0;
+    const int64_t total = wi * wj * A.n_k;
+    fwb::tip_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
+    FWB_KERNEL_CHECK("tip_scan_kernel");
+    return 0;
+}

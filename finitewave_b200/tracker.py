@@ -470,3 +470,102 @@ class Period2DTracker(LocalActivationTime2DTracker):
 
 class Period3DTracker(Period2DTracker):
     pass
+
+
+class SpiralWaveCore2DTracker(Tracker):
+    """Spiral-wave tips: cells in which the threshold isoline of the previous and of the
+    current sample cross, located by the bilinear interpolation of reference
+    cpuwave2D/tracker/spiral_wave_core_2d_tracker.py:9-248.  The scan runs on the device
+    (fwb_tip_scan); only the tips come back.  ``output`` is a DataFrame x, y, time, step."""
+    _device_hook = True
+    _COLS = ["x", "y", "time", "step"]
+
+    def __init__(self):
+        super().__init__()
+        self.threshold = 0.5
+        self.file_name = "spiral_wave_core"
+        self.sprial_wave_cores = []          # (sic) the reference's attribute name
+        self._dev = None
+
+    def initialize(self, model):
+        self.model = model
+        self.u_prev = self.model.u.copy()
+        self.sprial_wave_cores = []
+        self._dev = None
+
+    def _ensure_dev(self, engine):
+        if self._dev is None or self._dev["device"] != engine.device:
+            dev = engine.device
+            self._dev = dict(
+                device=dev, capacity=4096,
+                u_prev=torch.from_numpy(np.ascontiguousarray(self.u_prev, dtype=np.float64)).to(dev),
+                out=torch.zeros((4096, 3), dtype=torch.float64, device=dev),
+                count=torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._dev
+
+    def _scan(self, engine, u):
+        d = self._ensure_dev(engine)
+        L, st = engine.L, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        from ._lib import shape_arr
+        while True:
+            d["count"].zero_()
+            check(L.fwb_tip_scan(ctypes.c_void_p(d["u_prev"].data_ptr()),
+                                 ctypes.c_void_p(u.data_ptr()), len(engine.shape),
+                                 shape_arr(engine.shape), float(self.threshold),
+                                 ctypes.c_void_p(d["out"].data_ptr()), d["capacity"],
+                                 ctypes.c_void_p(d["count"].data_ptr()), st), "fwb_tip_scan")
+            n = int(d["count"].item())
+            if n <= d["capacity"]:
+                break
+            d["capacity"] = 2 * n
+            d["out"] = torch.zeros((d["capacity"], 3), dtype=torch.float64, device=engine.device)
+        rows = d["out"][:n].cpu().numpy()
+        rows = rows[np.argsort(rows[:, 2], kind="stable")]      # the reference's scan order
+        d["u_prev"].copy_(u)
+        return rows
+
+    def _frames(self, rows, t, step):
+        import pandas as pd
+        tips = pd.DataFrame(rows[:, :2], columns=["x", "y"])
+        tips["time"] = t
+        tips["step"] = step
+        return [tips]
+
+    def _track_device(self, engine, u, t):
+        rows = self._scan(engine, u)
+        self.sprial_wave_cores.extend(self._frames(rows, t, self.model.step))
+
+    def _track(self):
+        eng = self.model._engine
+        self._track_device(eng, eng.ubuf[eng.current()], self.model.t)
+
+    def write(self):
+        self.output.to_csv(Path(self.path, self.file_name).with_suffix(".csv"))
+
+    @property
+    def output(self):
+        import pandas as pd
+        valid = [df for df in self.sprial_wave_cores if not df.empty]
+        if not valid:
+            return pd.DataFrame(columns=self._COLS)
+        return pd.concat(valid, ignore_index=True)
+
+
+class SpiralWaveCore3DTracker(SpiralWaveCore2DTracker):
+    """The 2D scan on every slice of the last axis (reference
+    cpuwave3D/tracker/spiral_wave_core_3d_tracker.py:7-48); columns x, y, z, time, step."""
+    _COLS = ["x", "y", "z", "time", "step"]
+
+    def _frames(self, rows, t, step):
+        import pandas as pd
+        n_i, n_j, n_k = self.model.u.shape
+        z = (rows[:, 2] // (n_i * n_j)).astype(np.int64)
+        frames = []
+        for k in np.unique(z):                 # one frame per slice, like the reference
+            sel = rows[z == k]
+            tips = pd.DataFrame(sel[:, :2], columns=["x", "y"])
+            tips["z"] = int(k)
+            tips["time"] = t
+            tips["step"] = step
+            frames.append(tips)
+        return frames

@@ -188,6 +188,21 @@ FWB_API int fwb_compute_weights(int dim, int stencil, const int64_t *shape,
                         int64_t ld, double *weights, fwb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * SpiralWaveCore{2,3}DTracker on the device.  Replaces the serial njit
+ * _track_tip_line / _correct_tip_pos / _apply_threshold
+ * (finitewave/cpuwave2D/tracker/spiral_wave_core_2d_tracker.py:108-248; 3D: one scan per
+ * slice of the last axis, cpuwave3D/tracker/spiral_wave_core_3d_tracker.py:30-48).
+ *   u_prev, u   dense device potentials of the previous and the current sample
+ *   out         [capacity][3] rows {x = j + dy, y = i + dx, key = (k * n_i + i) * n_j + j};
+ *               rows come in no particular order: sort by key for the reference's order
+ *   count       device counter, incremented once per tip (may exceed capacity: rows beyond
+ *               it are dropped, the caller re-runs with a larger buffer); zero it first
+ * ---------------------------------------------------------------------- */
+FWB_API int fwb_tip_scan(const double *u_prev, const double *u, int dim, const int64_t *shape,
+                 double threshold, double *out, unsigned capacity, unsigned *count,
+                 fwb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Fibrosis patterns on the device.  Replaces the numpy generators
  * Diffuse{2,3}DPattern.generate / Structural{2,3}DPattern.generate
  * (finitewave/cpuwave2D/fibrosis/diffuse_2d_pattern.py:63-87, structural_2d_pattern.py:71-120,

@@ -303,6 +303,21 @@ def make_cases():
         trackers=[dict(kind="local_activation_time", threshold=0.5, step=5),
                   dict(kind="period", threshold=0.5, step=5, cell_ind=[[7, 6, 5], [12, 3, 8]])]))
 
+    # SpiralWaveCore trackers: Barkley spiral (the protocol of the
+    # reference's tests/test_trackers_2d.py:25-40, smaller), tips every 10 steps
+    cases.append(dict(
+        name="barkley2d_spiral_core", model="barkley", shape=[100, 100],
+        dt=0.01, dr=0.25, t_max=14,
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 100, 0, 3]),
+               dict(kind="voltage_coord", t=5, value=1, box=[0, 50, 0, 100])],
+        trackers=[dict(kind="spiral_core", threshold=0.5, step=10, start_time=6)]))
+    cases.append(dict(
+        name="barkley3d_spiral_core", model="barkley", shape=[48, 48, 5],
+        dt=0.01, dr=0.25, t_max=9,
+        stims=[dict(kind="voltage_coord", t=0, value=1, box=[0, 48, 0, 3, 0, 5]),
+               dict(kind="voltage_coord", t=2.4, value=1, box=[0, 24, 0, 48, 0, 5])],
+        trackers=[dict(kind="spiral_core", threshold=0.5, step=20, start_time=3)]))
+
     # SymmetricStencil2D: cell-centred 9-point weights, random fibres,
     # fibrosis and a conductivity map; the apply kernel is the asymmetric 9-point one
     rng = np.random.default_rng(21)
@@ -407,6 +422,10 @@ def build_model(fw, case):
             tr = getattr(fw, "LocalActivationTime" + sfx + "Tracker")()
             if "threshold" in t:
                 tr.threshold = t["threshold"]
+        elif kind == "spiral_core":
+            tr = getattr(fw, "SpiralWaveCore" + sfx + "Tracker")()
+            if "threshold" in t:
+                tr.threshold = t["threshold"]
         elif kind == "period":
             tr = getattr(fw, "Period" + sfx + "Tracker")()
             tr.cell_ind = t["cell_ind"]
@@ -431,6 +450,10 @@ def collect_outputs(case, model, trackers):
         if t["kind"] == "multi_variable":
             for v in t["vars"]:
                 out[f"tracker{i}_{v}"] = np.array(tr.output[v], dtype=np.float64)
+        elif t["kind"] == "spiral_core":
+            cols = ["x", "y", "time", "step"] if len(case["shape"]) == 2 else \
+                ["x", "y", "z", "time", "step"]
+            out[f"tracker{i}"] = np.array(tr.output[cols], dtype=np.float64).reshape(-1, len(cols))
         elif t["kind"] == "period":
             # the layers (n_layers, n_cells); `output` is a DataFrame of their differences
             tr.output

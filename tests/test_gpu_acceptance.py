@@ -386,3 +386,27 @@ def test_fibrosis_patterns_reference_assertions(fw):
     res = fw.Structural3DPattern(*box, 0.4, 5, 4, 3).generate(shape=shape3)
     sub = res[box[0]:box[1], box[2]:box[3], box[4]:box[5]]
     assert np.all(np.isin(res, [1, 2])) and abs(np.mean(sub == 2) - 0.4) < 0.05
+
+
+def test_spiral_wave_core_2d_tracker(fw):
+    """tests/test_trackers_2d.py:205-231: the tip of the Barkley spiral stays in a 6 x 6 box."""
+    ni = nj = 100
+    tissue = fw.CardiacTissue2D([ni, nj])
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, 1, 0, ni, 0, 3))
+    stims.add_stim(fw.StimVoltageCoord2D(5, 1, 0, ni // 2, 0, nj))
+    model = fw.Barkley2D()
+    model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 20, False
+    model.cardiac_tissue, model.stim_sequence = tissue, stims
+    tracker = fw.SpiralWaveCore2DTracker()
+    tracker.threshold, tracker.start_time, tracker.step = 0.5, 12, 10
+    seq = fw.TrackerSequence()
+    seq.add_tracker(tracker)
+    model.tracker_sequence = seq
+    model.run()
+    core = tracker.output
+    x, y = core["x"], core["y"]
+    assert len(x) > 0 and len(y) > 0
+    assert np.min(x) >= 32 and np.max(x) <= 38
+    assert np.min(y) >= 47 and np.max(y) <= 53
+    assert list(core.columns) == ["x", "y", "time", "step"]
