@@ -16,6 +16,9 @@ constexpr int MAX_STATE = 21;
 
 // thread-local last error (fwb_last_error)
 void set_error(const char *fmt, ...);
+// which step kernel the last launch used (fwb_last_step_variant): 0 = one block per tile,
+// plain loads; 1 = state rows by TMA; 2 = state + weight rows by TMA; 3 = persistent TMA ring
+void note_step_variant(int v);
 int cuda_fail(cudaError_t e, const char *what);
 
 #define FWB_CUDA(call)                                   \

@@ -424,6 +424,10 @@ extern "C" int64_t fwb_sim_tracker_samples(const FwbSim *s, int id)
 
 extern "C" int64_t fwb_sim_launch_count(const FwbSim *s) { return s ? s->launches : FWB_E_ARG; }
 
+static thread_local int g_step_variant = -1;
+namespace fwb { void note_step_variant(int v) { g_step_variant = v; } }
+extern "C" int fwb_last_step_variant(void) { return g_step_variant; }
+
 static inline bool gate(const Tracker &tr, double t, int64_t step)
 {
     // Tracker.track (core/tracker/tracker.py:70-84)

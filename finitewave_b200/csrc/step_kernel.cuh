@@ -646,7 +646,34 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
     const int64_t blocks = step_blocks(k.g);
     if (blocks <= 0) return 0;
+    if constexpr (stage_state<M>()) {
+        if (k.tile_base && k.records) {
+            // everything by TMA when three such blocks fit an SM and no ECG sample is due
+            // (its reduction buffer would cost the third block); else the state rows only
+            constexpr int K = Stencil<DIM, ST>::K;
+            constexpr bool FULL = !TRACK && stage_weights<M>() &&
+                                  3 * (StageCfg<M, K, 2>::SMEM + 1024 + 128) <= 228 * 1024;
+            if constexpr (FULL) {
+                auto kern = step_kernel<M, DIM, ST, TRACK, HALO, 2>;
+                static bool attr = false;
+                if (!attr) {
+                    FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)StageCfg<M, K, 2>::SMEM));
+                    attr = true;
+                }
+                kern<<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 2>::SMEM, s>>>(a);
+                note_step_variant(2);
+            } else {
+                step_kernel<M, DIM, ST, TRACK, HALO, 1>
+                    <<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 1>::SMEM, s>>>(a);
+                note_step_variant(1);
+            }
+            FWB_KERNEL_CHECK("step_kernel (staged)");
+            return 0;
+        }
+    }
     step_kernel<M, DIM, ST, TRACK, HALO><<<(unsigned)blocks, BLOCK_THREADS, 0, s>>>(a);
+    note_step_variant(0);
     FWB_KERNEL_CHECK("step_kernel");
     return 0;
 }
@@ -680,6 +707,7 @@ static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
         if (nb > blocks) { set_error("slab boundary does not fit the resident grid"); return FWB_E_UNSUPPORTED; }
     }
     kern<<<(unsigned)blocks, BLOCK_THREADS, C::SMEM, s>>>(a);
+    note_step_variant(3);
     FWB_KERNEL_CHECK("step_kernel_tma");
     return 0;
 }

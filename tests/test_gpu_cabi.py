@@ -165,3 +165,25 @@ def test_unknown_model_or_missing_fibers_raise(env):
     assert rc == -1
     with pytest.raises(lib.FwbError):
         lib.check(rc, "fwb_sim_create")
+
+
+def test_public_api_runs_the_tma_kernels():
+    """The host API lays the tissue out tile-ordered, so the step must take the TMA paths:
+    the persistent ring for the HBM-bound models (variant 3), staged state + weight rows for
+    the FP64-bound ones (2; state rows only, 1, on steps that sample the activation tracker).
+    Guards against silently falling back to the plain-load kernel (variant 0)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import finitewave_b200 as fw
+    from finitewave_b200 import _lib
+    from tests.cases import build_model, case_by_name
+    L = _lib.lib()
+    for name, want in (("c2_fk2d_aniso_fib", 3), ("c3_ms3d_iso_focal", 3),
+                       ("tp06_3d_iso_current", 2), ("lr91_2d_iso", 2),
+                       ("court2d_iso_current", 2), ("c5_tp06_3d_aniso_slab", 1)):
+        case = dict(case_by_name(name))
+        case["t_max"] = 0.2
+        model, _ = build_model(fw, case)
+        model.run()
+        assert L.fwb_last_step_variant() == want, (name, L.fwb_last_step_variant())
