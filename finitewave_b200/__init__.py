@@ -26,7 +26,8 @@ from .stimulation import (Stim, StimCurrent, StimCurrentArea2D, StimCurrentArea3
                           StimVoltageCoord3D, StimVoltageListMatrix3D, StimVoltageMatrix2D,
                           StimVoltageMatrix3D)
 from .tissue import CardiacTissue, CardiacTissue2D, CardiacTissue3D
-from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker,
+from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker, Animation2DTracker,
+                      Animation3DTracker, AnimationSlice3DTracker,
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,
                       ECG3DTracker, LocalActivationTime2DTracker, LocalActivationTime3DTracker,
                       MultiVariable2DTracker, MultiVariable3DTracker, Period2DTracker,

@@ -17,6 +17,7 @@ stores the ``.npy`` files (``AsyncCheckpointWriter``); the files are complete wh
 returns.  The final checkpoint (``time = -1``) is written from the arrays ``run()`` downloads
 anyway.
 """
+import queue
 import threading
 from pathlib import Path
 
@@ -123,6 +124,70 @@ class AsyncCheckpointWriter:
         if self.errors:
             e, self.errors = self.errors[0], []
             raise e
+
+
+class FrameStreamer:
+    """Streams device arrays to ``.npy`` files while the simulation keeps running (frame
+    dumps of the animation trackers).  Per frame: a device snapshot on
+    the compute stream (taken by the caller), a device-to-host copy on a copy stream into
+    one of ``depth`` pinned buffers, and the file write on a writer thread.  ``submit``
+    only blocks when all pinned buffers are still being written (back-pressure)."""
+
+    def __init__(self, shape, depth=3):
+        import torch
+        self.torch = torch
+        self.shape = tuple(shape)
+        self.copy_stream = torch.cuda.Stream()
+        self.free = queue.Queue()
+        for _ in range(depth):
+            self.free.put(torch.empty(self.shape, dtype=torch.float64, pin_memory=True))
+        self.jobs = queue.Queue()
+        self.errors = []
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            host, done, path, dtype, select = job
+            try:
+                done.synchronize()
+                a = host.numpy()
+                if select is not None:
+                    a = a[select]
+                np.save(path, a.astype(dtype))
+            except Exception as e:
+                self.errors.append(e)
+            finally:
+                self.free.put(host)
+                self.jobs.task_done()
+
+    def submit(self, snapshot, path, dtype, select=None):
+        """snapshot: a device tensor nobody will overwrite (its producer ran on the current
+        stream); select: optional index applied on the host (a slice of a 3D frame)."""
+        torch = self.torch
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        host = self.free.get()                       # back-pressure
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            host.copy_(snapshot, non_blocking=True)
+            snapshot.record_stream(self.copy_stream)
+            done.record(self.copy_stream)
+        self.jobs.put((host, done, path, dtype, select))
+
+    def wait(self):
+        self.jobs.join()
+        if self.errors:
+            e, self.errors = self.errors[0], []
+            raise e
+
+    def close(self):
+        self.wait()
+        self.jobs.put(None)
 
 
 class StateSaverCollection(StateSaver):

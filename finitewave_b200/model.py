@@ -381,6 +381,9 @@ class CardiacModel:
         self._collect_native()
         if getattr(self, "_ckpt_writer", None) is not None:
             self._ckpt_writer.wait()          # checkpoint files are complete on return
+        for tr in dev_tr:
+            if hasattr(tr, "_finish"):
+                tr._finish()                  # streamed frames are complete on return
         self.gpu_launches = eng.launch_count() - launches0
         self._live = None
 

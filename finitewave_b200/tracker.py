@@ -569,3 +569,105 @@ class SpiralWaveCore3DTracker(SpiralWaveCore2DTracker):
             tips["step"] = step
             frames.append(tips)
         return frames
+
+
+# ---- frame dumps ----------------------------------------------------
+class Animation2DTracker(Tracker):
+    """Saves ``model.<variable_name>`` as ``<path>/<dir_name>/<n>.npy`` at every sample
+    (reference cpuwave2D/tracker/animation_2d_tracker.py:8-77).  The frame is snapshotted
+    on the device and streamed out by hooks.FrameStreamer -- a copy stream and a writer
+    thread -- so the step loop does not wait for the disk; all frames are on disk when
+    ``run()`` returns.  ``write()`` (the mp4 builder of finitewave.tools) is not part of
+    this backend."""
+    _device_hook = True
+
+    def __init__(self):
+        super().__init__()
+        self.dir_name = "animation"
+        self.variable_name = "u"
+        self.frame_type = "float64"
+        self._frame_counter = 0
+        self.overwrite = True
+        self.file_name = "animation"
+        self._streamer = None
+
+    def initialize(self, model):
+        self.model = model
+        self._frame_counter = 0
+        out = Path(self.path, self.dir_name)
+        if not out.is_dir():
+            out.mkdir(parents=True)
+        if self.overwrite:
+            for f in out.glob("*.npy"):
+                f.unlink()
+        self._streamer = None
+
+    def _select(self):
+        return None
+
+    def _snapshot(self, engine, u):
+        name = self.variable_name
+        if name == "u":
+            return u.clone()
+        names = [v for v in self.model.state_vars if v != "u"]
+        if name not in names:
+            raise ValueError(f"Variable '{name}' not found in model.")
+        slot = names.index(name)
+        d = torch.empty(engine.shape, dtype=torch.float64, device=engine.device)
+        from .engine import _ptr, _stream
+        check(engine.L.fwb_scatter_compact(_ptr(engine.state[slot]), _ptr(d),
+                                           float(self.model._init_value(name)), engine.n_nodes,
+                                           _ptr(engine.chunk_bits), _ptr(engine.chunk_base),
+                                           _stream()), "fwb_scatter_compact")
+        return d
+
+    def _track_device(self, engine, u, t):
+        if self._streamer is None:
+            from .hooks import FrameStreamer
+            self._streamer = FrameStreamer(engine.shape)
+        path = Path(self.path, self.dir_name, str(self._frame_counter)).with_suffix(".npy")
+        self._streamer.submit(self._snapshot(engine, u), path, self.frame_type, self._select())
+        self._frame_counter += 1
+
+    def _track(self):
+        eng = self.model._engine
+        self._track_device(eng, eng.ubuf[eng.current()], self.model.t)
+        self._finish()
+
+    def _finish(self):
+        """Called by run() before it returns: every submitted frame is on disk."""
+        if self._streamer is not None:
+            self._streamer.wait()
+
+    def write(self, *args, **kwargs):
+        raise NotImplementedError(
+            "building the animation file is finitewave.tools' job (matplotlib / ffmpeg); the "
+            f"frames are in {Path(self.path, self.dir_name)}")
+
+
+class Animation3DTracker(Animation2DTracker):
+    pass
+
+
+class AnimationSlice3DTracker(Animation2DTracker):
+    """One plane of a 3D variable per frame (reference
+    cpuwave3D/tracker/animation_slice_3d_tracker.py:7-64): exactly one of ``slice_x``,
+    ``slice_y``, ``slice_z`` must be set."""
+
+    def __init__(self):
+        super().__init__()
+        self.slice_x = None
+        self.slice_y = None
+        self.slice_z = None
+
+    def initialize(self, model):
+        if np.count_nonzero([self.slice_x, self.slice_y, self.slice_z]) != 1:
+            raise ValueError("Exactly one slice must be specified.")
+        super().initialize(model)
+
+    def _select(self):
+        if self.slice_x is not None:
+            return (self.slice_x, slice(None), slice(None))
+        if self.slice_y is not None:
+            return (slice(None), self.slice_y, slice(None))
+        return (slice(None), slice(None), self.slice_z)

@@ -78,3 +78,57 @@ def test_checkpoint_restart_reproduces_the_run(fw, tmp_path):
     assert m2.step == remaining
     assert np.array_equal(m2.u, u_full)
     assert np.array_equal(m2.h, model.h)
+
+
+def test_animation_trackers_stream_frames(fw, tmp_path):
+    """Animation2D / AnimationSlice3D trackers (reference tests/test_trackers_2d.py:96-120,
+    test_trackers_3d.py): one .npy per sample, streamed while the run continues; the frames
+    equal what a host-hook tracker sees at the same steps."""
+    case = dict(case_by_name("c2_fk2d_aniso_fib"), t_max=4.0, trackers=[])
+    model, _ = build_model(fw, case)
+    anim = fw.Animation2DTracker()
+    anim.path, anim.dir_name, anim.step, anim.variable_name = str(tmp_path), "frames_u", 50, "u"
+    anim_v = fw.Animation2DTracker()
+    anim_v.path, anim_v.dir_name, anim_v.step, anim_v.variable_name = str(tmp_path), "frames_v", 100, "v"
+    anim_v.frame_type = "float32"
+
+    class Probe(fw.Tracker):                       # host hook: downloads the arrays
+        def initialize(self, model):
+            self.model, self.seen = model, []
+
+        def _track(self):
+            self.seen.append((self.model.u.copy(), self.model.v.copy()))
+    probe = Probe()
+    probe.step = 100
+    seq = fw.TrackerSequence()
+    for tr in (anim, anim_v, probe):
+        seq.add_tracker(tr)
+    model.tracker_sequence = seq
+    model.run()
+    n_u = len(list((tmp_path / "frames_u").glob("*.npy")))
+    n_v = len(list((tmp_path / "frames_v").glob("*.npy")))
+    assert n_u == model.step // 50 and n_v == model.step // 100 == len(probe.seen)
+    for i, (u, v) in enumerate(probe.seen):
+        assert np.array_equal(np.load(tmp_path / "frames_u" / f"{2 * i}.npy"), u)
+        fv = np.load(tmp_path / "frames_v" / f"{i}.npy")
+        assert fv.dtype == np.float32 and np.array_equal(fv, v.astype(np.float32))
+    assert any(np.any(np.load(tmp_path / "frames_u" / f"{i}.npy") > 0) for i in range(n_u))
+
+    case3 = dict(case_by_name("c3_ms3d_iso_focal"), t_max=2.0, trackers=[])
+    m3, _ = build_model(fw, case3)
+    sl = fw.AnimationSlice3DTracker()
+    sl.path, sl.dir_name, sl.step, sl.slice_z = str(tmp_path), "slices", 40, 12
+    full = fw.Animation3DTracker()
+    full.path, full.dir_name, full.step = str(tmp_path), "vol", 40
+    seq3 = fw.TrackerSequence()
+    seq3.add_tracker(sl)
+    seq3.add_tracker(full)
+    m3.tracker_sequence = seq3
+    m3.run()
+    for i in range(m3.step // 40):
+        vol = np.load(tmp_path / "vol" / f"{i}.npy")
+        assert vol.shape == (24, 24, 24)
+        assert np.array_equal(np.load(tmp_path / "slices" / f"{i}.npy"), vol[:, :, 12])
+    with pytest.raises(ValueError):
+        bad = fw.AnimationSlice3DTracker()
+        bad.initialize(m3)
