@@ -433,6 +433,7 @@ template <> struct Model<FWB_MODEL_TP06> {
         // fast path only (ionic_fast): logs of the numerators of the reversal potentials,
         // EC^2, F / (R T), and exp(offset / slope) of every shared-slope exponential
         double l_ko, l_nao, l_kpn, l_cao, EC2, F_RT;
+        int fast_ok;       // parameters allow the rearranged path (positive concentrations)
         double km1, km2, kj1, kd1, kd2, kd3, kf1, kf2, kf3, kf4, kf5, kr1, ks1, ks2;
         double kx1, kx2, kx3, kx4, kx5, kxs1, kxs2, kxs3;
     };
@@ -468,6 +469,8 @@ template <> struct Model<FWB_MODEL_TP06> {
                      pKNa = p[30];
         c.l_ko = log(ko); c.l_nao = log(nao); c.l_kpn = log(ko + pKNa * nao); c.l_cao = log(cao);
         c.EC2 = p[19] * p[19]; c.F_RT = F / (R * T);
+        c.fast_ok = ko > 0 && nao > 0 && cao > 0 && pKNa >= 0 && ko < 1e300 && nao < 1e300 &&
+                    cao < 1e300 && pKNa < 1e300;
         c.km1 = exp(-60. / 5.); c.km2 = exp(35. / 5.); c.kj1 = exp(-0.1 * 32.);
         c.kd1 = exp(-8. / 7.5); c.kd2 = exp(5. / 5.); c.kd3 = exp(50. / 20.);
         c.kf1 = exp(20. / 7.); c.kf2 = exp(13. / 10.); c.kf3 = exp(30. / 10.);
@@ -492,12 +495,18 @@ template <> struct Model<FWB_MODEL_TP06> {
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
+        const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
 #ifdef __CUDA_ARCH__
-        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_fast(u, un, io, c);
+        // the rearranged path needs |u| < 300 mV (fexp) and positive, normal concentrations
+        // (flog, branch-free reciprocals); anything else -- NaNs included, they fail every
+        // comparison -- takes the reference statement
+        if (c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(cai) && conc_ok(nai) && conc_ok(Ki))
+            ionic_fast(u, un, io, c, cai, nai, Ki);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c);
+            ionic_impl<IO, LibMath>(u, un, io, c, cai, nai, Ki);
     }
+    FWB_HD static bool conc_ok(double x) { return x > 1e-300 && x < 1e300; }
 
     // ------------------------------------------------------------------------------------
     // The device's normal path for |u| < 300 mV: the same equations as ionic_impl (which is
@@ -512,21 +521,22 @@ template <> struct Model<FWB_MODEL_TP06> {
     //    costs one reciprocal instead of one per term plus a division
     //  * every remaining division has a denominator that is positive and normal for any
     //    physical state: reciprocal seed + Newton steps without the special-operand branch
-    //  * log(a / x) = log(a) - log(x) with log(a) from the host
+    //  * log(a / x) = log(a) - log(x) with log(a) from the host and a table-driven flog(x)
+    //    (fexp.cuh: 10 FP64-pipe instructions instead of ~30 + 60 others)
     // ------------------------------------------------------------------------------------
     FWB_HD static double rlf(double inf, double x, double dt, double rtau)
     {
         return fma(x - inf, fexp_fast_neg(-dt * rtau), inf);
     }
     template <class IO>
-    FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c)
+    FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double cai,
+                                  double nai, double Ki)
     {
         const double dt = c.dt;
-        const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
-        const double Ek = c.RTONF * (c.l_ko - log(Ki));
-        const double Ena = c.RTONF * (c.l_nao - log(nai));
-        const double Eks = c.RTONF * (c.l_kpn - log(fma(c.pKNa, nai, Ki)));
-        const double Eca = c.half_RTONF * (c.l_cao - log(cai));
+        const double Ek = c.RTONF * (c.l_ko - flog(Ki));
+        const double Ena = c.RTONF * (c.l_nao - flog(nai));
+        const double Eks = c.RTONF * (c.l_kpn - flog(fma(c.pKNa, nai, Ki)));
+        const double Eca = c.half_RTONF * (c.l_cao - flog(cai));
 
         // shared exponentials of u
         const double g20 = fexp_fast(u * 0.05), g10 = g20 * g20, g5 = g10 * g10;
@@ -730,10 +740,10 @@ template <> struct Model<FWB_MODEL_TP06> {
     }
 
     template <class IO, class E>
-    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c, double cai,
+                                  double nai, double Ki)
     {
         const double dt = c.dt;
-        const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
         // reversal potentials :1072-1075
         const double Ek = c.RTONF * log(c.ko / Ki);
         const double Ena = c.RTONF * log(c.nao / nai);

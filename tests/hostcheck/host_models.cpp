@@ -77,8 +77,15 @@ int fwb_host_tp06_fast(double *u_new, const double *u, double *const *st, int64_
     for (int64_t i = 0; i < n; ++i) {
         IO io{st, i};
         double un = u_new[i];
-        M::ionic_fast(u[i], un, io, c);
+        M::ionic_fast(u[i], un, io, c, io.ld(0), io.ld(3), io.ld(4));
         u_new[i] = un;
     }
     return 0;
+}
+
+// host build of the device's table-driven log (finitewave_b200/csrc/fexp.cuh)
+extern "C" __attribute__((visibility("default")))
+void fwb_host_flog(const double *x, double *out, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = fwb::flog(x[i]);
 }

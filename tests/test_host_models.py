@@ -182,3 +182,23 @@ def test_fexp_within_two_ulp_of_libm(hostlib):
     assert both[0] == np.exp(-700.0) and both[1] == both[2] == _fexp(hostlib, [700.0], 0)[0]
     assert abs(both[3] / np.exp(12.0) - 1) < 1e-15
     print(f"fexp max error {ulp.max():.3f} ulp, mean {ulp.mean():.3f}")
+
+
+def test_flog_accuracy(hostlib):
+    """The device's table-driven log (same source, host build) on positive normal arguments:
+    <= 2 ulp of the result where |log x| >= 1/2, <= 3e-16 absolute near x = 1."""
+    rng = np.random.default_rng(9)
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 1_000_000)), rng.uniform(1e-5, 1e-2, 500_000),
+                        rng.uniform(1, 200, 500_000), rng.uniform(0.5, 2.0, 500_000),
+                        np.array([1.0, 2.0, 0.5, 7e-5, 138.3, 5.4, 1 + 2 ** -52, 2 - 2 ** -52])])
+    x = np.ascontiguousarray(x)
+    out = np.empty_like(x)
+    hostlib.fwb_host_flog(x.ctypes.data_as(c_double_p), out.ctypes.data_as(c_double_p),
+                          ctypes.c_int64(len(x)))
+    ref = np.log(x)
+    big = np.abs(ref) >= 0.5
+    ulp = np.abs(out - ref)[big] / np.spacing(np.abs(ref[big]))
+    assert ulp.max() <= 2.0, ulp.max()
+    assert np.abs(out - ref)[~big].max() <= 3e-16
+    print(f"flog max error {ulp.max():.3f} ulp (|log| >= 0.5), "
+          f"{np.abs(out - ref)[~big].max():.2e} absolute near 1")
