@@ -79,6 +79,7 @@ def _sig(L):
     L.fwb_sim_launch_count.argtypes = [p]
     L.fwb_sim_launch_count.restype = c_int64
     L.fwb_last_step_variant.restype = c_int
+    L.fwb_devmath.argtypes = [c_int, p, p, c_int64, p]
     L.fwb_diffuse.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_int64, p, c_int64,
                               p, p, p, p]
     L.fwb_dev_alloc.argtypes = [POINTER(c_void_p), c_int64]

@@ -1,5 +1,6 @@
 // aux_kernels.cu -- index structures, layout conversions, stimuli, tracker helpers.
 #include "aux_kernels.cuh"
+#include "fexp.cuh"
 
 namespace fwb {
 
@@ -924,5 +925,38 @@ extern "C" int fwb_tip_scan(const double *u_prev, const double *u, int dim, cons
     const int64_t total = wi * wj * A.n_k;
     fwb::tip_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
     FWB_KERNEL_CHECK("tip_scan_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Device evaluation of the fast-path math helpers (fexp.cuh) for the accuracy tests: the
+// host builds of the same sources are checked against libm on the CPU; this is the check of
+// what the GPU actually computes (MUFU seeds, FMA contraction).
+// ---------------------------------------------------------------------------
+namespace fwb {
+__global__ void devmath_kernel(int op, const double *x, double *y, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r;
+    switch (op) {
+    case 0: r = fexp(v); break;
+    case 1: r = fexp_fast(v); break;
+    case 2: r = flog(v); break;
+    case 3: r = frcp(v); break;
+    case 4: r = frcp3(v); break;
+    default: r = v;
+    }
+    y[i] = r;
+}
+}  // namespace fwb
+
+extern "C" int fwb_devmath(int op, const double *x, double *y, int64_t n, fwb_stream_t stream)
+{
+    if (!x || !y || n < 0 || op < 0 || op > 4) { set_error("fwb_devmath: bad argument"); return FWB_E_ARG; }
+    if (n == 0) return 0;
+    fwb::devmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, n);
+    FWB_KERNEL_CHECK("devmath_kernel");
     return 0;
 }

@@ -187,3 +187,41 @@ def test_public_api_runs_the_tma_kernels():
         model, _ = build_model(fw, case)
         model.run()
         assert L.fwb_last_step_variant() == want, (name, L.fwb_last_step_variant())
+
+
+def test_device_math_helpers_accuracy():
+    """What the GPU computes for the fast-path helpers of csrc/fexp.cuh (through fwb_devmath):
+    fexp / fexp_fast <= 2 ulp, flog <= 2 ulp (|log| >= 1/2), frcp <= 1 ulp, frcp3 <= 1.5 ulp."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from finitewave_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(17)
+
+    def run(op, x):
+        xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        yd = torch.empty_like(xd)
+        rc = L.fwb_devmath(op, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(yd.data_ptr()),
+                           xd.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        return yd.cpu().numpy()
+
+    x = np.concatenate([rng.uniform(-690, 690, 2_000_000), rng.uniform(-40, 40, 2_000_000),
+                        rng.uniform(-1e-3, 1e-3, 100_000)])
+    ref = np.exp(x)
+    for op in (0, 1):
+        ulp = np.abs(run(op, x) - ref) / np.spacing(ref)
+        assert ulp.max() <= 2.0, (op, ulp.max())
+    xl = np.concatenate([np.exp(rng.uniform(-690, 690, 2_000_000)), rng.uniform(1e-5, 200, 2_000_000)])
+    out, ref = run(2, xl), np.log(xl)
+    big = np.abs(ref) >= 0.5
+    assert (np.abs(out - ref)[big] / np.spacing(np.abs(ref[big]))).max() <= 2.0
+    assert np.abs(out - ref)[~big].max() <= 3e-16
+    xr = np.concatenate([np.exp(rng.uniform(-600, 600, 4_000_000)), rng.uniform(1, 2, 4_000_000),
+                         -np.exp(rng.uniform(-50, 50, 1_000_000))])
+    ref = 1.0 / xr
+    for op, bound in ((3, 1.0), (4, 1.5)):
+        ulp = np.abs(run(op, xr) - ref) / np.spacing(np.abs(ref))
+        print("frcp op", op, "max ulp", ulp.max())
+        assert ulp.max() <= bound, (op, ulp.max())
