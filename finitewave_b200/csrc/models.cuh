@@ -304,12 +304,17 @@ template <> struct Model<FWB_MODEL_BUENO_OROVIO> {
 // state: m,h,j,d,f,x,cai
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_LUO_RUDY91> {
-    static constexpr int NS = 7, NP = 15, MIN_BLOCKS = 3;
+#ifndef FWB_LR91_MIN_BLOCKS
+#define FWB_LR91_MIN_BLOCKS 4
+#endif
+    static constexpr int NS = 7, NP = 15, MIN_BLOCKS = FWB_LR91_MIN_BLOCKS;
     static constexpr bool USE_TMA = false;   // step_kernel_tma for HBM-bound models
     static constexpr uint32_t READ_MASK = 0x7f, WRITE_MASK = 0x7f;
     struct Consts {
         double dt, gna, gsi, gkp, gb;
         double E_Na, E_K, G_K, E_K1, G_K1;   // parameter-only (:478, :337-338, :496, :404)
+        // fast path only (ionic_fast): exp(offset * slope) of the shared-slope exponentials
+        double k47, k32, kd, kf1, kf2, kf3, kx1, kx2, kxa, kxb;
     };
     static bool derive(const double *p, double dt, Consts &c)
     {
@@ -321,6 +326,10 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         c.G_K = gk * sqrt(ko / 5.4);
         c.E_K1 = (R * T / F) * log(ko / ki);
         c.G_K1 = gk1 * sqrt(ko / 5.4);
+        c.k47 = exp(-0.1 * 47.13); c.k32 = exp(-0.1 * 32.); c.kd = exp(0.05 * 44.);
+        c.kf1 = exp(-0.02 * 30.); c.kf2 = exp(-0.2 * 30.); c.kf3 = exp(0.15 * 28.);
+        c.kx1 = exp(-0.06 * 20.); c.kx2 = exp(-0.04 * 20.);
+        c.kxa = exp(0.04 * (77. - 35.)); c.kxb = exp(-0.04 * 35.);
         return true;
     }
     FWB_HD static double gate(double var, double dt, double alpha, double beta)
@@ -333,14 +342,112 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
+        const double cai = io.ld(6);
 #ifdef __CUDA_ARCH__
-        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
+        // the rearranged path needs |u| < 300 mV and a positive, normal cai (flog); NaNs fail
+        // the comparisons and take the reference statement
+        if (fabs(u) < FAST_MATH_U_LIMIT && cai > 1e-300 && cai < 1e300) ionic_fast(u, un, io, c, cai);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c);
+            ionic_impl<IO, LibMath>(u, un, io, c, cai);
     }
+
+    // ------------------------------------------------------------------------------------
+    // The device's normal path: the equations of ionic_impl rearranged for the FP64 pipe
+    // (identities only; tests/test_host_models.py compares the two on random node states):
+    //  * forward-Euler gate: with tau = 1 / (a + b), inf = a / (a + b) the reference's
+    //    dt (inf - x) / tau is dt (a - x (a + b)): no division at all
+    //  * a = n1 / A, b = n2 / B are put over the common denominator A B: one reciprocal
+    //    (frcp3) per gate; K_1x = a / (a + b) likewise
+    //  * exponentials with commensurable slopes share one evaluation (-0.1, -0.02 / -0.04 /
+    //    -0.06 / -0.2, 0.05 / 0.15); Xi needs none: (exp(.04 (u + 77)) - 1) / exp(.04 (u + 35))
+    //    = exp(1.68) - exp(-1.4) exp(-.04 u)
+    //  * log(cai) by flog
+    // ------------------------------------------------------------------------------------
+    FWB_HD static double gatef(double x, double dt, double a, double ab) { return fma(dt, fma(-x, ab, a), x); }
+    template <class IO>
+    FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double cai)
+    {
+        const double dt = c.dt;
+        const double g01 = fexp_fast(-0.1 * u);
+        const double g02 = fexp_fast(-0.02 * u), g04 = g02 * g02, g06 = g04 * g02;
+        const double g08 = g04 * g04, g20 = g08 * g08 * g04;          // exp(-0.2 u)
+        const double g05 = fexp_fast(0.05 * u), g15 = g05 * g05 * g05;
+        // ---- I_Na (calc_ina :185-241)
+        double ah, sh, aj, sj;                                          // alpha, alpha + beta
+        if (u >= -40.) {
+            ah = 0.;
+            sh = frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
+            aj = 0.;
+            sj = 0.3 * fexp_fast(-2.535e-07 * u) * frcp3(fma(c.k32, g01, 1.));
+        } else {
+            ah = 0.135 * fexp_fast((80. + u) * (-1. / 6.8));
+            sh = ah + (3.56 * fexp_fast(0.079 * u) + 3.1e5 * fexp_fast(0.35 * u));
+            const double a = 1. + fexp_fast(0.311 * (u + 79.23));
+            const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
+            const double na = (-1.2714e5 * fexp_fast(0.2444 * u) -
+                               3.474e-5 * fexp_fast(-0.04391 * u)) * (u + 37.78);
+            const double nb = 0.1212 * fexp_fast(-0.01052 * u);
+            const double r = frcp3(a * b);
+            aj = na * b * r;
+            sj = fma(na, b, nb * a) * r;
+        }
+        const double am = 0.32 * (u + 47.13) * frcp3(fma(-c.k47, g01, 1.));
+        const double sm = am + 0.08 * fexp_fast(u * (-1. / 11.));
+        const double m = gatef(io.ld(0), dt, am, sm);
+        const double h = gatef(io.ld(1), dt, ah, sh);
+        const double j = gatef(io.ld(2), dt, aj, sj);
+        io.st(0, m); io.st(1, h); io.st(2, j);
+        const double ina = c.gna * m * m * m * h * j * (u - c.E_Na);
+        // ---- I_si (calc_isk :244-294): old d, f
+        double d = io.ld(3), f = io.ld(4);
+        const double E_Si = fma(-13.0287, flog(cai), 7.7);
+        const double I_Si = c.gsi * d * f * (u - E_Si);
+        {
+            const double n1 = 0.095 * fexp_fast(-0.01 * (u - 5.));
+            const double a = 1. + fexp_fast(-0.072 * (u - 5.));
+            const double n2 = 0.07 * fexp_fast(-0.017 * (u + 44.));
+            const double b = fma(c.kd, g05, 1.);
+            const double r = frcp3(a * b);
+            d = gatef(d, dt, n1 * b * r, fma(n1, b, n2 * a) * r);
+        }
+        {
+            const double n1 = 0.012 * fexp_fast(-0.008 * (u + 28.));
+            const double a = fma(c.kf3, g15, 1.);
+            const double n2 = 0.0065 * c.kf1 * g02;
+            const double b = fma(c.kf2, g20, 1.);
+            const double r = frcp3(a * b);
+            f = gatef(f, dt, n1 * b * r, fma(n1, b, n2 * a) * r);
+        }
+        io.st(3, d); io.st(4, f);
+        io.st(6, fma(dt, fma(-0.0001, I_Si, 0.07 * (0.0001 - cai)), cai));
+        // ---- I_K (calc_ik :297-356): old x
+        const double Xi = u > -100. ? 2.837 * fma(-c.kxb, g04, c.kxa) * frcp3(u + 77.) : 1.;
+        double x = io.ld(5);
+        const double I_K = c.G_K * x * Xi * (u - c.E_K);
+        {
+            const double n1 = 0.0005 * fexp_fast(0.083 * (u + 50.));
+            const double a = 1. + fexp_fast(0.057 * (u + 50.));
+            const double n2 = 0.0013 * c.kx1 * g06;
+            const double b = fma(c.kx2, g04, 1.);
+            const double r = frcp3(a * b);
+            x = gatef(x, dt, n1 * b * r, fma(n1, b, n2 * a) * r);
+        }
+        io.st(5, x);
+        // ---- I_K1, I_Kp, I_b (calc_ik1 :359-408, calc_ikp :411-427, calc_ib :430-443)
+        const double y = u - c.E_K1;
+        const double a1 = 1. + fexp_fast_clamped(0.2385 * (y - 59.215));
+        const double n1 = fma(0.49124, fexp_fast_clamped(0.08032 * (y + 5.476)),
+                              fexp_fast_clamped(0.06175 * (y - 594.31)));
+        const double b1 = 1.02 * (1. + fexp_fast_clamped(-0.5143 * (y + 4.753)));
+        const double ik1 = c.G_K1 * (b1 * frcp3(fma(n1, a1, b1))) * y;
+        const double ikp = c.gkp * frcp3(1. + fexp_fast((7.488 - u) * (1. / 5.98))) * y;
+        const double ib = c.gb * (u + 59.87);
+        un -= dt * (ina + I_Si + (ik1 + ikp + ib) + I_K);
+    }
+
     template <class IO, class E>
-    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c, double cai)
     {
         const double dt = c.dt;
         // calc_ina :185-241
@@ -364,7 +471,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         io.st(0, m); io.st(1, h); io.st(2, j);
         const double ina = c.gna * m * m * m * h * j * (u - c.E_Na);
         // calc_isk :244-294
-        double d = io.ld(3), f = io.ld(4), cai = io.ld(6);
+        double d = io.ld(3), f = io.ld(4);
         const double E_Si = 7.7 - 13.0287 * log(cai);
         const double I_Si = c.gsi * d * f * (u - E_Si);
         const double alpha_d = E::dv(0.095 * E::eu(-0.01 * (u - 5)), 1 + E::eu(-0.072 * (u - 5)));

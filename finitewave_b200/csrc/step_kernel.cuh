@@ -267,7 +267,10 @@ template <class M, int K, int STAGED> struct StageCfg {
     static constexpr int NSR = tma_popc(M::READ_MASK);
     static constexpr int ROWS = STAGED == 2 ? K + NSR : (STAGED == 1 ? NSR : 0);
     static constexpr size_t SMEM = (size_t)ROWS * TMA_SEG * sizeof(double);
-    static constexpr int BLOCKS = STAGED == 2 ? (M::MIN_BLOCKS < 3 ? M::MIN_BLOCKS : 3) : M::MIN_BLOCKS;
+    // blocks per SM the launch bounds ask for: the model's target, capped by what the staged
+    // rows leave of the 228 KB of shared memory per SM (1 KB per block is reserved)
+    static constexpr int FIT = SMEM ? (int)((228 * 1024) / (SMEM + 1024 + 128)) : 32;
+    static constexpr int BLOCKS = M::MIN_BLOCKS < FIT ? M::MIN_BLOCKS : (FIT < 1 ? 1 : FIT);
 };
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO, int STAGED = 0>
@@ -651,8 +654,7 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
             // everything by TMA when three such blocks fit an SM and no ECG sample is due
             // (its reduction buffer would cost the third block); else the state rows only
             constexpr int K = Stencil<DIM, ST>::K;
-            constexpr bool FULL = !TRACK && stage_weights<M>() &&
-                                  3 * (StageCfg<M, K, 2>::SMEM + 1024 + 128) <= 228 * 1024;
+            constexpr bool FULL = !TRACK && stage_weights<M>() && StageCfg<M, K, 2>::FIT >= 3;
             if constexpr (FULL) {
                 auto kern = step_kernel<M, DIM, ST, TRACK, HALO, 2>;
                 static bool attr = false;

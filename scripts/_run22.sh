@@ -1,0 +1,26 @@
+python -m pytest tests -m gpu -q -x -k "runs_the_tma or lr91 or luo" 2>&1 | tail -3
+for mb in 3 4; do
+rm -f finitewave_b200/_build/step_lr91.o; FWB_EXTRA_FLAGS="-DFWB_LR91_MIN_BLOCKS=$mb" python -m finitewave_b200.build > /dev/null 2>&1
+echo "LR91 MIN_BLOCKS=$mb"
+python - <<'PY'
+import sys; sys.path.insert(0, ".")
+import torch, finitewave_b200 as fw
+from finitewave_b200.devrun import DeviceSimulation
+from finitewave_b200 import workloads
+dev = torch.device("cuda")
+for n, dim in ((4096, 2), (256, 3)):
+    m = (fw.LuoRudy912D if dim == 2 else fw.LuoRudy913D)(); m.dt, m.dr, m.prog_bar = 0.01, 0.25, False
+    shape = (n,) * dim
+    sim = DeviceSimulation(m, workloads.fibrosis_mesh(shape, 0.0, 0, dev))
+    st = fw.StimVoltageCoord2D(0, -20, 0, n, 0, 5) if dim == 2 else fw.StimVoltageCoord3D(0, -20, 0, n, 0, n, 0, 5)
+    sim.add_stim(st)
+    sim.run(300); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); sim.run(50); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    B = 129 + 8 * (5 if dim == 2 else 7)
+    print(f"LR91 {dim}D {n}^{dim} iso: {ms:.3f} ms/step -> {sim.n_myo/ms/1e6:.2f} G/s ({B*sim.n_myo/ms/1e6/6532.9:.3f} of HBM)")
+PY
+done
+rm -f finitewave_b200/_build/step_lr91.o; python -m finitewave_b200.build > /dev/null 2>&1
+python bench.py --workload c5 --steps 20 --warmup 5 --no-e2e --no-cpu --no-extras | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c5', round(d['value']/1e9,3), 'G/s')"

@@ -89,3 +89,26 @@ void fwb_host_flog(const double *x, double *out, int64_t n)
 {
     for (int64_t i = 0; i < n; ++i) out[i] = fwb::flog(x[i]);
 }
+
+// host build of LR91's rearranged device path (Model<LR91>::ionic_fast)
+extern "C" __attribute__((visibility("default")))
+int fwb_host_lr91_fast(double *u_new, const double *u, double *const *st, int64_t n, double dt,
+                       const double *p)
+{
+    using M = Model<FWB_MODEL_LUO_RUDY91>;
+    M::Consts c;
+    if (!M::derive(p, dt, c)) return -1;
+    struct IO {
+        double *const *arr;
+        int64_t i;
+        double ld(int q) const { return arr[q][i]; }
+        void st(int q, double v) const { arr[q][i] = v; }
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        IO io{st, i};
+        double un = u_new[i];
+        M::ionic_fast(u[i], un, io, c, io.ld(6));
+        u_new[i] = un;
+    }
+    return 0;
+}
