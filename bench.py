@@ -337,7 +337,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
         if not args.no_extras:
             extras = []
-            for w in ("c3", "c4", "c5"):
+            for w in ("c3", "c4", "c5", "lr91"):
                 if w == args.workload:
                     continue
                 try:

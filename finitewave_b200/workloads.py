@@ -144,6 +144,10 @@ def build(name, device, scale=1.0, rank=0, world=1, dist=None):
     elif name == "c5":
         n = r32(1024)
         own, rest, dim = r32(128), (n, n), 3
+    elif name == "lr91":
+        # not a BASELINE config: the remaining FP64-bound on-path model, same size as C2
+        n = r32(4096, 64)
+        own, rest, dim = n, (n,), 2
     else:
         raise ValueError(f"unknown workload {name}")
     n_global = own * world
@@ -160,6 +164,12 @@ def build(name, device, scale=1.0, rank=0, world=1, dist=None):
         sim.add_stim(StimVoltageCoord2D(3.0, 1, 0, n_global // 2, 0, n))
         info = dict(workload=f"C2 Fenton-Karma 2D {n_global}x{n} aniso 9-pt, 30% random fibrosis",
                     model="fenton_karma", K=9)
+    elif name == "lr91":
+        mesh = fibrosis_mesh(shape, 0.0, 0, device, lo, halo)
+        sim = DeviceSimulation(_cfg(_m.LuoRudy912D()), mesh, **kw)
+        sim.add_stim(StimVoltageCoord2D(0, -20, 0, n_global, 0, 5))
+        info = dict(workload=f"LR91 2D {n_global}x{n} iso 5-pt, planar wave (extra, not a "
+                             "BASELINE config)", model="luo_rudy91", K=5)
     elif name == "c3":
         mesh = fibrosis_mesh(shape, 0.0, 0, device, lo, halo)
         sim = DeviceSimulation(_cfg(_m.MitchellSchaeffer3D()), mesh, **kw)
