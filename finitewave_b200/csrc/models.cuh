@@ -1061,6 +1061,10 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         double ipcamax, krel, iupmax, kup, Vrel, Vup, Vrel_Vup, Fn_a, Fn_b;
         double trpn_k, kmtrpn, cmdn_k, kmcmdn, csqn_k, kmcsqn;
         DivC RT, caupmax, FVj, FVj2, Vj;
+        // fast path only (ionic_fast)
+        double l_nao, l_ko, l_cao, F_RT, e_fca, e_urel;
+        double k47, k32, k5a, k5b, k17a, k17b, k17c, k85;
+        int fast_ok;
     };
     static bool derive(const double *p, double dt, Consts &c)
     {
@@ -1082,6 +1086,13 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         c.csqn_k = p[32] * p[29]; c.kmcsqn = p[29];
         c.caupmax = make_divc(p[20]); c.FVj = make_divc(F * Vj); c.FVj2 = make_divc(2 * F * Vj);
         c.Vj = make_divc(Vj);
+        c.l_nao = log(nao); c.l_ko = log(ko); c.l_cao = log(p[17]); c.F_RT = F / (R * T);
+        c.e_fca = exp(-dt / 2); c.e_urel = exp(-dt / 8);
+        c.k47 = exp(-0.1 * 47.13); c.k32 = exp(-0.1 * 32.);
+        c.k5a = exp(-14.1 / 5.); c.k5b = exp(7.9 / 5.);
+        c.k17a = exp(19.9 / 17.); c.k17b = exp(40. / 17.); c.k17c = exp(82. / 17.);
+        c.k85 = exp(-10. / 8.5);
+        c.fast_ok = nao > 0 && ko > 0 && p[17] > 0 && nao < 1e300 && ko < 1e300 && p[17] < 1e300;
         return divc_ok(c.RT) && divc_ok(c.caupmax) && divc_ok(c.FVj) && divc_ok(c.FVj2) &&
                divc_ok(c.Vj);
     }
@@ -1093,17 +1104,192 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
+        const double nai = io.ld(0), ki = io.ld(1), cai = io.ld(2);
 #ifdef __CUDA_ARCH__
-        if (fabs(u) < FAST_MATH_U_LIMIT) ionic_impl<IO, FastMath>(u, un, io, c);
+        // the rearranged path needs |u| < 300 mV and positive, normal nai / ki / cai (flog,
+        // branch-free reciprocals); NaNs fail the comparisons and take the reference statement
+        if (c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(nai) && conc_ok(ki) && conc_ok(cai))
+            ionic_fast(u, un, io, c, nai, ki, cai);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c);
+            ionic_impl<IO, LibMath>(u, un, io, c, nai, ki, cai);
     }
-    template <class IO, class E>
-    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c)
+    FWB_HD static bool conc_ok(double x) { return x > 1e-300 && x < 1e300; }
+    FWB_HD static double rlf(double inf, double x, double e) { return fma(x - inf, e, inf); }
+
+    // ------------------------------------------------------------------------------------
+    // The device's normal path: ionic_impl's equations rearranged for the FP64 pipe, the
+    // recipe of TP06 / LR91 (identities only; tests/test_host_models.py compares the two):
+    // a Rush-Larsen factor needs 1 / tau, and tau = 1 / (a + b) here, so most gates need no
+    // division for it; x_inf = a / (a + b) and the k / (c + exp) rates are put over common
+    // denominators (one frcp3 each); exponentials with slopes -1/5, +-1/17, -2/17, -0.1
+    // share evaluations; exp(-dt / 2), exp(-dt / 8) (constant time constants) come from the
+    // host; logs by flog; x^1.5 = x sqrt(x).
+    // ------------------------------------------------------------------------------------
+    template <class IO>
+    FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double nai,
+                                  double ki, double cai)
     {
         const double dt = c.dt;
-        const double nai = io.ld(0), ki = io.ld(1), cai = io.ld(2);
+        const double ena = c.RT_F * (c.l_nao - flog(nai));
+        const double ek = c.RT_F * (c.l_ko - flog(ki));
+        const double eca = c.RT_2F * (c.l_cao - flog(cai));
+        const double g01 = fexp_fast(-0.1 * u);
+        const double g5 = fexp_fast(-0.2 * u);                    // exp(-u / 5)
+        const double g17 = fexp_fast(u * (1. / 17.)), i17 = frcp3(g17);
+        // ---- I_Na
+        double ina;
+        {
+            const double am = u == -47.13 ? 3.2 : 0.32 * (u + 47.13) * frcp3(fma(-c.k47, g01, 1.));
+            const double sm = am + 0.08 * fexp_fast(u * (-1. / 11.));
+            const double m = rlf(am * frcp3(sm), io.ld(5), fexp_fast_neg(-dt * sm));
+            double h_inf, sh, j_inf, sj;
+            if (u >= -40) {
+                h_inf = 0.;
+                sh = frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
+                j_inf = 0.;
+                sj = 0.3 * fexp_fast(-0.0000002535 * u) * frcp3(fma(c.k32, g01, 1.));
+            } else {
+                const double ah = 0.135 * fexp_fast((80. + u) * (-1. / 6.8));
+                sh = ah + (3.56 * fexp_fast(0.079 * u) + 310000. * fexp_fast(0.35 * u));
+                h_inf = ah * frcp3(sh);
+                const double a = 1. + fexp_fast(0.311 * (u + 79.23));
+                const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
+                const double nab = (-127140. * fexp_fast(0.2444 * u) -
+                                    0.00003474 * fexp_fast(-0.04391 * u)) * (u + 37.78) * b;
+                const double tot = fma(0.1212 * fexp_fast(-0.01052 * u), a, nab);   // na b + nb a
+                sj = tot * frcp3(a * b);
+                j_inf = nab * frcp3(tot);
+            }
+            const double h = rlf(h_inf, io.ld(6), fexp_fast_neg(-dt * sh));
+            const double j = rlf(j_inf, io.ld(7), fexp_fast_neg(-dt * sj));
+            io.st(5, m); io.st(6, h); io.st(7, j);
+            ina = c.gna * (m * (m * m)) * h * j * (u - ena);
+        }
+        const double ik1 = c.gk1 * (u - ek) * frcp3(1. + fexp_fast(0.07 * (u + 80.)));
+        // ---- I_to, I_Kur (share tau_o)
+        double ito, ikur;
+        {
+            const double A = fma(c.k85, i17 * i17, fexp_fast((u - 30.) * (-1. / 59.0)));
+            const double B = fma(c.k17c, g17, 2.5);
+            const double rtau_o = c.kq10 * 0.65 * (A + B) * frcp3(A * B);
+            const double o_inf = frcp3(1. + fexp_fast((u + 20.47) * (-1. / 17.54)));
+            const double C = 18.53 + fexp_fast((u + 113.7) * (1. / 10.95));
+            const double D = 35.56 + fexp_fast((u + 1.26) * (-1. / 7.44));
+            const double rtau_oi = c.kq10 * (C + D) * frcp3(C * D);
+            const double oi_inf = frcp3(1. + fexp_fast((u + 43.1) * (1. / 5.3)));
+            const double e_o = fexp_fast_neg(-dt * rtau_o);
+            const double oa = rlf(o_inf, io.ld(10), e_o);
+            const double oi = rlf(oi_inf, io.ld(11), fexp_fast_neg(-dt * rtau_oi));
+            io.st(10, oa); io.st(11, oi);
+            ito = c.gto * (oa * (oa * oa)) * oi * (u - ek);
+
+            const double gkur = fma(0.05, frcp3(1. + fexp_fast((u - 15.) * (-1. / 13.0))), 0.005);
+            const double ua_inf = frcp3(1. + fexp_fast((u + 30.3) * (-1. / 9.6)));
+            const double rtau_ui = c.kq10 * (frcp3(21. + fexp_fast((u - 185.) * (-1. / 28.0))) +
+                                             fexp_fast((u - 158.) * (1. / 16.0)));
+            const double ui_inf = frcp3(1. + fexp_fast((u - 99.45) * (1. / 27.48)));
+            const double ua = rlf(ua_inf, io.ld(12), e_o);          // tau_ua == tau_o
+            const double ui = rlf(ui_inf, io.ld(13), fexp_fast_neg(-dt * rtau_ui));
+            io.st(12, ua); io.st(13, ui);
+            ikur = c.gkur_coeff * gkur * (ua * (ua * ua)) * ui * (u - ek);
+        }
+        // ---- I_Kr (gate in slot 15)
+        double ikr;
+        {
+            const double d1 = fma(-c.k5a, g5, 1.);                                   // 1 - exp(-(u+14.1)/5)
+            const double d2 = fexp_fast((u - 3.3328) * (1. / 5.1237)) - 1.;
+            const double rtau_xr = fma(0.0003 * (u + 14.1), d2, 0.000073898 * (u - 3.3328) * d1) *
+                                   frcp3(d1 * d2);
+            const double xr_inf = frcp3(1. + fexp_fast((u + 14.1) * (-1. / 6.5)));
+            const double xr = rlf(xr_inf, io.ld(15), fexp_fast_neg(-dt * rtau_xr));
+            io.st(15, xr);
+            ikr = 0.0294 * xr * (u - ek) * frcp3(1. + fexp_fast((u + 15.) * (1. / 22.4)));
+        }
+        // ---- I_Ks (gate in slot 14)
+        double iks;
+        {
+            const double d1 = fma(-c.k17a, i17, 1.);                                 // 1 - exp(-(u-19.9)/17)
+            const double d2 = fexp_fast((u - 19.9) * (1. / 9.)) - 1.;
+            const double rtau_xs = 2. * (u - 19.9) * fma(0.00004, d2, 0.000035 * d1) * frcp3(d1 * d2);
+            const double xs_inf = frcp3(sqrt(1. + fexp_fast((u - 19.9) * (-1. / 12.7))));
+            const double xs = rlf(xs_inf, io.ld(14), fexp_fast_neg(-dt * rtau_xs));
+            io.st(14, xs);
+            iks = c.gks * (xs * xs) * (u - ek);
+        }
+        // ---- I_CaL
+        double ical;
+        {
+            const double e10 = fexp_fast((u + 10.) * (-1. / 6.24));
+            const double rtau_d = 0.035 * (u + 10.) * (1. + e10) * frcp3(1. - e10);
+            const double d_inf = frcp3(1. + fexp_fast((u + 10.) * (-1. / 8.0)));
+            const double rtau_f = fma(0.0197, fexp_fast(-(0.0337 * 0.0337) * ((u + 10.) * (u + 10.))),
+                                      0.02) * (1. / 9.);
+            const double f_inf = frcp3(1. + fexp_fast((u + 28.) * (1. / 6.9)));
+            const double fca_inf = frcp3(fma(cai, 1. / 0.00035, 1.));
+            const double d = rlf(d_inf, io.ld(8), fexp_fast_neg(-dt * rtau_d));
+            const double f = rlf(f_inf, io.ld(9), fexp_fast_neg(-dt * rtau_f));
+            const double fca = rlf(fca_inf, io.ld(16), c.e_fca);
+            io.st(8, d); io.st(9, f); io.st(16, fca);
+            ical = c.gcal * d * f * fca * (u - 65.);
+        }
+        // ---- I_NaK, I_NaCa
+        const double x = u * c.F_RT;
+        const double en01 = fexp_fast(-0.1 * x);
+        const double en02 = en01 * en01, en04 = en02 * en02, en08 = en04 * en04;
+        const double en_x = en08 * en02;                                             // exp(-x)
+        const double qn = c.kmnai * frcp3(nai);
+        const double inak = c.inakmax * c.ko_kmko *
+                            frcp3(fma(0.0365 * c.nak_s, en_x, fma(0.1245, en01, 1.)) *
+                                  fma(qn, sqrt(qn), 1.));
+        const double e_rev = fexp_fast(-0.65 * x);
+        const double inaca = c.inacamax * e_rev * fma(-c.nao3 * cai, en_x, (nai * (nai * nai)) * c.cao) *
+                             frcp3(en_x * c.ncx_t12 * fma(c.ksatncx, e_rev, 1.));
+        const double ibca = c.gcab * (u - eca);
+        const double ibna = c.gnab * (u - ena);
+        const double ipca = c.ipcamax * cai * frcp3(cai + 0.0005);
+        un -= dt * (ina + ik1 + ito + ikur + ikr + iks + ical + ipca + inak + inaca + ibna + ibca);
+        io.st(0, fma(dt, (-3 * inak - 3 * inaca - ibna - ina) * c.FVj.rc, nai));
+        io.st(1, fma(dt, (2 * inak - ik1 - ito - ikur - ikr - iks - c.ibk) * c.FVj.rc, ki));
+        // ---- SR fluxes
+        const double caup = io.ld(3), carel = io.ld(4);
+        double irel;
+        {
+            const double Fn = c.Fn_a * io.ld(17) - c.Fn_b * (0.5 * ical - 0.2 * inaca);
+            const double u_inf = frcp3(1. + fexp_fast_clamped((Fn - 3.4175e-13) * (-1. / 13.67e-16)));
+            const double rtau_v = frcp3(fma(2.09, u_inf, 1.91));
+            const double v_inf = 1. - frcp3(1. + fexp_fast_clamped((Fn - 6.835e-14) * (-1. / 13.67e-16)));
+            const double e79 = c.k5b * g5;                                           // exp(-(u-7.9)/5)
+            const double rtau_w = fma(0.3, e79, 1.) * (u - 7.9) * frcp3(6. * (1. - e79));
+            const double w_inf = 1. - frcp3(fma(c.k17b, i17, 1.));
+            const double urel = rlf(u_inf, io.ld(19), c.e_urel);
+            const double vrel = rlf(v_inf, io.ld(18), fexp_fast_neg(-dt * rtau_v));
+            const double wrel = rlf(w_inf, io.ld(20), fexp_fast_neg(-dt * rtau_w));
+            irel = c.krel * (urel * urel) * vrel * wrel * (carel - cai);
+            io.st(17, irel); io.st(19, urel); io.st(18, vrel); io.st(20, wrel);
+        }
+        const double itr = (caup - carel) * (1. / 180.);
+        const double iup = c.iupmax * cai * frcp3(cai + c.kup);
+        const double iupleak = caup * c.caupmax.rc * c.iupmax;
+        io.st(3, fma(dt, iup - iupleak - itr * c.Vrel_Vup, caup));
+        {
+            const double B1 = (2 * inaca - ipca - ical - ibca) * c.FVj2.rc +
+                              (c.Vup * (iupleak - iup) + irel * c.Vrel) * c.Vj.rc;
+            const double P = (cai + c.kmtrpn) * (cai + c.kmtrpn), Q = (cai + c.kmcmdn) * (cai + c.kmcmdn);
+            const double PQ = P * Q;
+            io.st(2, fma(dt, B1 * PQ * frcp3(fma(c.trpn_k, Q, fma(c.cmdn_k, P, PQ))), cai));
+        }
+        {
+            const double S = (carel + c.kmcsqn) * (carel + c.kmcsqn);
+            io.st(4, fma(dt, (itr - irel) * S * frcp3(S + c.csqn_k), carel));
+        }
+    }
+
+    template <class IO, class E>
+    FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c, double nai,
+                                  double ki, double cai)
+    {
+        const double dt = c.dt;
         // calc_equilibrum_potentials :246-251
         const double ena = c.RT_F * log(c.nao / nai);
         const double ek = c.RT_F * log(c.ko / ki);

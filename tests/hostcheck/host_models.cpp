@@ -112,3 +112,26 @@ int fwb_host_lr91_fast(double *u_new, const double *u, double *const *st, int64_
     }
     return 0;
 }
+
+// host build of Courtemanche's rearranged device path (Model<COURTEMANCHE>::ionic_fast)
+extern "C" __attribute__((visibility("default")))
+int fwb_host_court_fast(double *u_new, const double *u, double *const *st, int64_t n, double dt,
+                        const double *p)
+{
+    using M = Model<FWB_MODEL_COURTEMANCHE>;
+    M::Consts c;
+    if (!M::derive(p, dt, c)) return -1;
+    struct IO {
+        double *const *arr;
+        int64_t i;
+        double ld(int q) const { return arr[q][i]; }
+        void st(int q, double v) const { arr[q][i] = v; }
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        IO io{st, i};
+        double un = u_new[i];
+        M::ionic_fast(u[i], un, io, c, io.ld(0), io.ld(1), io.ld(2));
+        u_new[i] = un;
+    }
+    return 0;
+}

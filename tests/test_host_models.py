@@ -168,6 +168,36 @@ def test_lr91_fast_path_matches_reference_statement(hostlib):
         assert err.max() < 2e-12, (name, err.max(), u[err.argmax()])
 
 
+def test_courtemanche_fast_path_matches_reference_statement(hostlib):
+    """Model<COURTEMANCHE>::ionic_fast against the reference statement, one step from the
+    same node states (away from the removable 0/0 points of the rate functions)."""
+    rng = np.random.default_rng(6)
+    n = 200000
+    spec = oracle.MODELS["courtemanche"]
+    u, st = _random_node_states("courtemanche", n, rng)
+    u[-n // 10:] = rng.uniform(-290.0, 290.0, n // 10)
+    for sing in (-47.13, -14.1, 3.3328, 19.9, -10.0, 7.9):
+        u[np.abs(u - sing) < 1e-3] += 0.01
+    pvec = np.array([float(v) for v in spec["params"].values()], dtype=np.float64)
+    diff = rng.uniform(-1, 1, n) * 0.01 + u
+    outs = []
+    for fn, extra in ((hostlib.fwb_host_ionic, (MODEL_IDS["courtemanche"],)),
+                      (hostlib.fwb_host_court_fast, ())):
+        un = diff.copy()
+        s2 = [s.copy() for s in st]
+        arr = (c_double_p * len(s2))(*[s.ctypes.data_as(c_double_p) for s in s2])
+        rc = fn(*extra, un.ctypes.data_as(c_double_p), u.ctypes.data_as(c_double_p), arr,
+                ctypes.c_int64(n), ctypes.c_double(0.01), pvec.ctypes.data_as(c_double_p))
+        assert rc == 0
+        outs.append((un, s2))
+    (un_r, st_r), (un_f, st_f) = outs
+    err = np.abs(un_f - un_r) / np.maximum(np.abs(un_r), 1.0)
+    assert err.max() < 1e-12, ("u_new", err.max(), u[err.argmax()])
+    for name, a, b in zip(spec["state"], st_f, st_r):
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+        assert err.max() < 5e-12, (name, err.max(), u[err.argmax()])
+
+
 def test_param_order_matches_oracle_tables():
     """The device parameter vectors are indexed by position: the attribute order in
     finitewave_b200.model must be the oracle's (= the reference's kernel call order)."""
