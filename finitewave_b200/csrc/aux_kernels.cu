@@ -946,6 +946,7 @@ __global__ void devmath_kernel(int op, const double *x, double *y, int64_t n)
     case 2: r = flog(v); break;
     case 3: r = frcp(v); break;
     case 4: r = frcp3(v); break;
+    case 5: r = fsqrt(v); break;
     default: r = v;
     }
     y[i] = r;
@@ -954,7 +955,7 @@ __global__ void devmath_kernel(int op, const double *x, double *y, int64_t n)
 
 extern "C" int fwb_devmath(int op, const double *x, double *y, int64_t n, fwb_stream_t stream)
 {
-    if (!x || !y || n < 0 || op < 0 || op > 4) { set_error("fwb_devmath: bad argument"); return FWB_E_ARG; }
+    if (!x || !y || n < 0 || op < 0 || op > 5) { set_error("fwb_devmath: bad argument"); return FWB_E_ARG; }
     if (n == 0) return 0;
     fwb::devmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, n);
     FWB_KERNEL_CHECK("devmath_kernel");

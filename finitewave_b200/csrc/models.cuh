@@ -766,7 +766,7 @@ template <> struct Model<FWB_MODEL_TP06> {
         double iks;
         {
             const double xs_inf = g14 * frcp3(g14 + c.kxs1);
-            const double sq = sqrt(fma(c.kxs2, n6, 1.));                // Axs = 1400 / sq
+            const double sq = fsqrt(fma(c.kxs2, n6, 1.));                // Axs = 1400 / sq
             const double sb = sq * fma(c.kxs3, g15, 1.);                // Bxs = 1 / (1 + kxs3 g15)
             const double rtau_xs = sb * frcp3(fma(80., sb, 1400.));      // tau_xs = 1400 / sb + 80
             const double xs = rlf(xs_inf, io.ld(10), dt, rtau_xs);
@@ -835,7 +835,7 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double dCaSR = dt * (iup - irel - ileak);
             const double bjsr = c.Bufsr - CaCSQN - dCaSR - casr + c.Kbufsr;
             const double cjsr = c.Kbufsr * (CaCSQN + dCaSR + casr);
-            io.st(1, (sqrt(fma(bjsr, bjsr, 4 * cjsr)) - bjsr) * 0.5);
+            io.st(1, (fsqrt(fma(bjsr, bjsr, 4 * cjsr)) - bjsr) * 0.5);
         }
         {
             const double CaSSBuf = c.Bufss * cass * frcp3(cass + c.Kbufss);
@@ -843,7 +843,7 @@ template <> struct Model<FWB_MODEL_TP06> {
                                        (-ical * c.inversevssF2 * c.CAPACITANCE));
             const double bcss = c.Bufss - CaSSBuf - dCaSS - cass + c.Kbufss;
             const double ccss = c.Kbufss * (CaSSBuf + dCaSS + cass);
-            io.st(2, (sqrt(fma(bcss, bcss, 4 * ccss)) - bcss) * 0.5);
+            io.st(2, (fsqrt(fma(bcss, bcss, 4 * ccss)) - bcss) * 0.5);
         }
     }
 
@@ -1212,7 +1212,7 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
             const double d1 = fma(-c.k17a, i17, 1.);                                 // 1 - exp(-(u-19.9)/17)
             const double d2 = fexp_fast((u - 19.9) * (1. / 9.)) - 1.;
             const double rtau_xs = 2. * (u - 19.9) * fma(0.00004, d2, 0.000035 * d1) * frcp3(d1 * d2);
-            const double xs_inf = frcp3(sqrt(1. + fexp_fast((u - 19.9) * (-1. / 12.7))));
+            const double xs_inf = frcp3(fsqrt(1. + fexp_fast((u - 19.9) * (-1. / 12.7))));
             const double xs = rlf(xs_inf, io.ld(14), fexp_fast_neg(-dt * rtau_xs));
             io.st(14, xs);
             iks = c.gks * (xs * xs) * (u - ek);
@@ -1241,7 +1241,7 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         const double qn = c.kmnai * frcp3(nai);
         const double inak = c.inakmax * c.ko_kmko *
                             frcp3(fma(0.0365 * c.nak_s, en_x, fma(0.1245, en01, 1.)) *
-                                  fma(qn, sqrt(qn), 1.));
+                                  fma(qn, fsqrt(qn), 1.));
         const double e_rev = fexp_fast(-0.65 * x);
         const double inaca = c.inacamax * e_rev * fma(-c.nao3 * cai, en_x, (nai * (nai * nai)) * c.cao) *
                              frcp3(en_x * c.ncx_t12 * fma(c.ksatncx, e_rev, 1.));

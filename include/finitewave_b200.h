@@ -321,7 +321,7 @@ FWB_API int fwb_sim_run(FwbSim *sim, int64_t n_steps);
 /* kernel launches issued by fwb_sim_run so far */
 FWB_API int64_t fwb_sim_launch_count(const FwbSim *sim);
 /* diagnostics: evaluate one of the fast-path math helpers of csrc/fexp.cuh on the device,
- * y[i] = f(x[i]); op 0 fexp, 1 fexp_fast, 2 flog, 3 frcp, 4 frcp3 (accuracy tests) */
+ * y[i] = f(x[i]); op 0 fexp, 1 fexp_fast, 2 flog, 3 frcp, 4 frcp3, 5 fsqrt (accuracy tests) */
 FWB_API int fwb_devmath(int op, const double *x, double *y, int64_t n, fwb_stream_t stream);
 /* diagnostics: the step-kernel variant of the calling thread's last step launch --
  * 0 one block per tile with plain loads, 1 state rows staged by TMA, 2 state + weight rows

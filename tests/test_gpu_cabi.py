@@ -225,3 +225,8 @@ def test_device_math_helpers_accuracy():
         ulp = np.abs(run(op, xr) - ref) / np.spacing(np.abs(ref))
         print("frcp op", op, "max ulp", ulp.max())
         assert ulp.max() <= bound, (op, ulp.max())
+    xs = np.concatenate([np.exp(rng.uniform(-600, 600, 4_000_000)), rng.uniform(1, 4, 4_000_000)])
+    ref = np.sqrt(xs)
+    ulp = np.abs(run(5, xs) - ref) / np.spacing(ref)
+    print("fsqrt max ulp", ulp.max())
+    assert ulp.max() <= 1.0, ulp.max()
