@@ -31,7 +31,8 @@ from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker, Animat
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,
                       ECG3DTracker, LocalActivationTime2DTracker, LocalActivationTime3DTracker,
                       MultiVariable2DTracker, MultiVariable3DTracker, Period2DTracker,
-                      Period3DTracker, SpiralWaveCore2DTracker, SpiralWaveCore3DTracker, Tracker,
+                      Period3DTracker, PeriodAnimation2DTracker, PeriodAnimation3DTracker,
+                      SpiralWaveCore2DTracker, SpiralWaveCore3DTracker, Tracker,
                       TrackerSequence, Variable2DTracker, Variable3DTracker)
 
 __version__ = "0.1.0"

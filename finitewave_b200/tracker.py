@@ -671,3 +671,92 @@ class AnimationSlice3DTracker(Animation2DTracker):
         if self.slice_y is not None:
             return (slice(None), self.slice_y, slice(None))
         return (slice(None), slice(None), self.slice_z)
+
+
+class PeriodAnimation2DTracker(LocalActivationTime2DTracker):
+    """Frame dump of the map of every node's latest threshold up-crossing time (reference
+    cpuwave2D/tracker/period_animation_2d_tracker.py:7-72: ``period_map = where(cross, t,
+    period_map)``, one ``.npy`` per sample).  Crossing detection and map update run on the
+    device (fwb_lat_cross / fwb_lat_write); the frames are streamed out like the animation
+    trackers' (hooks.FrameStreamer).  ``write()`` (the mp4 builder) is not part of this
+    backend."""
+
+    def __init__(self):
+        super().__init__()
+        self.dir_name = "period"
+        self.file_name = "period"
+        self.overwrite = False
+        self._frame_counter = 0
+        self.period_map = np.ndarray
+        self._streamer = None
+
+    def initialize(self, model):
+        self.model = model
+        self._frame_counter = 0
+        self.period_map = -np.ones_like(self.model.u)
+        self._activated = np.full(self.model.u.shape, 0, dtype=bool)
+        out = Path(self.path, self.dir_name)
+        if not out.is_dir():
+            out.mkdir(parents=True)
+        if self.overwrite:
+            for f in out.glob("*.npy"):
+                f.unlink()
+        self._dev = None
+        self._streamer = None
+
+    def _ensure_dev(self, engine):
+        if self._dev is None or self._dev["device"] != engine.device:
+            dev = engine.device
+            self._dev = dict(
+                device=dev,
+                activated=torch.from_numpy(np.ascontiguousarray(self._activated, dtype=np.uint8)
+                                           .reshape(-1)).to(dev),
+                cross=torch.zeros(engine.n_nodes, dtype=torch.uint8, device=dev),
+                map=torch.from_numpy(np.ascontiguousarray(self.period_map, dtype=np.float64)).to(dev),
+                dirty=False)
+        return self._dev
+
+    def _track_device(self, engine, u, t):
+        d = self._ensure_dev(engine)
+        L, st = engine.L, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n = engine.n_nodes
+        check(L.fwb_lat_cross(ctypes.c_void_p(u.data_ptr()), n, float(self.threshold),
+                              ctypes.c_void_p(d["activated"].data_ptr()),
+                              ctypes.c_void_p(d["cross"].data_ptr()), None, None, st), "fwb_lat_cross")
+        check(L.fwb_lat_write(ctypes.c_void_p(d["cross"].data_ptr()), n, float(t),
+                              ctypes.c_void_p(d["map"].data_ptr()), st), "fwb_lat_write")
+        if self._streamer is None:
+            from .hooks import FrameStreamer
+            self._streamer = FrameStreamer(engine.shape)
+        path = Path(self.path, self.dir_name, str(self._frame_counter)).with_suffix(".npy")
+        self._streamer.submit(d["map"].clone(), path, "float64")
+        self._frame_counter += 1
+        d["dirty"] = True
+
+    def _collect(self, engine=None):
+        d = self._dev
+        if d is None or not d["dirty"]:
+            return
+        shape = self.model.u.shape
+        self.period_map = d["map"].cpu().numpy().reshape(shape)
+        self._activated = d["activated"].cpu().numpy().reshape(shape).astype(bool)
+        d["dirty"] = False
+
+    def _finish(self):
+        if self._streamer is not None:
+            self._streamer.wait()
+        self._collect()
+
+    @property
+    def output(self):
+        self._collect()
+        return self.period_map
+
+    def write(self, *args, **kwargs):
+        raise NotImplementedError(
+            "building the animation file is finitewave.tools' job (matplotlib / ffmpeg); the "
+            f"frames are in {Path(self.path, self.dir_name)}")
+
+
+class PeriodAnimation3DTracker(PeriodAnimation2DTracker):
+    pass

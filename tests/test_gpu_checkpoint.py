@@ -132,3 +132,29 @@ def test_animation_trackers_stream_frames(fw, tmp_path):
     with pytest.raises(ValueError):
         bad = fw.AnimationSlice3DTracker()
         bad.initialize(m3)
+
+
+def test_period_animation_tracker(fw, tmp_path):
+    """PeriodAnimation2DTracker (reference period_animation_2d_tracker.py:49-60): frame i is the
+    map of the latest up-crossing time after sample i; the last frame equals the per-node
+    maximum over the LocalActivationTime layers sampled at the same steps."""
+    case = dict(case_by_name("barkley2d_lat_period"), trackers=[])
+    model, _ = build_model(fw, case)
+    pa = fw.PeriodAnimation2DTracker()
+    pa.path, pa.dir_name, pa.threshold, pa.step, pa.overwrite = str(tmp_path), "pm", 0.5, 20, True
+    lat = fw.LocalActivationTime2DTracker()
+    lat.threshold, lat.step = 0.5, 20
+    seq = fw.TrackerSequence()
+    seq.add_tracker(pa)
+    seq.add_tracker(lat)
+    model.tracker_sequence = seq
+    model.run()
+    n = model.step // 20
+    frames = [np.load(tmp_path / "pm" / f"{i}.npy") for i in range(n)]
+    assert len(list((tmp_path / "pm").glob("*.npy"))) == n
+    last = np.max(lat.output, axis=0)
+    assert np.array_equal(frames[-1], last)
+    assert np.array_equal(pa.output, last)
+    assert (frames[0] == -1).sum() > (frames[-1] == -1).sum()
+    for a, b in zip(frames, frames[1:]):
+        assert np.all(b >= a)
