@@ -303,6 +303,34 @@ def make_cases():
         trackers=[dict(kind="local_activation_time", threshold=0.5, step=5),
                   dict(kind="period", threshold=0.5, step=5, cell_ind=[[7, 6, 5], [12, 3, 8]])]))
 
+    # StimCurrentArea2D / 3D: coordinate lists with duplicates, fibrotic entries and a u_max
+    # clamp (numpy applies `u[inds] += x` once per distinct node)
+    rng = np.random.default_rng(31)
+    pts2 = np.column_stack([rng.integers(2, 12, 60), rng.integers(2, 30, 60)])
+    pts2 = np.vstack([pts2, pts2[:10]])
+    cases.append(dict(
+        name="fk2d_current_area", model="fenton_karma", shape=[36, 32],
+        dt=0.01, dr=0.25, t_max=5,
+        mesh=random_fibrosis([36, 32], 0.15, 32),
+        stims=[dict(kind="current_area", t=0.3, value=6, duration=0.6, coords=pts2, u_max=0.95)],
+        trackers=[dict(kind="activation_time", threshold=0.4, step=1)]))
+    pts3 = np.column_stack([rng.integers(1, 5, 80), rng.integers(1, 11, 80), rng.integers(1, 9, 80)])
+    cases.append(dict(
+        name="ms3d_current_area", model="mitchell_schaeffer", shape=[14, 12, 10],
+        dt=0.01, dr=0.25, t_max=4,
+        stims=[dict(kind="current_area", t=0, value=4, duration=0.4, coords=pts3)],
+        trackers=[dict(kind="action_potential", cell_ind=[3, 5, 4], step=2)]))
+    # StimVoltageListMatrix3D: a voltage ramp, one list entry per firing
+    mat = np.zeros([12, 10, 10])
+    mat[1:4, :, :] = 1
+    cases.append(dict(
+        name="ap3d_voltage_list", model="aliev_panfilov", shape=[12, 10, 10],
+        dt=0.01, dr=0.25, t_max=4,
+        mesh=random_fibrosis([12, 10, 10], 0.1, 33),
+        stims=[dict(kind="voltage_list_matrix", t=0.2, duration=0.3, matrix=mat,
+                    value=list(np.linspace(0.1, 1.0, 40)))],
+        trackers=[dict(kind="action_potential", cell_ind=[6, 5, 5], step=1)]))
+
     # SpiralWaveCore trackers: Barkley spiral (the protocol of the
     # reference's tests/test_trackers_2d.py:25-40, smaller), tips every 10 steps
     cases.append(dict(
@@ -391,6 +419,9 @@ def build_model(fw, case):
         elif kind == "current_matrix":
             st = getattr(fw, "StimCurrentMatrix" + sfx)(s["t"], s["value"], s["duration"],
                                                         s["matrix"], u_max=s.get("u_max"))
+        elif kind == "voltage_list_matrix":
+            st = getattr(fw, "StimVoltageListMatrix" + sfx)(s["t"], list(s["value"]), s["duration"],
+                                                            np.array(s["matrix"]))
         elif kind == "current_area":
             st = getattr(fw, "StimCurrentArea" + sfx)(s["t"], s["value"], s["duration"],
                                                       coords=np.array(s["coords"]),
