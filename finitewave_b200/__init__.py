@@ -25,7 +25,7 @@ from .stimulation import (Stim, StimCurrent, StimCurrentArea2D, StimCurrentArea3
                           StimCurrentMatrix3D, StimSequence, StimVoltage, StimVoltageCoord2D,
                           StimVoltageCoord3D, StimVoltageListMatrix3D, StimVoltageMatrix2D,
                           StimVoltageMatrix3D)
-from .tissue import CardiacTissue, CardiacTissue2D, CardiacTissue3D
+from .tissue import CardiacTissue, CardiacTissue2D, CardiacTissue3D, IncorrectWeightsModeError2D
 from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker, Animation2DTracker,
                       Animation3DTracker, AnimationSlice3DTracker,
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,

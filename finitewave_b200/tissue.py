@@ -18,6 +18,21 @@ import copy
 import numpy as np
 
 
+class IncorrectWeightsModeError2D(Exception):
+    """Raised for a 2D weights mode other than 'iso' / 'aniso' (reference
+    finitewave/cpuwave2D/exception/exceptions_2d.py:1-37: attributes ``mode`` and
+    ``message``, and the offending mode appended in ``str()``).  The reference exports the
+    class but never raises it (the stencil is chosen from ``tissue.fibers``); kept so that
+    user code catching it keeps working."""
+
+    def __init__(self, mode, message="CardiacTissue2D mode attribute must be 'iso' or 'aniso'"):
+        super().__init__(message)
+        self.mode, self.message = mode, message
+
+    def __str__(self):
+        return f"{self.message} (Invalid mode: '{self.mode}')"
+
+
 class CardiacTissue:
     _DIM = None
 
