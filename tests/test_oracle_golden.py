@@ -41,6 +41,43 @@ def test_oracle_matches_reference(case):
             assert np.array_equal(out[k], g[k]), f"{k}: {max_rel_err(out[k], g[k]):.3e}"
 
 
+def _weight_cases():
+    from tests.golden.make_weights_golden import weight_cases
+    return weight_cases()
+
+
+@pytest.mark.parametrize("kind", ["iso2d", "aniso2d", "sym2d", "iso3d", "aniso3d"])
+def test_oracle_weights_match_reference_on_wide_inputs(kind):
+    """Weights-only fixtures of the live reference (tests/golden/make_weights_golden.py):
+    conductivity arrays together with fibres, non-default D_al / D_ac, 42 % fibrosis with
+    isolated nodes and one-node strands, odd dt / dr / D_model -- bit for bit."""
+    c = next(x for x in _weight_cases() if x["name"] == kind)
+    g = np.load(GOLDEN / f"weights_{kind}.npz")
+    mesh = oracle.apply_boundaries(c["mesh"].copy())
+    assert int(g["mesh_sum"]) == int(mesh.astype(np.int64).sum())
+    w = oracle.compute_weights(mesh, c["conductivity"], c["fibers"], c["kind"], c["D_model"],
+                               c["dt"], c["dr"], D_al=c["D_al"], D_ac=c["D_ac"])
+    assert np.array_equal(w, g["weights"])
+
+
+@pytest.mark.parametrize("model", list(oracle.MODELS))
+def test_oracle_ionic_matches_reference_one_step(model):
+    """One call of the live reference's own ``run_ionic_kernel()`` on random node states on
+    both sides of (and exactly at) every branch threshold
+    (tests/golden/make_ionic_golden.py): u_new and every state array, bit for bit."""
+    from tests.golden.make_ionic_golden import DT, SHAPE, ionic_inputs
+    spec = oracle.MODELS[model]
+    g = np.load(GOLDEN / f"ionic_{model}.npz")
+    u, u_new, states = ionic_inputs(model)
+    idx = np.flatnonzero(oracle.apply_boundaries(np.ones(SHAPE, dtype=np.int8)) == 1)
+    states = [np.ascontiguousarray(s) for s in states]
+    pvec = np.array([float(v) for v in spec["params"].values()], dtype=np.float64)
+    oracle.ionic(model, u_new, u, states, idx.astype(np.int64), DT, pvec)
+    assert np.array_equal(u_new, g["u_new"])
+    for var, s in zip(spec["state"], states):
+        assert np.array_equal(s, g[var]), var
+
+
 def test_golden_inputs_unchanged():
     """The case definitions still produce the inputs the fixtures were made from."""
     from tests.golden.make_golden import input_checksum
