@@ -234,3 +234,74 @@ def test_user_defined_stimulus_and_tracker_run_as_host_hooks():
     assert samples[0][1] == 0.0 and samples[1][1] == 0.0      # stimulus not yet due at 0.1-
     assert samples[2][1] > 0.5                                 # fired on the step t >= 0.1
     assert sseq.sequence[0].passed
+
+
+def _stim_specs():
+    from tests.golden.make_stim_golden import stim_specs
+    return stim_specs()
+
+
+@pytest.mark.parametrize("spec", _stim_specs(), ids=[s[0] for s in _stim_specs()])
+def test_stimulus_host_statements_match_reference(spec):
+    """Every stimulus class, one or two ``stimulate()`` calls on a random field (fixtures of
+    tests/golden/make_stim_golden.py from the live reference: negative / out-of-range boxes,
+    empty boxes, float matrices, biting u_max clamps, duplicate coordinates, voltage lists):
+    the product's host statement AND the oracle's restatement, bit for bit."""
+    from oracle import oracle
+    from tests.golden.make_stim_golden import DT, apply, fields
+    key, dim, cls, args, kwargs, calls = spec
+    want = np.load(GOLDEN / "stim_onecall.npz")[key]
+    assert np.array_equal(apply(fw, spec), want)
+
+    kind = {"StimVoltageCoord": "voltage_coord", "StimCurrentCoord": "current_coord",
+            "StimVoltageMatrix": "voltage_matrix", "StimCurrentMatrix": "current_matrix",
+            "StimCurrentArea": "current_area",
+            "StimVoltageListMatrix": "voltage_list_matrix"}[cls[:-2]]
+    st = dict(kind=kind, value=args[1], u_max=kwargs.get("u_max"))
+    if kind.endswith("_coord"):
+        st["box"] = list(args[3:] if kind == "current_coord" else args[2:])
+    elif kind == "current_area":
+        st["coords"] = kwargs["coords"]
+    else:
+        st["matrix"] = np.asarray(args[-1])
+    mesh, u = fields(dim)
+    counters = {}
+    for _ in range(calls):
+        oracle._stimulate(st, u, mesh, DT, counters)
+    assert np.array_equal(u, want)
+
+
+@pytest.mark.parametrize("spec", _stim_specs(), ids=[s[0] for s in _stim_specs()])
+def test_native_stimulus_descriptors_select_the_reference_nodes(spec):
+    """The descriptor a built-in stimulus hands to the device runner -- a normalised index box
+    (`_norm_box`) or a flat node list (`_flat_nodes`) -- applied the way the stim kernels
+    document it (value / += dt * value / clamp, on mesh == 1 nodes of the box; on every listed
+    node) gives the live reference's field.  The kernels themselves are covered on the GPU
+    (tests/test_gpu_cabi.py, tests/test_gpu_parity.py)."""
+    import types
+    from tests.golden.make_stim_golden import DT, fields
+    key, dim, cls, args, kwargs, calls = spec
+    want = np.load(GOLDEN / "stim_onecall.npz")[key]
+    mesh, u = fields(dim)
+    model = types.SimpleNamespace(u=u, dt=DT, t=0.0, cardiac_tissue=types.SimpleNamespace(mesh=mesh))
+    st = getattr(fw, cls)(*args, **kwargs)
+    st.initialize(model)
+    if hasattr(st, "_box"):
+        b = st._norm_box(mesh.shape)
+        sel = np.zeros(mesh.shape, dtype=bool)
+        sel[tuple(slice(b[2 * d], b[2 * d + 1]) for d in range(dim))] = True
+        flat = np.flatnonzero(sel & (mesh == 1))
+    else:
+        flat = np.asarray(st._flat_nodes(model))
+        assert len(np.unique(flat)) == len(flat)
+    uf = u.reshape(-1)
+    for k in range(calls):
+        if cls.startswith("StimVoltageList"):
+            uf[flat] = st.volt_value[k]
+        elif cls.startswith("StimVoltage"):
+            uf[flat] = st.volt_value
+        else:
+            uf[flat] += DT * st.curr_value
+            if st.u_max is not None:
+                uf[flat] = np.minimum(uf[flat], st.u_max)
+    assert np.array_equal(u, want)
