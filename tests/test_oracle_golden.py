@@ -78,6 +78,26 @@ def test_oracle_ionic_matches_reference_one_step(model):
         assert np.array_equal(s, g[var]), var
 
 
+def test_oracle_ecg_and_tip_finder_match_reference_one_call():
+    """``compute_ecg`` (leads on a node, inside and far outside the tissue) to 1e-12 and the
+    spiral-tip finder on smooth random field pairs (dozens of tips per frame) bit for bit,
+    against one-call outputs of the live reference (tests/golden/make_tracker_golden.py)."""
+    from tests.golden.make_tracker_golden import ecg_inputs, tip_inputs
+    g = np.load(GOLDEN / "tracker_onecall.npz")
+    for dim in (2, 3):
+        mesh, u, u_tr, coords, dr = ecg_inputs(dim)
+        idx = np.flatnonzero(mesh == 1).astype(np.int64)
+        got = oracle.ecg(u_tr, u, coords, dr, idx, mesh.shape)
+        assert max_rel_err(got, g[f"ecg{dim}"]) <= 1e-12
+    n_tips = 0
+    for k in range(4):
+        a, b, thr = tip_inputs(k)
+        tips = np.array(oracle.tip_scan_2d(a, b, thr), dtype=np.float64).reshape(-1, 2)
+        assert np.array_equal(tips, g[f"tips{k}"]), k
+        n_tips += len(tips)
+    assert n_tips > 40
+
+
 def test_golden_inputs_unchanged():
     """The case definitions still produce the inputs the fixtures were made from."""
     from tests.golden.make_golden import input_checksum
