@@ -95,3 +95,45 @@ def test_product_never_imports_the_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), py
     for cu in (ROOT / "finitewave_b200" / "csrc").iterdir():
         assert "fw_oracle" not in cu.read_text().replace("oracle/", ""), cu
+
+
+def test_ctypes_signatures_match_the_header(L):
+    """Binding drift is the classic FFI bug: every prototype of include/finitewave_b200.h is
+    compared with the ctypes ``argtypes`` the package declares for it (finitewave_b200/_lib.py)
+    -- same number of parameters, and pointer / double / int64_t / int / unsigned in the same
+    positions."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = re.findall(r"FWB_API\s+[\w\s\*]+?\s*\b(fwb_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert sorted(n for n, _ in protos) == _declared()
+
+    def kind(param):
+        param = " ".join(param.split())
+        if param in ("void", ""):
+            return None
+        if "*" in param or "fwb_stream_t" in param:
+            return "ptr"
+        return param.rsplit(" ", 1)[0].replace("const ", "").strip()
+
+    def matches(k, a):
+        if k == "ptr":
+            return a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, ctypes._Pointer)
+        return a in {"double": (ctypes.c_double,), "int64_t": (ctypes.c_int64,),
+                     "int": (ctypes.c_int,), "unsigned": (ctypes.c_uint, ctypes.c_uint32),
+                     "uint32_t": (ctypes.c_uint, ctypes.c_uint32),
+                     "uint64_t": (ctypes.c_uint64,),
+                     "unsigned long long": (ctypes.c_uint64, ctypes.c_ulonglong)}.get(k, ())
+
+    checked = 0
+    for name, params in protos:
+        kinds = [k for k in (kind(p) for p in params.split(",")) if k is not None]
+        argtypes = getattr(L, name).argtypes
+        if argtypes is None:
+            assert not kinds, f"{name}: {len(kinds)} parameters but no argtypes declared"
+            continue
+        assert len(argtypes) == len(kinds), (name, len(argtypes), len(kinds))
+        for i, (k, a) in enumerate(zip(kinds, argtypes)):
+            assert matches(k, a), (name, i, k, a)
+        checked += 1
+    assert checked >= 45
