@@ -126,7 +126,7 @@ def cpu_case(workload):
     return cases_for_bench(workload)
 
 
-def cpu_time(workload, budget_s, steps=None):
+def cpu_time(workload, budget_s, steps=None, warmup=3):
     from oracle import oracle
     oracle.build()
     threads = os.cpu_count() or 1
@@ -135,7 +135,7 @@ def cpu_time(workload, budget_s, steps=None):
         sec, n_myo = oracle.time_steps(case, 3, n_threads=threads, warmup=1)
         per = sec / 3
         steps = int(min(2000, max(5, budget_s / max(per, 1e-6))))
-    sec, n_myo = oracle.time_steps(case, steps, n_threads=threads, warmup=2)
+    sec, n_myo = oracle.time_steps(case, steps, n_threads=threads, warmup=max(3, warmup))
     return dict(value=n_myo * steps / sec, unit=UNIT, cores=threads, kind="port",
                 sample=f"{sample}, {steps} steps in {sec:.1f} s (oracle/fw_oracle.c, OpenMP)"), sec, steps
 
@@ -147,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb, sec, steps = cpu_time(args.workload, 0, steps=args.steps)
+    cb, sec, steps = cpu_time(args.workload, 0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -173,8 +173,10 @@ WORKLOAD_NAMES = {
 # ---------------------------------------------------------------------------
 # GPU side
 # ---------------------------------------------------------------------------
-def time_device(sim, steps, warmup, dist=None):
+def time_device(sim, steps, warmup, dist=None, propagate=0):
     import torch
+    if propagate > 0:
+        sim.run(propagate)       # time from the state after >= 500 steps of propagation
     sim.run(warmup)
     torch.cuda.synchronize()
     if dist is not None:
@@ -283,7 +285,7 @@ def run_b200(args):
                                 dist=dist)
 
     with ClockSampler(local) as clk:
-        ms, launches = time_device(sim, args.steps, args.warmup, dist)
+        ms, launches = time_device(sim, args.steps, args.warmup, dist, args.propagate)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,6 +308,8 @@ def run_b200(args):
                    "l2_policy": "working set per step >> 126 MB L2 (no flush needed)"
                    if info["bytes_per_node"] * info["n_myo"] > 4 * 126e6 else
                    "working set fits L2; number is L2-resident",
+                   "state": f"after {args.propagate} propagation steps + {args.warmup} warm-up steps "
+                            "from the stimulus at t = 0",
                    "parallelism": "1 GPU" if world == 1 else f"{world} slabs, 1-plane halo exchange"},
         "gpu_launches": launches,
         "clocks": clk.summary(),
@@ -342,7 +346,7 @@ def run_b200(args):
                     continue
                 try:
                     s2, i2 = workloads.build(w, device, scale=args.scale)
-                    ms2, l2 = time_device(s2, max(10, args.steps // 8), 5)
+                    ms2, l2 = time_device(s2, max(10, args.steps // 8), 5, None, args.propagate)
                     k = max(10, args.steps // 8)
                     ach = i2["bytes_per_node"] * i2["n_myo"] * k / (ms2 * 1e-3) / 1e9
                     extras.append({"workload": i2["workload"], "value": i2["n_myo"] * k / (ms2 * 1e-3),
@@ -379,6 +383,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1000,
                     help="time steps per model.run() call of the e2e leg (README quick start: 1000)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--propagate", type=int, default=500,
+                    help="untimed time steps before the warm-up (SURVEY 8d: >= 500)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
