@@ -10,6 +10,8 @@ hand-written sm_100a CUDA kernels behind the C ABI of include/finitewave_b200.h
 There is no CPU fallback: without the CUDA library or a CUDA device every compute
 entry raises ``FwbError``.
 """
+import sys
+
 from ._lib import FwbError
 from .fibrosis import (Diffuse2DPattern, Diffuse3DPattern, FibrosisPattern, Structural2DPattern,
                        Structural3DPattern)
@@ -25,7 +27,8 @@ from .stimulation import (Stim, StimCurrent, StimCurrentArea2D, StimCurrentArea3
                           StimCurrentMatrix3D, StimSequence, StimVoltage, StimVoltageCoord2D,
                           StimVoltageCoord3D, StimVoltageListMatrix3D, StimVoltageMatrix2D,
                           StimVoltageMatrix3D)
-from .tissue import CardiacTissue, CardiacTissue2D, CardiacTissue3D, IncorrectWeightsModeError2D
+from .tissue import (CardiacTissue, CardiacTissue2D, CardiacTissue3D, IncorrectNumberOfWeights,
+                     IncorrectWeightsModeError2D, IncorrectWeightsShapeError)
 from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker, Animation2DTracker,
                       Animation3DTracker, AnimationSlice3DTracker,
                       ActivationTime2DTracker, ActivationTime3DTracker, ECG2DTracker,
@@ -36,3 +39,7 @@ from .tracker import (ActionPotential2DTracker, ActionPotential3DTracker, Animat
                       TrackerSequence, Variable2DTracker, Variable3DTracker)
 
 __version__ = "0.1.0"
+
+# the reference's sub-module import paths (finitewave.cpuwave2D.fibrosis.diffuse_2d_pattern, ...)
+from . import _compat  # noqa: E402
+_compat.install(sys.modules[__name__])

@@ -33,6 +33,21 @@ class IncorrectWeightsModeError2D(Exception):
         return f"{self.message} (Invalid mode: '{self.mode}')"
 
 
+class IncorrectWeightsShapeError(Exception):
+    """finitewave/core/exception/exceptions.py:1-3 (exported by ``finitewave.core.exception``,
+    raised nowhere in the reference)."""
+
+
+class IncorrectNumberOfWeights(Exception):
+    """finitewave/core/exception/exceptions.py:6-39: number of stencil weights that is neither
+    of the two expected counts."""
+
+    def __init__(self, number_of_weights, n1, n2):
+        self.message = (f"Number of weights provided ({number_of_weights})"
+                        f"does not match the expected {n1} or {n2}.")
+        super().__init__(self.message)
+
+
 class CardiacTissue:
     _DIM = None
 

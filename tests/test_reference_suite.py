@@ -1,0 +1,88 @@
+"""
+Drop-in checks against the reference's own public layout and its OWN tests (CPU, no GPU).
+
+* every sub-module import path of the reference resolves inside this package and yields the
+  very class the flat namespace exports (finitewave_b200/_compat.py);
+* where the reference tree is present (/root/reference, build container only -- skipped
+  elsewhere), its own test files run UNMODIFIED, in place, with ``finitewave`` resolving to
+  finitewave_b200 on the CPU test double (tests/reference_shim.py).  The default selection
+  (state loading, commands, Aliev-Panfilov and Barkley in 2D and 3D: 6 tests, ~10 s) keeps
+  the CPU suite short; FWB_FULL_REFERENCE_SUITE=1 runs every test that does not need a
+  device-only tracker / pattern: test_basics.py, test_models_2d.py, test_models_3d.py --
+  18 tests, all eight models, 18 passed on 2026-10-17 (about half an hour of CPU oracle).
+"""
+import importlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+import finitewave_b200 as fw
+from finitewave_b200 import _compat
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_TESTS = Path("/root/reference/tests")
+
+
+def test_reference_submodule_paths_resolve():
+    assert len(_compat._LAYOUT) >= 95
+    for path, (is_package, names) in _compat._LAYOUT.items():
+        mod = importlib.import_module(f"finitewave_b200.{path}")
+        assert hasattr(mod, "__path__") == is_package, path
+        assert names, path
+        for name in names:
+            assert getattr(mod, name) is getattr(fw, name), (path, name)
+    from finitewave_b200.cpuwave2D.fibrosis.diffuse_2d_pattern import Diffuse2DPattern
+    from finitewave_b200.cpuwave3D.model.tp06_3d import TP063D
+    assert Diffuse2DPattern is fw.Diffuse2DPattern and TP063D is fw.TP063D
+    with pytest.raises(ModuleNotFoundError):
+        importlib.import_module("finitewave_b200.cpuwave2D.no_such_module")
+    # real sub-modules are untouched by the finder
+    assert Path(importlib.import_module("finitewave_b200.tracker").__file__).name == "tracker.py"
+
+
+def test_paths_resolve_under_the_reference_package_name(monkeypatch):
+    monkeypatch.setitem(sys.modules, "finitewave", fw)
+    try:
+        from finitewave.core.state.state_saver import StateSaver
+        from finitewave.cpuwave3D.fibrosis.structural_3d_pattern import Structural3DPattern
+        assert StateSaver is fw.StateSaver and Structural3DPattern is fw.Structural3DPattern
+    finally:
+        for k in [k for k in sys.modules if k.startswith("finitewave.")]:
+            del sys.modules[k]
+
+
+def test_exception_classes_of_the_reference():
+    e = fw.IncorrectNumberOfWeights(6, 5, 9)
+    assert "(6)" in str(e) and "5 or 9" in str(e)
+    assert issubclass(fw.IncorrectWeightsShapeError, Exception)
+    e = fw.IncorrectWeightsModeError2D("xx")
+    assert e.mode == "xx" and "Invalid mode: 'xx'" in str(e)
+
+
+def _run_reference_tests(tmp_path, files, select=None):
+    cmd = [sys.executable, "-m", "pytest", "-p", "tests.reference_shim", "-q", "-x",
+           "-p", "no:cacheprovider", "-p", "no:warnings", "--rootdir", str(tmp_path)]
+    if select:
+        cmd += ["-k", select]
+    cmd += [str(REF_TESTS / f) for f in files]
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    return subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=3000)
+
+
+@pytest.mark.skipif(not REF_TESTS.exists(), reason="reference tree not present (build container only)")
+def test_reference_own_tests_pass_unmodified(tmp_path):
+    full = os.environ.get("FWB_FULL_REFERENCE_SUITE") == "1"
+    if full:
+        p = _run_reference_tests(tmp_path, ["test_basics.py", "test_models_2d.py", "test_models_3d.py"])
+        want = 18
+    else:
+        p = _run_reference_tests(tmp_path, ["test_basics.py", "test_models_2d.py",
+                                            "test_models_3d.py"],
+                                 "state_loading or commands or aliev_panfilov or barkley")
+        want = 6
+    tail = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-500:]
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
+    assert f"{want} passed" in tail, tail
