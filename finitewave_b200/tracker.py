@@ -630,9 +630,17 @@ class Animation2DTracker(Tracker):
         self._frame_counter += 1
 
     def _track(self):
-        eng = self.model._engine
-        self._track_device(eng, eng.ubuf[eng.current()], self.model.t)
-        self._finish()
+        """Called by hand (or from a host hook), outside the device loop: ``model.<variable>``
+        is then a current host array and the reference's statement applies as it is
+        (animation_2d_tracker.py:64-77, animation_slice_3d_tracker.py:45-56) -- a file write,
+        no computation.  Works on any object with that attribute, as in the reference's tests."""
+        frame = np.asarray(self.model.__dict__[self.variable_name])
+        sel = self._select()
+        if sel is not None:
+            frame = frame[sel]
+        np.save(Path(self.path, self.dir_name, str(self._frame_counter)).with_suffix(".npy"),
+                frame.astype(self.frame_type))
+        self._frame_counter += 1
 
     def _finish(self):
         """Called by run() before it returns: every submitted frame is on disk."""
@@ -671,6 +679,10 @@ class AnimationSlice3DTracker(Animation2DTracker):
         if self.slice_y is not None:
             return (slice(None), self.slice_y, slice(None))
         return (slice(None), slice(None), self.slice_z)
+
+    def select_frame(self, array):
+        """The 2D slice of a 3D array (animation_slice_3d_tracker.py:58-80)."""
+        return array[self._select()]
 
 
 class PeriodAnimation2DTracker(LocalActivationTime2DTracker):

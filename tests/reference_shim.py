@@ -37,4 +37,6 @@ def _finitewave_b200_on_the_cpu_double(monkeypatch):
             cls = getattr(mod, name)
             if isinstance(cls, type) and cls.__dict__.get("_native", False):
                 monkeypatch.setattr(cls, "_native", False)
+    # the animation trackers' frame dump has a host statement too (plain np.save)
+    monkeypatch.setattr(tracker.Animation2DTracker, "_device_hook", False)
     monkeypatch.setattr(model.CardiacModel, "async_checkpoints", False, raising=False)

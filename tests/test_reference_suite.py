@@ -6,10 +6,11 @@ Drop-in checks against the reference's own public layout and its OWN tests (CPU,
 * where the reference tree is present (/root/reference, build container only -- skipped
   elsewhere), its own test files run UNMODIFIED, in place, with ``finitewave`` resolving to
   finitewave_b200 on the CPU test double (tests/reference_shim.py).  The default selection
-  (state loading, commands, Aliev-Panfilov and Barkley in 2D and 3D: 6 tests, ~10 s) keeps
-  the CPU suite short; FWB_FULL_REFERENCE_SUITE=1 runs every test that does not need a
-  device-only tracker / pattern: test_basics.py, test_models_2d.py, test_models_3d.py --
-  18 tests, all eight models, 18 passed on 2026-10-17 (about half an hour of CPU oracle).
+  (state loading, commands, Aliev-Panfilov and Barkley in 2D and 3D, and the nine tracker
+  tests whose trackers have a host statement: 15 tests, ~15 s) keeps the CPU suite short;
+  FWB_FULL_REFERENCE_SUITE=1 adds the other six models in 2D and 3D: 27 of the reference's
+  41 tests, all passing on 2026-10-17 (about half an hour of CPU oracle).  The remaining 14
+  need device-only trackers / patterns and are mirrored in tests/test_gpu_acceptance.py.
 """
 import importlib
 import os
@@ -72,17 +73,22 @@ def _run_reference_tests(tmp_path, files, select=None):
     return subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=3000)
 
 
+# tracker tests of the reference whose trackers have a host statement (the others -- ECG,
+# LocalActivationTime, Period, PeriodAnimation, SpiralWaveCore -- are device kernels only)
+_HOST_TRACKER_TESTS = ("(activation_time or action_potential or multi_variable or animation) "
+                       "and not local and not period")
+_ALL = ["test_basics.py", "test_models_2d.py", "test_models_3d.py", "test_trackers_2d.py",
+        "test_trackers_3d.py"]
+
+
 @pytest.mark.skipif(not REF_TESTS.exists(), reason="reference tree not present (build container only)")
 def test_reference_own_tests_pass_unmodified(tmp_path):
     full = os.environ.get("FWB_FULL_REFERENCE_SUITE") == "1"
-    if full:
-        p = _run_reference_tests(tmp_path, ["test_basics.py", "test_models_2d.py", "test_models_3d.py"])
-        want = 18
-    else:
-        p = _run_reference_tests(tmp_path, ["test_basics.py", "test_models_2d.py",
-                                            "test_models_3d.py"],
-                                 "state_loading or commands or aliev_panfilov or barkley")
-        want = 6
+    models = "aliev_panfilov or barkley or mitchell or fenton or bueno or luo_rudy or tp06 or " \
+             "courtemanche" if full else "aliev_panfilov or barkley"
+    p = _run_reference_tests(tmp_path, _ALL,
+                             f"state_loading or commands or {models} or ({_HOST_TRACKER_TESTS})")
+    want = 27 if full else 15
     tail = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-500:]
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
     assert f"{want} passed" in tail, tail
