@@ -90,12 +90,23 @@ class _BuiltinStencil(Stencil):
         return diffusion_kernel
 
 
+# The three public helpers below exist in the reference as building blocks of its host-side
+# weight computation.  Here the weights are computed by the device kernel (csrc/weights.cu,
+# which evaluates the same expressions per node); the helpers are kept as plain numpy
+# utilities for user code that calls them, and are not used by this package.
 class IsotropicStencil2D(_BuiltinStencil):
     """5-point: slots (i-1,j) (i,j-1) (i,j) (i,j+1) (i+1,j)."""
     _KIND, _DIM = _lib.STENCIL_ISO, 2
 
+    def compute_half_step_diffusion(self, mesh, conductivity, num_axes=None):
+        """Conductivity at i + 1/2 along every axis, shape ``(num_axes, *mesh.shape)``
+        (isotropic_stencil_2d.py:71-95, isotropic_stencil_3d.py)."""
+        num_axes = self._DIM if num_axes is None else num_axes
+        c = conductivity * np.ones(np.shape(mesh))
+        return np.stack([0.5 * (c + np.roll(c, -1, axis=a)) for a in range(num_axes)])
 
-class IsotropicStencil3D(_BuiltinStencil):
+
+class IsotropicStencil3D(IsotropicStencil2D):
     """7-point: slots (i-1) (j-1) (k-1) centre (k+1) (j+1) (i+1)."""
     _KIND, _DIM = _lib.STENCIL_ISO, 3
 
@@ -108,6 +119,24 @@ class AsymmetricStencil2D(_BuiltinStencil):
         self.D_al = 1
         self.D_ac = 1 / 9
 
+    def compute_diffusion_components(self, fibers, ind0, ind1, D_al, D_ac):
+        """``D_ac * delta + (D_al - D_ac) f_ind0 f_ind1`` per node
+        (asymmetric_stencil_2d.py:138-161)."""
+        fibers = np.asarray(fibers)
+        return D_ac * (ind0 == ind1) + (D_al - D_ac) * fibers[..., ind0] * fibers[..., ind1]
+
+    def compute_half_step_diffusion(self, mesh, conductivity, fibers, axis, num_axes=None):
+        """Row ``axis`` of the diffusion tensor times the conductivity, averaged onto the
+        interface at i + 1/2 along ``axis``: shape ``(num_axes, *mesh.shape)``
+        (asymmetric_stencil_2d.py:97-136)."""
+        num_axes = self._DIM if num_axes is None else num_axes
+        c = conductivity * np.ones(np.shape(mesh))
+        out = []
+        for b in range(num_axes):
+            d = self.compute_diffusion_components(fibers, axis, b, self.D_al, self.D_ac)
+            out.append(0.5 * (d * c + np.roll(d, -1, axis=axis) * np.roll(c, -1, axis=axis)))
+        return np.stack(out)
+
 
 class AsymmetricStencil3D(AsymmetricStencil2D):
     """19-point (faces + 12 edges), slot order of asymmetric_stencil_3d.py:26-44."""
@@ -119,3 +148,15 @@ class SymmetricStencil2D(AsymmetricStencil2D):
     slot order and apply kernel as AsymmetricStencil2D, only the weights differ.  Never
     auto-selected: assign ``model.stencil = SymmetricStencil2D()``."""
     _KIND, _DIM = _lib.STENCIL_SYM, 2
+
+    def compute_half_step_diffusion(self, mesh, conductivity, fibers, D_al, D_ac):
+        """The four tensor components times the conductivity, averaged onto the cell centre
+        (i + 1/2, j + 1/2): shape ``(4, *mesh.shape)`` in the order xx, xy, yx, yy
+        (symmetric_stencil_2d.py:69-118)."""
+        c = conductivity * np.ones(np.shape(mesh))
+        out = []
+        for k in range(4):
+            d = self.compute_diffusion_components(fibers, k // 2, k % 2, D_al, D_ac) * c
+            right = np.roll(d, -1, axis=1)
+            out.append(0.25 * (d + np.roll(d, -1, axis=0) + right + np.roll(right, -1, axis=0)))
+        return np.stack(out)

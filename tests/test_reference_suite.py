@@ -92,3 +92,22 @@ def test_reference_own_tests_pass_unmodified(tmp_path):
     tail = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-500:]
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
     assert f"{want} passed" in tail, tail
+
+
+def test_public_stencil_helpers():
+    """`compute_diffusion_components` / `compute_half_step_diffusion` (public building blocks of
+    the reference's host-side weights; numpy utilities here, compared bit for bit with the
+    live reference when they were written): analytic values on uniform inputs."""
+    import numpy as np
+    st = fw.AsymmetricStencil2D()
+    f = np.zeros((4, 5, 2))
+    f[..., 0], f[..., 1] = 0.6, 0.8
+    assert np.allclose(st.compute_diffusion_components(f, 0, 0, 1.0, 0.2), 0.2 + 0.8 * 0.36)
+    assert np.allclose(st.compute_diffusion_components(f, 0, 1, 1.0, 0.2), 0.8 * 0.48)
+    st.D_al, st.D_ac = 1.0, 0.2
+    half = st.compute_half_step_diffusion(np.ones((4, 5)), 2.0, f, 1)
+    assert half.shape == (2, 4, 5) and np.allclose(half[1], 2.0 * (0.2 + 0.8 * 0.64))
+    iso = fw.IsotropicStencil3D().compute_half_step_diffusion(np.ones((3, 4, 5)), np.arange(60.).reshape(3, 4, 5))
+    assert iso.shape == (3, 3, 4, 5) and iso[2, 0, 0, 0] == 0.5 and iso[0, 0, 0, 0] == 10.0
+    sym = fw.SymmetricStencil2D().compute_half_step_diffusion(np.ones((4, 5)), 1.0, f, 1.0, 0.2)
+    assert sym.shape == (4, 4, 5) and np.allclose(sym[1], sym[2]) and np.allclose(sym[3], 0.2 + 0.8 * 0.64)
