@@ -1,0 +1,91 @@
+"""
+GPU tests that have NOT run on a B200 yet -- deliberately not collected by `pytest tests/`
+(the file name has no `test_` prefix).  They take the one-call fixtures that were added from
+the live reference on the CPU side at the end of round 1 (tests/golden/make_weights_golden.py,
+make_stim_golden.py, make_tracker_golden.py) through the CUDA kernels.  First thing to do with
+a GPU:
+
+    python -m pytest tests/pending_gpu_fixtures.py -q
+
+and, once green, rename the file to tests/test_gpu_fixtures.py.
+"""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _weight_cases():
+    from tests.golden.make_weights_golden import weight_cases
+    return weight_cases()
+
+
+@pytest.mark.parametrize("name", ["iso2d", "aniso2d", "sym2d", "iso3d", "aniso3d"])
+def test_device_weights_match_reference_on_wide_inputs(name):
+    """fwb_compute_weights with a conductivity array + fibres and non-default D_al / D_ac."""
+    from finitewave_b200.engine import Engine
+    from oracle import oracle
+    c = next(x for x in _weight_cases() if x["name"] == name)
+    want = np.load(GOLDEN / f"weights_{name}.npz")["weights"]
+    mesh = oracle.apply_boundaries(c["mesh"].copy())
+    eng = Engine(mesh.shape)
+    eng.set_tissue(mesh)
+    kind = {"iso": 0, "aniso": 1, "sym": 2}[c["kind"]]
+    eng.compute_weights(kind, c["conductivity"], c["fibers"], c["D_al"], c["D_ac"], c["D_model"],
+                        c["dt"], c["dr"])
+    got = eng.weights_dense()
+    assert np.array_equal(got[mesh == 1], want[mesh == 1])
+    assert np.array_equal(got, want)
+
+
+def _stim_specs():
+    from tests.golden.make_stim_golden import stim_specs
+    return stim_specs()
+
+
+@pytest.mark.parametrize("spec", _stim_specs(), ids=[s[0] for s in _stim_specs()])
+def test_device_stimuli_match_reference_one_call(spec):
+    """The native (device) face of every stimulus class: after ONE step the buffer that was
+    `u` during the step holds the stimulated field (the stimulus edits `u` in place before the
+    diffusion reads it)."""
+    import finitewave_b200 as fw
+    from tests.golden.make_stim_golden import DT, apply, fields
+    key, dim, cls, args, kwargs, calls = spec
+    mesh, u0 = fields(dim)
+    want = apply(fw, (key, dim, cls, args, kwargs, 1))       # host statement, one call;
+    if calls == 1:                                           # == the live reference's fixture
+        assert np.array_equal(want, np.load(GOLDEN / "stim_onecall.npz")[key])
+    tissue = (fw.CardiacTissue2D if dim == 2 else fw.CardiacTissue3D)(list(mesh.shape))
+    tissue.mesh = mesh.copy()
+    model = (fw.AlievPanfilov2D if dim == 2 else fw.AlievPanfilov3D)()
+    model.dt, model.dr, model.t_max, model.prog_bar = DT, 0.25, 0.5 * DT, False
+    model.cardiac_tissue = tissue
+    seq = fw.StimSequence()
+    seq.add_stim(getattr(fw, cls)(*args, **kwargs))
+    model.stim_sequence = seq
+    model.initialize()
+    model.u[...] = u0
+    model.run(initialize=False)
+    assert model.step == 1
+    assert np.array_equal(model.u_new, want)                 # the pre-swap `u`, post-stimulus
+
+
+def test_device_tip_scan_matches_reference_on_random_fields():
+    """fwb_tip_scan on the smooth random field pairs (53 tips) of tracker_onecall.npz."""
+    import torch
+    import finitewave_b200 as fw
+    from finitewave_b200.engine import Engine
+    from tests.golden.make_tracker_golden import tip_inputs
+    g = np.load(GOLDEN / "tracker_onecall.npz")
+    for k in range(4):
+        a, b, thr = tip_inputs(k)
+        eng = Engine(a.shape)
+        tr = fw.SpiralWaveCore2DTracker()
+        tr.threshold = thr
+        tr.initialize(types.SimpleNamespace(u=a))
+        rows = tr._scan(eng, torch.from_numpy(np.ascontiguousarray(b)).to(eng.device))
+        assert np.array_equal(rows[:, :2], g[f"tips{k}"]), k
