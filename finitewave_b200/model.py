@@ -148,6 +148,27 @@ class CardiacModel:
             w = DeviceWeights(eng)
         self.weights = w
 
+    def _rebuild_device_side(self):
+        """run(initialize=False) on a model without a device side -- a clone()
+        (``copy.deepcopy`` keeps the host arrays and drops the engine): tissue index structures
+        again, and the weights the model carries (a clone holds them as the reference's
+        ``(*shape, K)`` ndarray) packed back onto the device, so the run continues exactly
+        where the copied arrays stand."""
+        tissue = self.cardiac_tissue
+        if tissue is None or not isinstance(self.__dict__.get("u"), np.ndarray):
+            raise RuntimeError("run(initialize=False) needs an initialised model")
+        w = self.weights
+        if isinstance(w, np.ndarray) and w.shape[:-1] == tuple(tissue.mesh.shape):
+            tissue.compute_myo_indexes()
+            if self.stencil is None:
+                self.stencil = self.select_stencil(tissue)
+            eng = self._engine_for(tissue)
+            eng.set_tissue(tissue.mesh, tissue.special_boundaries)
+            eng.set_weights_dense(w)
+            self.weights = DeviceWeights(eng)
+        else:
+            self.compute_weights()
+
     def select_stencil(self, cardiac_tissue):
         iso, aniso = ((IsotropicStencil2D, AsymmetricStencil2D) if self._DIM == 2
                       else (IsotropicStencil3D, AsymmetricStencil3D))
@@ -267,6 +288,8 @@ class CardiacModel:
             self.state_loader.load()
 
         iters = int(np.ceil((self.t_max - self.t) / self.dt))
+        if self._engine is None:
+            self._rebuild_device_side()
         eng = self._engine
 
         stims = self.stim_sequence.sequence if self.stim_sequence else []

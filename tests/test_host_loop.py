@@ -305,3 +305,30 @@ def test_native_stimulus_descriptors_select_the_reference_nodes(spec):
             if st.u_max is not None:
                 uf[flat] = np.minimum(uf[flat], st.u_max)
     assert np.array_equal(u, want)
+
+
+def test_clone_continues_like_the_original():
+    """``model.clone()`` is a deep copy without the device side (reference
+    cardiac_model.py clone = deepcopy); ``run(initialize=False)`` on the clone rebuilds it from
+    the copied host state -- arrays, weights, stimulus / tracker status -- and continues bit
+    for bit like the original."""
+    case = dict(case_by_name("fk2d_iso_current"), t_max=0.75, trackers=[
+        dict(kind="action_potential", cell_ind=[3, 16], step=5)])
+    model, trackers = build_model(fw, case)
+    host_faces_only(model)
+    model.run()                                   # stops in the middle of the current pulse
+    twin = model.clone()
+    assert twin._engine is None and isinstance(twin.weights, np.ndarray)
+    assert np.array_equal(twin.weights, np.asarray(model.weights))
+    for m in (model, twin):
+        m.t_max = 2.0
+        m.run(initialize=False)
+    assert twin.step == model.step == 200
+    for name in ("u", "v", "w"):
+        assert np.array_equal(getattr(twin, name), getattr(model, name)), name
+    a = model.tracker_sequence.sequence[0].output
+    b = twin.tracker_sequence.sequence[0].output
+    assert len(a) == 40 and np.array_equal(a, b)
+    # and the uninterrupted run agrees with both
+    whole, _ = _run(dict(case, t_max=2.0))
+    assert np.array_equal(whole.u, model.u)
