@@ -1,0 +1,144 @@
+"""
+Usage-scenario fixtures from the LIVE reference (build container only): what the reference
+does when a model is used in the less obvious ways its API allows -- a Command that shortens
+or lengthens ``t_max`` mid-run, parameters / ``dt`` / arrays edited between ``run()`` and
+``run(initialize=False)``, a tracker window, a second full ``run()``, a Command that edits
+the mesh and recomputes the weights.
+
+    python tests/golden/make_scenario_golden.py
+
+Writes tests/golden/scenarios.npz (u, v, the action-potential trace, step and t per
+scenario).  The scenario functions take the package as argument and are shared with the
+tests: tests/test_host_loop.py runs them on the CPU test double, tests/pending_gpu_fixtures.py
+on the device.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent.parent))
+
+
+def _base(fw, t_max=2.0):
+    tissue = fw.CardiacTissue2D([24, 14])
+    m = fw.AlievPanfilov2D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, t_max, False
+    m.cardiac_tissue = tissue
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, 1, 0, 4, 0, 14))
+    stims.add_stim(fw.StimCurrentCoord2D(0.8, 5, 0.4, 10, 14, 0, 14))
+    m.stim_sequence = stims
+    ap = fw.ActionPotential2DTracker()
+    ap.cell_ind, ap.step = [12, 7], 2
+    seq = fw.TrackerSequence()
+    seq.add_tracker(ap)
+    m.tracker_sequence = seq
+    return m, ap
+
+
+def command_shortens_t_max(fw):
+    m, ap = _base(fw)
+
+    class Stop(fw.Command):
+        def execute(self, model):
+            model.t_max = 0.6
+    cs = fw.CommandSequence()
+    cs.add_command(Stop(0.5))
+    m.command_sequence = cs
+    m.run()
+    return m, ap
+
+
+def command_lengthens_t_max(fw):
+    m, ap = _base(fw, 1.0)
+
+    class More(fw.Command):
+        def execute(self, model):
+            model.t_max = 3.0          # the iteration count was fixed at loop entry
+    cs = fw.CommandSequence()
+    cs.add_command(More(0.5))
+    m.command_sequence = cs
+    m.run()
+    return m, ap
+
+
+def parameters_changed_between_runs(fw):
+    m, ap = _base(fw, 1.0)
+    m.run()
+    m.a, m.k, m.t_max = 0.15, 7.0, 2.0
+    m.run(initialize=False)
+    return m, ap
+
+
+def dt_changed_between_runs(fw):
+    m, ap = _base(fw, 1.0)
+    m.run()
+    m.dt, m.t_max = 0.005, 1.5         # the weights keep the old dt (no recompute)
+    m.run(initialize=False)
+    return m, ap
+
+
+def tracker_window(fw):
+    m, ap = _base(fw, 2.0)
+    ap.start_time, ap.end_time = 0.5, 1.25
+    m.run()
+    return m, ap
+
+
+def second_full_run(fw):
+    m, ap = _base(fw, 1.0)
+    m.run()
+    m.run()                            # re-initialises the arrays; the trace keeps growing
+    return m, ap
+
+
+def arrays_edited_between_runs(fw):
+    m, ap = _base(fw, 1.0)
+    m.run()
+    m.u[5:9, 3:6] = 0.9
+    m.v[...] *= 0.5
+    m.t_max = 1.5
+    m.run(initialize=False)
+    return m, ap
+
+
+def command_edits_mesh(fw):
+    m, ap = _base(fw, 1.5)
+
+    class Scar(fw.Command):
+        def execute(self, model):
+            model.cardiac_tissue.mesh[8:12, 2:12] = 2
+            model.compute_weights()
+    cs = fw.CommandSequence()
+    cs.add_command(Scar(0.7))
+    m.command_sequence = cs
+    m.run()
+    return m, ap
+
+
+SCENARIOS = [command_shortens_t_max, command_lengthens_t_max, parameters_changed_between_runs,
+             dt_changed_between_runs, tracker_window, second_full_run,
+             arrays_edited_between_runs, command_edits_mesh]
+
+
+def outputs(m, ap):
+    return dict(u=np.array(m.u), v=np.array(m.v), ap=np.array(ap.output, dtype=np.float64),
+                step=np.int64(m.step), t=np.float64(m.t))
+
+
+def main():
+    from make_golden import import_reference
+    fw = import_reference()
+    out = {}
+    for f in SCENARIOS:
+        m, ap = f(fw)
+        for k, v in outputs(m, ap).items():
+            out[f"{f.__name__}.{k}"] = v
+        print(f"{f.__name__:34s} step={m.step} samples={len(ap.output)} u.sum={m.u.sum():.12g}")
+    np.savez_compressed(HERE / "scenarios.npz", **out)
+
+
+if __name__ == "__main__":
+    main()

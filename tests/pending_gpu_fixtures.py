@@ -89,3 +89,21 @@ def test_device_tip_scan_matches_reference_on_random_fields():
         tr.initialize(types.SimpleNamespace(u=a))
         rows = tr._scan(eng, torch.from_numpy(np.ascontiguousarray(b)).to(eng.device))
         assert np.array_equal(rows[:, :2], g[f"tips{k}"]), k
+
+
+def _scenarios():
+    from tests.golden.make_scenario_golden import SCENARIOS
+    return SCENARIOS
+
+
+@pytest.mark.parametrize("scenario", _scenarios(), ids=[f.__name__ for f in _scenarios()])
+def test_usage_scenarios_on_the_device(scenario):
+    """tests/golden/scenarios.npz through the real engine (Aliev-Panfilov: bit-exact)."""
+    import finitewave_b200 as fw
+    from tests.golden.make_scenario_golden import outputs
+    g = np.load(GOLDEN / "scenarios.npz")
+    m, ap = scenario(fw)
+    for k, v in outputs(m, ap).items():
+        want = g[f"{scenario.__name__}.{k}"]
+        assert np.shape(v) == want.shape, k
+        assert np.array_equal(v, want), k

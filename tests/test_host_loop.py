@@ -332,3 +332,29 @@ def test_clone_continues_like_the_original():
     # and the uninterrupted run agrees with both
     whole, _ = _run(dict(case, t_max=2.0))
     assert np.array_equal(whole.u, model.u)
+
+
+def _scenarios():
+    from tests.golden.make_scenario_golden import SCENARIOS
+    return SCENARIOS
+
+
+@pytest.mark.parametrize("scenario", _scenarios(), ids=[f.__name__ for f in _scenarios()])
+def test_usage_scenarios_match_reference(scenario, monkeypatch):
+    """The less obvious ways of using a model -- Commands that move ``t_max``, parameters /
+    ``dt`` / arrays edited between ``run()`` and ``run(initialize=False)``, tracker windows, a
+    second full run, a Command that edits the mesh and recomputes the weights -- give what the
+    live reference gives (tests/golden/make_scenario_golden.py), bit for bit."""
+    from finitewave_b200 import stimulation, tracker
+    from tests.golden.make_scenario_golden import outputs
+    for mod in (stimulation, tracker):                  # built-ins on their host statements
+        for name in dir(mod):
+            cls = getattr(mod, name)
+            if isinstance(cls, type) and cls.__dict__.get("_native", False):
+                monkeypatch.setattr(cls, "_native", False)
+    g = np.load(GOLDEN / "scenarios.npz")
+    m, ap = scenario(fw)
+    for k, v in outputs(m, ap).items():
+        want = g[f"{scenario.__name__}.{k}"]
+        assert np.shape(v) == want.shape, k
+        assert np.array_equal(v, want), k
