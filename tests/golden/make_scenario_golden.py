@@ -2,8 +2,10 @@
 Usage-scenario fixtures from the LIVE reference (build container only): what the reference
 does when a model is used in the less obvious ways its API allows -- a Command that shortens
 or lengthens ``t_max`` mid-run, parameters / ``dt`` / arrays edited between ``run()`` and
-``run(initialize=False)``, a tracker window, a second full ``run()``, a Command that edits
-the mesh and recomputes the weights.
+``run(initialize=False)``, a tracker window, a second full ``run()``, Commands that edit the
+mesh or the conductivity and recompute the weights, a clone that continues, stimuli / trackers
+added or removed between runs, a user-defined Stencil, two models on one tissue, a StateSaver
+that fires before the run is continued.
 
     python tests/golden/make_scenario_golden.py
 
@@ -118,9 +120,99 @@ def command_edits_mesh(fw):
     return m, ap
 
 
+def clone_continues(fw):
+    m, _ = _base(fw, 0.9)
+    m.run()
+    twin = m.clone()
+    twin.t_max = 1.6
+    twin.run(initialize=False)
+    return twin, twin.tracker_sequence.sequence[0]
+
+
+def stimulus_added_between_runs(fw):
+    m, ap = _base(fw, 1.0)
+    m.run()
+    m.stim_sequence.add_stim(fw.StimVoltageCoord2D(1.2, 1, 18, 22, 0, 14))
+    m.t_max = 1.6
+    m.run(initialize=False)
+    return m, ap
+
+
+def stimuli_and_trackers_removed_between_runs(fw):
+    m, ap = _base(fw, 0.9)
+    m.run()
+    m.stim_sequence.remove_stim()
+    m.tracker_sequence.remove_trackers()
+    m.t_max = 1.5
+    m.run(initialize=False)
+    return m, ap
+
+
+def command_changes_conductivity(fw):
+    """examples/basics/2D/change_conductivity_2d.py"""
+    m, ap = _base(fw, 1.5)
+
+    class Slow(fw.Command):
+        def execute(self, model):
+            c = np.ones(model.cardiac_tissue.mesh.shape)
+            c[:, 7:] = 0.3
+            model.cardiac_tissue.conductivity = c
+            model.compute_weights()
+    cs = fw.CommandSequence()
+    cs.add_command(Slow(0.4))
+    m.command_sequence = cs
+    m.run()
+    return m, ap
+
+
+def user_defined_stencil(fw):
+    m, ap = _base(fw, 1.0)
+
+    class Leaky(fw.IsotropicStencil2D):
+        def compute_weights(self, model, tissue):
+            w = np.array(super().compute_weights(model, tissue)).copy()
+            w[..., 2] -= 0.01
+            return w
+    m.stencil = Leaky()
+    m.run()
+    return m, ap
+
+
+def two_models_on_one_tissue(fw):
+    m, ap = _base(fw, 0.8)
+    m.run()
+    other = fw.Barkley2D()
+    other.dt, other.dr, other.t_max, other.prog_bar = 0.01, 0.25, 0.5, False
+    other.cardiac_tissue = m.cardiac_tissue
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, 1, 0, 4, 0, 14))
+    other.stim_sequence = stims
+    other.run()
+    m.t_max = 1.2
+    m.run(initialize=False)
+    m.v = m.v + other.v                # both models end up in the compared arrays
+    return m, ap
+
+
+def saver_fires_then_run_continues(fw):
+    import os
+    import tempfile
+    d = tempfile.mkdtemp()
+    m, ap = _base(fw, 1.0)
+    m.state_saver = fw.StateSaver(os.path.join(d, "s"), time=0.5)
+    m.run()
+    m.t_max = 1.5
+    m.run(initialize=False)
+    m.v = m.v + np.load(os.path.join(d, "s", "u.npy"))
+    return m, ap
+
+
 SCENARIOS = [command_shortens_t_max, command_lengthens_t_max, parameters_changed_between_runs,
              dt_changed_between_runs, tracker_window, second_full_run,
-             arrays_edited_between_runs, command_edits_mesh]
+             arrays_edited_between_runs, command_edits_mesh, clone_continues,
+             stimulus_added_between_runs, stimuli_and_trackers_removed_between_runs,
+             command_changes_conductivity, user_defined_stencil, two_models_on_one_tissue,
+             saver_fires_then_run_continues]
 
 
 def outputs(m, ap):

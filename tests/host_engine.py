@@ -116,6 +116,20 @@ class OracleEngine:
             flat[...] = fill
         flat[self.indexes] = self.dense_state[slot].reshape(-1)[self.indexes]
 
+    def snapshot_async(self, fills):
+        """Same contract as Engine.snapshot_async: (host arrays [u, state...], an event whose
+        synchronize() says they are valid, keep-alive list)."""
+        arrays = [self.ubuf[self.sim.cur].copy()]
+        for slot in range(self.n_state):
+            a = np.full(self.shape, float(fills[slot]))
+            self.download_state(slot, a, fills[slot])
+            arrays.append(a)
+
+        class _Done:
+            def synchronize(self):
+                pass
+        return arrays, _Done(), list(arrays)
+
     # ---- simulation object ---------------------------------------------------
     def create_sim(self, model_id, params, dt, use_tma=True):
         from finitewave_b200 import _lib
