@@ -207,12 +207,112 @@ def saver_fires_then_run_continues(fw):
     return m, ap
 
 
+def _with_trace(fw, m, cell, dim=2):
+    ap = (fw.ActionPotential2DTracker if dim == 2 else fw.ActionPotential3DTracker)()
+    ap.cell_ind = cell
+    seq = fw.TrackerSequence()
+    seq.add_tracker(ap)
+    m.tracker_sequence = seq
+    return ap
+
+
+def special_boundaries_and_area_stimulus_3d(fw):
+    tissue = fw.CardiacTissue3D([10, 9, 8])
+    sb = np.zeros((10, 9, 8), dtype=np.int8)
+    sb[4:6, 3:5, 2:6] = 1
+    tissue.special_boundaries = sb
+    m = fw.MitchellSchaeffer3D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, 1.0, False
+    m.cardiac_tissue = tissue
+    st = fw.StimCurrentArea3D(0.1, 6, 0.3, u_max=0.8)
+    st.add_stim_point([3, 3, 3], tissue.mesh, size=2.5)
+    stims = fw.StimSequence()
+    stims.add_stim(st)
+    m.stim_sequence = stims
+    ap = _with_trace(fw, m, [[3, 3, 3], [5, 4, 4]], dim=3)
+    m.run()
+    m.v = m.h
+    return m, ap
+
+
+def luo_rudy_with_edited_parameters(fw):
+    m = fw.LuoRudy912D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, 2.0, False
+    m.cardiac_tissue = fw.CardiacTissue2D([12, 8])
+    m.gna, m.init_u, m.init_m, m.D_model = 20.0, -80.0, 0.01, 0.2
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimCurrentCoord2D(0, 40, 1.0, 0, 4, 0, 8))
+    m.stim_sequence = stims
+    ap = _with_trace(fw, m, [6, 4])
+    m.run()
+    m.v = m.m
+    return m, ap
+
+
+def odd_inputs(fw):
+    """Float, non-contiguous mesh; fibres that are not unit vectors; scalar conductivity;
+    t_max that is no multiple of dt; a stimulus in the past, one never reached, and a current
+    stimulus of zero duration."""
+    grid = np.ones((9, 14))
+    grid[3:5, 2:7] = 2.0
+    tissue = fw.CardiacTissue2D([14, 9])
+    tissue.mesh = grid.T
+    rng = np.random.default_rng(5)
+    f = rng.normal(size=(14, 9, 2))
+    tissue.fibers = 1.3 * f / np.linalg.norm(f, axis=-1, keepdims=True)
+    tissue.conductivity = 0.5
+    m = fw.FentonKarma2D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, 0.333, False
+    m.cardiac_tissue = tissue
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(-1.0, 1, 0, 3, 0, 9))
+    stims.add_stim(fw.StimVoltageCoord2D(5.0, 1, 0, 3, 0, 9))
+    stims.add_stim(fw.StimCurrentCoord2D(0.1, 3.0, 0.0, 8, 12, 0, 9))
+    m.stim_sequence = stims
+    ap = _with_trace(fw, m, [7, 4])
+    m.run()
+    return m, ap
+
+
+def stimulus_on_fibrotic_nodes_only(fw):
+    tissue = fw.CardiacTissue2D([12, 10])
+    tissue.mesh[2:5, :] = 2
+    m = fw.Barkley2D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, 0.5, False
+    m.cardiac_tissue = tissue
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, 1, 2, 5, 0, 10))
+    m.stim_sequence = stims
+    ap = _with_trace(fw, m, [3, 3])
+    m.run()
+    return m, ap
+
+
+def tp06_with_edited_parameters(fw):
+    m = fw.TP062D()
+    m.dt, m.dr, m.t_max, m.prog_bar = 0.01, 0.25, 1.0, False
+    m.cardiac_tissue = fw.CardiacTissue2D([10, 6])
+    m.gkr, m.gks, m.init_cai, m.ko = 0.1, 0.5, 0.0001, 4.0
+    stims = fw.StimSequence()
+    stims.add_stim(fw.StimVoltageCoord2D(0, -20, 0, 3, 0, 6))
+    m.stim_sequence = stims
+    ap = _with_trace(fw, m, [5, 3])
+    m.run()
+    m.v = m.cai + m.Ki
+    return m, ap
+
+
 SCENARIOS = [command_shortens_t_max, command_lengthens_t_max, parameters_changed_between_runs,
              dt_changed_between_runs, tracker_window, second_full_run,
              arrays_edited_between_runs, command_edits_mesh, clone_continues,
              stimulus_added_between_runs, stimuli_and_trackers_removed_between_runs,
              command_changes_conductivity, user_defined_stencil, two_models_on_one_tissue,
-             saver_fires_then_run_continues]
+             saver_fires_then_run_continues, special_boundaries_and_area_stimulus_3d,
+             luo_rudy_with_edited_parameters, odd_inputs, stimulus_on_fibrotic_nodes_only,
+             tp06_with_edited_parameters]
+# bit-exact on the device as well (no transcendental functions in the model)
+DEVICE_EXACT = {f.__name__ for f in SCENARIOS} - {
+    "luo_rudy_with_edited_parameters", "odd_inputs", "tp06_with_edited_parameters"}
 
 
 def outputs(m, ap):

@@ -98,12 +98,17 @@ def _scenarios():
 
 @pytest.mark.parametrize("scenario", _scenarios(), ids=[f.__name__ for f in _scenarios()])
 def test_usage_scenarios_on_the_device(scenario):
-    """tests/golden/scenarios.npz through the real engine (Aliev-Panfilov: bit-exact)."""
+    """tests/golden/scenarios.npz through the real engine: bit-exact for the models without
+    transcendental functions, 1e-9 relative (north-star bar) for FK / LR91 / TP06."""
     import finitewave_b200 as fw
-    from tests.golden.make_scenario_golden import outputs
+    from tests.cases import max_rel_err
+    from tests.golden.make_scenario_golden import DEVICE_EXACT, outputs
     g = np.load(GOLDEN / "scenarios.npz")
     m, ap = scenario(fw)
     for k, v in outputs(m, ap).items():
         want = g[f"{scenario.__name__}.{k}"]
         assert np.shape(v) == want.shape, k
-        assert np.array_equal(v, want), k
+        if scenario.__name__ in DEVICE_EXACT or k in ("step", "t"):
+            assert np.array_equal(v, want), k
+        else:
+            assert max_rel_err(v, want) <= 1e-9, k
