@@ -384,6 +384,23 @@ class LocalActivationTime2DTracker(Tracker):
         eng = self.model._engine
         self._track_device(eng, eng.ubuf[eng.current()], self.model.t)
 
+    def cross_threshold(self):
+        """Public in the reference (local_activation_time_2d_tracker.py:71-90): the boolean
+        array of the nodes of ``model.u`` that cross the threshold upwards now; arms / disarms
+        the per-node ``activated`` state.  Called by hand it stages the host ``model.u`` on the
+        device and runs fwb_lat_cross -- the same kernel the sampled steps use."""
+        eng = self.model._engine
+        d = self._ensure_dev(eng)
+        u = torch.from_numpy(np.ascontiguousarray(self.model.u, dtype=np.float64)).to(eng.device)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(eng.L.fwb_lat_cross(ctypes.c_void_p(u.data_ptr()), eng.n_nodes,
+                                  float(self.threshold),
+                                  ctypes.c_void_p(d["activated"].data_ptr()),
+                                  ctypes.c_void_p(d["cross"].data_ptr()), None, None, st),
+              "fwb_lat_cross")
+        d["dirty"] = True
+        return d["cross"].cpu().numpy().reshape(self.model.u.shape).astype(bool)
+
     def _collect(self, engine=None):
         d = self._dev
         if d is None or not d["dirty"]:
@@ -523,6 +540,35 @@ class SpiralWaveCore2DTracker(Tracker):
         rows = rows[np.argsort(rows[:, 2], kind="stable")]      # the reference's scan order
         d["u_prev"].copy_(u)
         return rows
+
+    def track_tip_line(self, u, u_new, threshold):
+        """Public in the reference (spiral_wave_core_2d_tracker.py:60-80): the tips between two
+        2D potential fields as a list of ``[x, y]`` in the reference's scan order.  Stages the
+        two host arrays on the device and runs fwb_tip_scan, the kernel the sampled steps use."""
+        from ._lib import lib, shape_arr
+        from .engine import require_cuda
+        require_cuda()
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        a = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(dev)
+        b = torch.from_numpy(np.ascontiguousarray(u_new, dtype=np.float64)).to(dev)
+        if a.dim() != 2 or a.shape != b.shape:
+            raise ValueError("track_tip_line takes two 2D arrays of the same shape")
+        L, st = lib(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        capacity = 4096
+        while True:
+            out = torch.zeros((capacity, 3), dtype=torch.float64, device=dev)
+            count = torch.zeros(1, dtype=torch.int32, device=dev)
+            check(L.fwb_tip_scan(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), 2,
+                                 shape_arr(a.shape), float(threshold),
+                                 ctypes.c_void_p(out.data_ptr()), capacity,
+                                 ctypes.c_void_p(count.data_ptr()), st), "fwb_tip_scan")
+            n = int(count.item())
+            if n <= capacity:
+                break
+            capacity = 2 * n
+        rows = out[:n].cpu().numpy()
+        rows = rows[np.argsort(rows[:, 2], kind="stable")]
+        return [[float(x), float(y)] for x, y in rows[:, :2]]
 
     def _frames(self, rows, t, step):
         import pandas as pd

@@ -11,8 +11,8 @@ tracker and stimulus defaults).
 2026-10-17: 75 classes; constructor parameters equal except a trailing optional ``seed`` on
 the four fibrosis patterns (device draws are seeded hashes) and ``shape`` on the abstract
 CardiacTissue base; default values equal on all 65 constructible classes; public methods
-missing here: ECG*Tracker.calc_ecg, LocalActivationTime* / Period* .cross_threshold,
-SpiralWaveCore*Tracker.track_tip_line (device computations).
+missing here: ECG*Tracker.calc_ecg (the ECG reduction exists only fused into the step
+kernel).
 """
 import inspect
 import sys

@@ -112,3 +112,37 @@ def test_usage_scenarios_on_the_device(scenario):
             assert np.array_equal(v, want), k
         else:
             assert max_rel_err(v, want) <= 1e-9, k
+
+
+def test_public_track_tip_line_and_cross_threshold():
+    """The two hand-callable device methods added without a GPU: SpiralWaveCore2DTracker.
+    track_tip_line(u, u_new, threshold) against the live-reference tips, and
+    LocalActivationTime2DTracker.cross_threshold() against the reference's statement
+    (local_activation_time_2d_tracker.py:71-90) over a sequence of fields."""
+    import finitewave_b200 as fw
+    from tests.golden.make_tracker_golden import tip_inputs
+    g = np.load(GOLDEN / "tracker_onecall.npz")
+    tr = fw.SpiralWaveCore2DTracker()
+    for k in range(4):
+        a, b, thr = tip_inputs(k)
+        tips = np.array(tr.track_tip_line(a, b, thr), dtype=np.float64).reshape(-1, 2)
+        assert np.array_equal(tips, g[f"tips{k}"]), k
+
+    tissue = fw.CardiacTissue2D([20, 16])
+    model = fw.AlievPanfilov2D()
+    model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 0.01, False
+    model.cardiac_tissue = tissue
+    lat = fw.LocalActivationTime2DTracker()
+    lat.threshold = 0.4
+    seq = fw.TrackerSequence()
+    seq.add_tracker(lat)
+    model.tracker_sequence = seq
+    model.initialize()
+    rng = np.random.default_rng(9)
+    activated = np.zeros((20, 16), dtype=bool)
+    for _ in range(6):
+        model.u[...] = rng.random((20, 16))
+        want = (model.u >= 0.4) & ~activated
+        activated = np.where(want, True, activated)
+        activated = np.where((model.u < 0.4) & activated, False, activated)
+        assert np.array_equal(lat.cross_threshold(), want)
