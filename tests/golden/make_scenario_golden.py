@@ -11,7 +11,7 @@ that fires before the run is continued.
 
 Writes tests/golden/scenarios.npz (u, v, the action-potential trace, step and t per
 scenario).  The scenario functions take the package as argument and are shared with the
-tests: tests/test_host_loop.py runs them on the CPU test double, tests/pending_gpu_fixtures.py
+tests: tests/test_host_loop.py runs them on the CPU test double, tests/test_gpu_fixtures.py
 on the device.
 """
 import sys

@@ -1,13 +1,11 @@
 """
-GPU tests that have NOT run on a B200 yet -- deliberately not collected by `pytest tests/`
-(the file name has no `test_` prefix).  They take the one-call fixtures that were added from
-the live reference on the CPU side at the end of round 1 (tests/golden/make_weights_golden.py,
-make_stim_golden.py, make_tracker_golden.py) through the CUDA kernels.  First thing to do with
-a GPU:
-
-    python -m pytest tests/pending_gpu_fixtures.py -q
-
-and, once green, rename the file to tests/test_gpu_fixtures.py.
+The one-call fixtures taken from the live reference on the CPU side (tests/golden/
+make_weights_golden.py, make_stim_golden.py, make_tracker_golden.py, make_scenario_golden.py)
+through the CUDA kernels: fwb_compute_weights with conductivity arrays + fibres and
+non-default D_al / D_ac, the device face of every stimulus class, fwb_tip_scan on smooth
+random fields, the twenty usage scenarios through the real engine, and the hand-callable
+track_tip_line() / cross_threshold().  First run on a B200: 40 passed
+(profiles/r1_final_fixture_tests.log).
 """
 import types
 from pathlib import Path
@@ -115,7 +113,7 @@ def test_usage_scenarios_on_the_device(scenario):
 
 
 def test_public_track_tip_line_and_cross_threshold():
-    """The two hand-callable device methods added without a GPU: SpiralWaveCore2DTracker.
+    """The two hand-callable device methods: SpiralWaveCore2DTracker.
     track_tip_line(u, u_new, threshold) against the live-reference tips, and
     LocalActivationTime2DTracker.cross_threshold() against the reference's statement
     (local_activation_time_2d_tracker.py:71-90) over a sequence of fields."""
