@@ -12,7 +12,7 @@ tracker and stimulus defaults).
 the four fibrosis patterns (device draws are seeded hashes) and ``shape`` on the abstract
 CardiacTissue base; default values equal on all 65 constructible classes; public methods
 missing here: ECG*Tracker.calc_ecg (the ECG reduction exists only fused into the step
-kernel, DESIGN.md section 8 item 5).
+kernel, DESIGN.md section 8 item 6).
 """
 import inspect
 import sys
