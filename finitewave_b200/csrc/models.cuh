@@ -210,8 +210,31 @@ template <> struct Model<FWB_MODEL_FENTON_KARMA> {
                divc_ok(c.two_tau_si) && divc_ok(c.tau_v_m) && divc_ok(c.tau_v_p) &&
                divc_ok(c.tau_w_m) && divc_ok(c.tau_w_p);
     }
+    // 1 + tanh(x) as 2 g / (1 + g), g = exp(2x): CUDA's tanh switches algorithm at
+    // |x| = 0.55, and on an excited sheet k (u - uc_si) straddles that value inside most
+    // warps of the plateau -- both paths get executed (C2: 0.905 -> 0.85 of HBM once half of
+    // the tissue is excited).  This form costs the same on every lane (table-driven fexp +
+    // frcp3, fexp.cuh) and is accurate to a few ulp RELATIVE for any x, where 1 + tanh(x)
+    // cancels for x << 0.  |x| >= 300 and NaN take the library statement.
+    FWB_HD static double one_plus_tanh_fast(double x)
+    {
+        if (fabs(x) < 300.0) {
+            const double g = fexp_fast(2.0 * x);
+            return (2.0 * g) * frcp3(1.0 + g);
+        }
+        return 1 + tanh(x);
+    }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
+    {
+#ifdef __CUDA_ARCH__
+        ionic_t<IO, true>(u, un, io, c);
+#else
+        ionic_t<IO, false>(u, un, io, c);     // the reference statement (host check)
+#endif
+    }
+    template <class IO, bool FAST>
+    FWB_HD static void ionic_t(double u, double &un, IO &io, const Consts &c)
     {
         const double H1 = (c.u_c - u >= 0) ? 1.0 : 0.0;
         const double H2 = (u - c.u_c >= 0) ? 1.0 : 0.0;
@@ -222,7 +245,9 @@ template <> struct Model<FWB_MODEL_FENTON_KARMA> {
         io.st(1, w);
         const double J_fi = divc(-(v * H2 * (1 - u) * (u - c.u_c)), c.tau_d);
         const double J_so = divc(u * H1, c.tau_o) + divc(H2, c.tau_r);
-        const double J_si = divc(-v * (1 + tanh(c.k * (u - c.uc_si))), c.two_tau_si);
+        const double x = c.k * (u - c.uc_si);
+        const double th1 = FAST ? one_plus_tanh_fast(x) : 1 + tanh(x);
+        const double J_si = divc(-v * th1, c.two_tau_si);
         un += c.dt * (-J_fi - J_so - J_si);
     }
 };

@@ -135,3 +135,33 @@ int fwb_host_court_fast(double *u_new, const double *u, double *const *st, int64
     }
     return 0;
 }
+
+// host build of Fenton-Karma's device path (Model<FK>::ionic_t<IO, true>: branch-free
+// 1 + tanh) and of the helper itself
+extern "C" __attribute__((visibility("default")))
+void fwb_host_one_plus_tanh(const double *x, double *out, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = Model<FWB_MODEL_FENTON_KARMA>::one_plus_tanh_fast(x[i]);
+}
+
+extern "C" __attribute__((visibility("default")))
+int fwb_host_fk_fast(double *u_new, const double *u, double *const *st, int64_t n, double dt,
+                     const double *p)
+{
+    using M = Model<FWB_MODEL_FENTON_KARMA>;
+    M::Consts c;
+    if (!M::derive(p, dt, c)) return -1;
+    struct IO {
+        double *const *arr;
+        int64_t i;
+        double ld(int q) const { return arr[q][i]; }
+        void st(int q, double v) const { arr[q][i] = v; }
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        IO io{st, i};
+        double un = u_new[i];
+        M::ionic_t<IO, true>(u[i], un, io, c);
+        u_new[i] = un;
+    }
+    return 0;
+}

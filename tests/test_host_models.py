@@ -270,7 +270,7 @@ def test_kernel_header_matches_live_reference_one_step(hostlib, model):
     tests/golden/make_ionic_golden.py: one ``run_ionic_kernel()`` call of the numba code on
     random node states, thresholds included): the reference statement (`Model<>::ionic` as the
     host compiles it) bit for bit; the rearranged device paths of LR91 / TP06 / Courtemanche
-    (`ionic_fast`) to rounding level -- the 1e-9-after-1000-steps bar leaves 1e-12 per step."""
+    (`ionic_fast`) and Fenton-Karma (`ionic_t<IO, true>`) to rounding level -- the 1e-9-after-1000-steps bar leaves 1e-12 per step."""
     from tests.golden.make_ionic_golden import DT, SHAPE, ionic_inputs
     spec = oracle.MODELS[model]
     g = np.load(ROOT / "tests" / "golden" / f"ionic_{model}.npz")
@@ -297,7 +297,8 @@ def test_kernel_header_matches_live_reference_one_step(hostlib, model):
         assert np.array_equal(s[myo], g[var].reshape(-1)[myo]), var
 
     fast = {"tp06": hostlib.fwb_host_tp06_fast, "luo_rudy91": hostlib.fwb_host_lr91_fast,
-            "courtemanche": hostlib.fwb_host_court_fast}.get(model)
+            "courtemanche": hostlib.fwb_host_court_fast,
+            "fenton_karma": hostlib.fwb_host_fk_fast}.get(model)
     if fast is None:
         return
     un, st = run(fast)
@@ -314,3 +315,49 @@ def test_kernel_header_matches_live_reference_one_step(hostlib, model):
         r = g[var].reshape(-1)
         err = np.abs(s - r) / np.maximum(np.abs(r), 1e-3)
         assert err[myo & ~near].max() < 2e-12 and err[myo].max() < 1e-9, (var, err[myo].max())
+
+
+def test_fenton_karma_device_path_matches_reference_statement(hostlib):
+    """Model<FK>::ionic_t<IO, true> (the device's path: 1 + tanh(x) as 2 g / (1 + g) with
+    g = exp(2x), the same cost on every lane) against the exact value and against the reference
+    statement, one step from the same node states."""
+    # the helper: a few ulp RELATIVE to the exact 2 e^2x / (1 + e^2x) for any x (1 + tanh(x)
+    # itself cancels for x << 0), NaN / huge arguments through the library statement
+    x = np.concatenate([np.linspace(-340, 340, 200001), np.random.default_rng(8).normal(0, 2, 200000),
+                        [0.0, -0.55, 0.55, 299.999, -299.999, 300.0, -300.0, 1e6, -1e6]])
+    out = np.empty_like(x)
+    hostlib.fwb_host_one_plus_tanh(x.ctypes.data_as(c_double_p), out.ctypes.data_as(c_double_p),
+                                   ctypes.c_int64(len(x)))
+    xl = x.astype(np.longdouble)
+    g = np.exp(2 * np.clip(xl, -5000, 5000))
+    exact = np.where(xl > 300, np.longdouble(2.0), 2 * g / (1 + g))
+    inside = np.abs(x) < 300
+    rel = np.abs((out - exact) / np.where(exact > 0, exact, 1)).astype(np.float64)
+    assert rel[inside].max() < 1.5e-15, rel[inside].max()
+    assert np.array_equal(out[~inside], 1 + np.tanh(x[~inside]))
+    nan = np.array([np.nan])
+    hostlib.fwb_host_one_plus_tanh(nan.ctypes.data_as(c_double_p), nan.ctypes.data_as(c_double_p),
+                                   ctypes.c_int64(1))
+    assert np.isnan(nan[0])
+
+    rng = np.random.default_rng(12)
+    n = 200000
+    spec = oracle.MODELS["fenton_karma"]
+    u, st = _random_node_states("fenton_karma", n, rng)
+    u[-n // 10:] = rng.uniform(0.75, 0.95, n // 10)           # around the tanh's centre
+    pvec = np.array([float(v) for v in spec["params"].values()], dtype=np.float64)
+    diff = rng.uniform(-1, 1, n) * 0.01 + u
+    outs = []
+    for fn, extra in ((hostlib.fwb_host_ionic, (MODEL_IDS["fenton_karma"],)),
+                      (hostlib.fwb_host_fk_fast, ())):
+        un = diff.copy()
+        s2 = [s.copy() for s in st]
+        arr = (c_double_p * len(s2))(*[s.ctypes.data_as(c_double_p) for s in s2])
+        rc = fn(*extra, un.ctypes.data_as(c_double_p), u.ctypes.data_as(c_double_p), arr,
+                ctypes.c_int64(n), ctypes.c_double(0.01), pvec.ctypes.data_as(c_double_p))
+        assert rc == 0
+        outs.append((un, s2))
+    (un_r, st_r), (un_f, st_f) = outs
+    assert np.max(np.abs(un_f - un_r)) < 1e-16 * 50          # dt * J_si differs by a few ulp
+    for a, b in zip(st_f, st_r):
+        assert np.array_equal(a, b)                           # v, w do not depend on the tanh
