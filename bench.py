@@ -2,28 +2,30 @@
 """
 bench.py -- throughput of the fused per-time-step path (myocyte-node-updates/s, fp64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4|lr91]
                     [--impl b200|reference] [--no-extras]
 
-A "step" is ONE explicit time step (one fused kernel launch: diffusion stencil +
-ionic ODE + trackers) over the whole tissue.  The N=1 workload is BASELINE.json's
-configs[1] (C2: Fenton-Karma 2D 4096x4096, anisotropic 9-point stencil, 30 % random
-fibrosis); `--workload` selects another BASELINE config.  With N > 1 (torchrun, one
-rank per GPU) every rank owns a slab of an N-times larger tissue (weak scaling) and
-exchanges one halo plane per neighbour per step.
+A "step" is ONE explicit time step (one fused kernel launch: diffusion stencil + ionic ODE
++ trackers) over the whole tissue.  The default workload is the one BASELINE.json's metric
+is quoted on -- C5, the TP06 3D anisotropic (19-point) slab cut along the fibre-rotation
+axis: 128 x 1024 x 1024 nodes per GPU, i.e. 1024^3 (1.06e9 myocytes) at 8 GPUs (weak
+scaling; one rank per GPU under torchrun, every rank owns one slab and exchanges one halo
+plane per neighbour and step from inside the step kernel).  `--workload` selects another
+BASELINE config.
 
 One JSON line on stdout (rank 0):
   value      device-resident whole-job node-updates/s (CUDA events, max over ranks)
-  e2e        the same metric through the public host API (model.run() on numpy
-             arrays in pinned host memory): every timed call uploads u, u_new and
-             all state arrays, runs `steps_per_call` time steps (1000, the run length
-             of the reference's README quick start), downloads them again
-  roofline   fused step kernel vs the measured HBM copy bandwidth
-             (MEASURED_PEAKS.json), algorithmic bytes per node from SURVEY.md 8d
-  cpu_baseline  the CPU oracle port (oracle/, OpenMP, all host threads) timed on a
-             bounded sample of the same workload (N=1, rank 0 only)
-`--impl reference` times that CPU port alone (the reference is Python + numba and
-cannot be built or shipped to the GPU box).
+  e2e        the same metric through the public host API -- `TP063D.run()` on numpy arrays
+             in pinned host memory: every timed call uploads u, u_new and all state arrays,
+             runs `steps_per_call` time steps and downloads them again
+  roofline   fused step kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json),
+             algorithmic bytes per node from SURVEY.md 8d
+  cpu_baseline  the REFERENCE's own numba path (oracle/_ref copy made by oracle/make_ref.py,
+             `CardiacModel.run(initialize=False)`, all host threads) on a bounded sample of the
+             same workload; the C/OpenMP oracle port's rate rides along as `port_value`
+  other_workloads  C1 (launch-bound: steps/s), C2, C3, C4, C5 with the activation tracker, LR91
+`--impl reference` prints the reference arm's line: the numba reference timed alone (the
+oracle port only if the copy of the reference is missing, and then it says so).
 """
 import argparse
 import json
@@ -41,6 +43,30 @@ import numpy as np  # noqa: E402
 
 METRIC = "myocyte-node-updates/sec (fp64, device-timed); % of HBM roofline"
 UNIT = "node-updates/s"
+
+# name -> (label, shape per GPU, stencil points, algorithmic bytes per node-update)
+WORKLOADS = {
+    "c5": ("C5 TP06 3D 1024x1024 x 128-per-GPU aniso 19-pt slab, cut along the fibre-rotation "
+           "axis (1024^3 at 8 GPUs), face stimulus", [128, 1024, 1024], 19, 457),
+    "c2": ("C2 Fenton-Karma 2D 4096x4096 aniso 9-pt, 30% random fibrosis", [4096, 4096], 9, 121),
+    "c3": ("C3 Mitchell-Schaeffer 3D 512^3 iso 7-pt, focal stimulus, activation-time tracker "
+           "every step", [512, 512, 512], 7, 97),
+    "c4": ("C4 TP06 3D ventricle-shaped shell in 512^3, helix fibres, 19-pt", [512, 512, 512],
+           19, 457),
+    "lr91": ("LR91 2D 4096x4096 iso 5-pt, planar wave (extra, not a BASELINE config)",
+             [4096, 4096], 5, 169),
+    "c5t": ("C5 with an ActivationTime3DTracker sampling every step (TP06 + tracker)",
+            [128, 1024, 1024], 19, 465),
+}
+
+
+def workload_config(name, world):
+    """The `config` object: identical in the b200 arm and the reference arm."""
+    label, shape, K, B = WORKLOADS[name]
+    return {"workload": label, "shape_per_gpu": shape, "stencil_points": K,
+            "bytes_per_node_update": B,
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} slabs along axis 0, 1-plane halo exchange per step"}
 
 
 # ---------------------------------------------------------------------------
@@ -118,19 +144,15 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU side: the oracle port on a bounded sample of the workload
+# CPU side: the reference's numba path (and the oracle port) on a bounded sample
 # ---------------------------------------------------------------------------
-def cpu_case(workload):
-    """Reduced-shape twin of a workload for the CPU legs."""
-    from oracle.bench_cases import cases_for_bench
-    return cases_for_bench(workload)
-
-
-def cpu_time(workload, budget_s, steps=None, warmup=3):
+def port_time(workload, budget_s, steps=None, warmup=3):
+    """The C/OpenMP oracle port (oracle/fw_oracle.c) on its bounded sample."""
     from oracle import oracle
+    from oracle.bench_cases import cases_for_bench
     oracle.build()
     threads = os.cpu_count() or 1
-    case, sample = cpu_case(workload)
+    case, sample = cases_for_bench("c5" if workload == "c5t" else workload)
     if steps is None:
         sec, n_myo = oracle.time_steps(case, 3, n_threads=threads, warmup=1)
         per = sec / 3
@@ -140,34 +162,65 @@ def cpu_time(workload, budget_s, steps=None, warmup=3):
                 sample=f"{sample}, {steps} steps in {sec:.1f} s (oracle/fw_oracle.c, OpenMP)"), sec, steps
 
 
+def reference_time(workload, steps, warmup):
+    """The reference itself (numba) on its bounded sample -> cpu_baseline dict, sec, steps."""
+    from oracle import ref_numba
+    r = ref_numba.time_reference("c5" if workload == "c5t" else workload, steps, warmup=warmup)
+    return dict(value=r["n_myo"] * r["steps"] / r["seconds"], unit=UNIT, cores=r["threads"],
+                kind="reference", sample=r["sample"],
+                init_seconds=r["init_seconds"]), r["seconds"], r["steps"]
+
+
+def cpu_baseline(workload, budget_s):
+    """cpu_baseline object of the b200 arm's line: numba reference, port as a second field."""
+    out = None
+    try:
+        # a first short run sizes the sample to ~budget_s of CPU work
+        cb, sec, steps = reference_time(workload, 3, 2)
+        per = sec / max(1, steps)
+        more = int(min(1000, budget_s / max(per, 1e-6)))
+        if more > 2 * steps:
+            cb, sec, steps = reference_time(workload, more, 1)
+        out = cb
+    except Exception as e:
+        out = {"error": "numba reference unavailable: " + repr(e)}
+    try:
+        pb, _, _ = port_time(workload, min(budget_s, 8.0))
+        if "value" in out:
+            out["port_value"], out["port_sample"] = pb["value"], pb["sample"]
+        else:
+            pb["note"] = out["error"]
+            out = pb
+    except Exception as e:
+        out["port_error"] = repr(e)
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the numba
-    reference cannot travel) on the host cores, K timed steps of a bounded sample."""
+    """--impl reference: the reference's own numba CPU implementation of the path on the host
+    cores (oracle/_ref; falls back to the oracle port if that copy is missing), W warm-up and
+    K timed steps of a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb, sec, steps = cpu_time(args.workload, 0, steps=args.steps, warmup=args.warmup)
+    try:
+        cb, sec, steps = reference_time(args.workload, args.steps, args.warmup)
+    except Exception as e:
+        cb, sec, steps = port_time(args.workload, 0, steps=args.steps, warmup=args.warmup)
+        cb["note"] = "numba reference unavailable (" + repr(e) + "): oracle port timed instead"
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * sec / max(1, steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "sample": cb["sample"]},
+        "config": workload_config(args.workload, max(1, args.gpus)),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
-
-
-WORKLOAD_NAMES = {
-    "c2": "C2 Fenton-Karma 2D 4096x4096 aniso 9-pt, 30% random fibrosis",
-    "c3": "C3 Mitchell-Schaeffer 3D 512^3 iso 7-pt, focal stimulus, activation-time tracker",
-    "c4": "C4 TP06 3D ventricle-shaped shell in 512^3, helix fibres, 19-pt",
-    "c5": "C5 TP06 3D 1024x1024x128-per-GPU aniso 19-pt slab",
-}
 
 
 # ---------------------------------------------------------------------------
@@ -194,31 +247,63 @@ def time_device(sim, steps, warmup, dist=None, propagate=0):
     return ms, sim.launch_count() - l0
 
 
+def host_model(workload, scale=1.0):
+    """The workload through the PUBLIC host API (numpy tissue, model classes)."""
+    import finitewave_b200 as fw
+
+    def r32(x, lo=32):
+        return max(lo, int(round(x * scale)) // 32 * 32)
+    if workload == "c2":
+        n = r32(4096, 64)
+        rng = np.random.default_rng(2)
+        tissue = fw.CardiacTissue2D([n, n])
+        mesh = np.ones((n, n), dtype=np.int8)
+        mesh[rng.random((n, n)) <= 0.30] = 2
+        tissue.mesh = mesh
+        f = np.empty((n, n, 2))
+        f[..., 0], f[..., 1] = np.cos(0.25 * np.pi), np.sin(0.25 * np.pi)
+        tissue.fibers = f
+        model = fw.FentonKarma2D()
+        seq = fw.StimSequence()
+        seq.add_stim(fw.StimVoltageCoord2D(0, 1, 0, n, 0, 5))
+    elif workload in ("c5", "c5t"):
+        s, n = r32(128), r32(1024)
+        tissue = fw.CardiacTissue3D([s, n, n])
+        phi = np.linspace(-np.pi / 3, np.pi / 2, s - 2)
+        f = np.zeros((s, n, n, 3))
+        f[1:-1, :, :, 1] = np.cos(phi)[:, None, None]
+        f[1:-1, :, :, 2] = np.sin(phi)[:, None, None]
+        tissue.fibers = f
+        model = fw.TP063D()
+        seq = fw.StimSequence()
+        seq.add_stim(fw.StimVoltageCoord3D(0, -20, 0, s, 0, 5, 0, n))
+        if workload == "c5t":
+            tr = fw.ActivationTime3DTracker()
+            tr.threshold, tr.step = -40, 1
+            ts = fw.TrackerSequence()
+            ts.add_tracker(tr)
+            model.tracker_sequence = ts
+    else:
+        return None
+    model.dt, model.dr, model.prog_bar = 0.01, 0.25, False
+    model.cardiac_tissue = tissue
+    model.stim_sequence = seq
+    return model
+
+
 def e2e_host_api(workload, steps_per_call, calls, scale=1.0):
     """Public API with host buffers: CardiacModel.run() on numpy (pinned) arrays."""
     import torch
-    import finitewave_b200 as fw
-    if workload != "c2":
+    model = host_model(workload, scale)
+    if model is None:
         return None
-    n = max(64, int(round(4096 * scale)) // 32 * 32)
-    rng = np.random.default_rng(2)
-    tissue = fw.CardiacTissue2D([n, n])
-    mesh = np.ones((n, n), dtype=np.int8)
-    mesh[rng.random((n, n)) <= 0.30] = 2
-    tissue.mesh = mesh
-    f = np.empty((n, n, 2))
-    f[..., 0], f[..., 1] = np.cos(0.25 * np.pi), np.sin(0.25 * np.pi)
-    tissue.fibers = f
-    model = fw.FentonKarma2D()
-    model.dt, model.dr, model.prog_bar = 0.01, 0.25, False
-    model.cardiac_tissue = tissue
-    seq = fw.StimSequence()
-    seq.add_stim(fw.StimVoltageCoord2D(0, 1, 0, n, 0, 5))
-    model.stim_sequence = seq
+    t_init = time.perf_counter()
     model.t_max = 0.2
     model.run()                                   # initialise + warm up (20 steps)
+    init_s = time.perf_counter() - t_init
     n_myo = model._engine.n_myo
-    per_call = 4 * n * n * 8                      # u, u_new, v, w each way
+    n_arrays = 2 + len(model._STATE)              # u, u_new, every state array, each way
+    per_call = n_arrays * int(np.prod(model.cardiac_tissue.mesh.shape)) * 8
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     launches = 0
@@ -228,12 +313,13 @@ def e2e_host_api(workload, steps_per_call, calls, scale=1.0):
         launches += model.gpu_launches
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
+    name = type(model).__name__
     return {"value": n_myo * steps_per_call * calls / sec, "unit": UNIT,
             "h2d_bytes_per_step": per_call, "d2h_bytes_per_step": per_call,
-            "steps_per_call": steps_per_call, "calls": calls,
-            "api": "finitewave_b200.FentonKarma2D.run(initialize=False) on pinned numpy arrays; "
-                   "one e2e step = one run() call of steps_per_call time steps",
-            "launches": launches}
+            "steps_per_call": steps_per_call, "calls": calls, "seconds": sec,
+            "api": f"finitewave_b200.{name}.run(initialize=False) on pinned numpy arrays; one "
+                   "e2e step = one run() call of steps_per_call time steps (bytes are per call)",
+            "launches": launches, "initialize_seconds": init_s}
 
 
 def e2e_slabs(sim, info, steps_per_call, calls, dist, device):
@@ -260,6 +346,57 @@ def e2e_slabs(sim, info, steps_per_call, calls, dist, device):
             "steps_per_call": steps_per_call, "calls": calls,
             "api": "finitewave_b200.devrun.DeviceSimulation upload_host -> run -> download_host "
                    "per rank (bytes are per rank and call); one e2e step = one call"}
+
+
+def c1_line(device):
+    """C1 (README quick start, AP 2D 100x100, 1000 steps): launch-latency-bound, 0.7 MB of
+    state -- a roofline fraction is meaningless at this size, so it is reported as steps/s:
+    device time of 1000 steps (CUDA events) and the wall time of the user's `model.run()`."""
+    import torch
+    import finitewave_b200 as fw
+
+    def make():
+        tissue = fw.CardiacTissue2D([100, 100])
+        model = fw.AlievPanfilov2D()
+        model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 10, False
+        seq = fw.StimSequence()
+        seq.add_stim(fw.StimVoltageCoord2D(0, 1, 1, 99, 1, 3))
+        tr = fw.ActivationTime2DTracker()
+        tr.threshold, tr.step = 0.5, 100
+        ts = fw.TrackerSequence()
+        ts.add_tracker(tr)
+        model.cardiac_tissue, model.stim_sequence, model.tracker_sequence = tissue, seq, ts
+        return model
+    model = make()
+    model.run()                                     # warm-up (allocations, graph capture)
+    n_myo = model._engine.n_myo
+    best_wall, best_dev = 1e9, 1e9
+    for _ in range(5):
+        model = make()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.run()                                 # initialize + 1000 steps + download
+        best_wall = min(best_wall, time.perf_counter() - t0)
+        # device time of 1000 more steps alone
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng = model._engine
+        eng.set_time(model.t, model.step)
+        e0.record()
+        eng.run(1000)
+        e1.record()
+        torch.cuda.synchronize()
+        best_dev = min(best_dev, e0.elapsed_time(e1) * 1e-3)
+    return {"workload": "C1 Aliev-Panfilov 2D 100x100 iso 5-pt, planar wave, activation tracker "
+                        "every 100 steps, 1000 steps (README quick start)",
+            "steps": 1000, "myocyte_nodes": n_myo,
+            "device_ms_per_1000_steps": best_dev * 1e3, "steps_per_s": 1000 / best_dev,
+            "value": n_myo * 1000 / best_dev, "unit": UNIT,
+            "e2e": {"value": n_myo * 1000 / best_wall, "unit": UNIT,
+                    "seconds_per_run": best_wall,
+                    "api": "finitewave_b200.AlievPanfilov2D.run() -- initialize(), upload, "
+                           "1000 steps, download; best of 5"},
+            "note": "launch-latency-bound: 9604 nodes, 0.7 MB; no roofline fraction at this size",
+            "gpu_launches": int(model.gpu_launches)}
 
 
 def run_b200(args):
@@ -298,19 +435,19 @@ def run_b200(args):
     value = n_total * args.steps / (ms_max * 1e-3)
     kernel_ms = ms / args.steps
     achieved = info["bytes_per_node"] * info["n_myo"] / (kernel_ms * 1e-3) / 1e9
+    big = info["bytes_per_node"] * info["n_myo"] > 4 * 126e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": info["workload"], "shape_per_gpu": info["shape"],
-                   "myocyte_nodes_per_gpu": info["n_myo"], "stencil_points": info["K"],
-                   "bytes_per_node_update": info["bytes_per_node"],
-                   "l2_policy": "working set per step >> 126 MB L2 (no flush needed)"
-                   if info["bytes_per_node"] * info["n_myo"] > 4 * 126e6 else
-                   "working set fits L2; number is L2-resident",
-                   "state": f"after {args.propagate} propagation steps + {args.warmup} warm-up steps "
-                            "from the stimulus at t = 0",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} slabs, 1-plane halo exchange"},
+        "config": workload_config(args.workload, world),
+        "workload_detail": {
+            "built": info["workload"], "shape_per_gpu": info["shape"],
+            "myocyte_nodes_per_gpu": info["n_myo"], "myocyte_nodes_total": int(n_total),
+            "l2_policy": "working set per step >> 126 MB L2 (no flush needed)" if big else
+            "working set fits L2; number is L2-resident",
+            "state": f"after {args.propagate} propagation steps + {args.warmup} warm-up steps "
+                     "from the stimulus at t = 0", "scale": args.scale},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -331,23 +468,30 @@ def run_b200(args):
     torch.cuda.empty_cache()
 
     if rank == 0 and world == 1:
+        import gc
         try:
             line["e2e"] = None if args.no_e2e else e2e_host_api(args.workload, args.e2e_steps, 2,
                                                                 scale=args.scale)
         except Exception as e:                               # never lose the device number
             line["e2e"] = {"error": repr(e)}
         if line.get("e2e") is None:
-            line["e2e"] = {"value": None, "unit": UNIT, "note": "host-API e2e is measured on C2"}
+            line["e2e"] = {"value": None, "unit": UNIT,
+                           "note": "host-API e2e is measured for c5 and c2"}
+        gc.collect()
         torch.cuda.empty_cache()
         if not args.no_extras:
             extras = []
-            for w in ("c3", "c4", "c5", "lr91"):
+            try:
+                extras.append(c1_line(device))
+            except Exception as e:
+                extras.append({"workload": "c1", "error": repr(e)})
+            for w in ("c5t", "c2", "c3", "c4", "c5", "lr91"):
                 if w == args.workload:
                     continue
                 try:
                     s2, i2 = workloads.build(w, device, scale=args.scale)
-                    ms2, l2 = time_device(s2, max(10, args.steps // 8), 5, None, args.propagate)
-                    k = max(10, args.steps // 8)
+                    k = max(10, args.steps // 2)
+                    ms2, l2 = time_device(s2, k, 5, None, args.propagate)
                     ach = i2["bytes_per_node"] * i2["n_myo"] * k / (ms2 * 1e-3) / 1e9
                     extras.append({"workload": i2["workload"], "value": i2["n_myo"] * k / (ms2 * 1e-3),
                                    "unit": UNIT, "ms_per_step": ms2 / k, "steps": k,
@@ -357,12 +501,12 @@ def run_b200(args):
                     del s2
                 except Exception as e:
                     extras.append({"workload": w, "error": repr(e)})
+                gc.collect()
                 torch.cuda.empty_cache()
             line["other_workloads"] = extras
         if not args.no_cpu:
             try:
-                cb, _, _ = cpu_time(args.workload, args.cpu_budget)
-                line["cpu_baseline"] = cb
+                line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_budget)
             except Exception as e:
                 line["cpu_baseline"] = {"error": repr(e)}
     line["wall_s"] = time.perf_counter() - t_wall0
@@ -375,13 +519,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOAD_NAMES))
+    ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every axis (debugging)")
-    ap.add_argument("--e2e-steps", type=int, default=1000,
-                    help="time steps per model.run() call of the e2e leg (README quick start: 1000)")
+    ap.add_argument("--e2e-steps", type=int, default=500,
+                    help="time steps per model.run() call of the e2e leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--propagate", type=int, default=500,
                     help="untimed time steps before the warm-up (SURVEY 8d: >= 500)")

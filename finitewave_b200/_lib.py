@@ -9,8 +9,13 @@ from ctypes import (POINTER, c_char_p, c_double, c_int, c_int64, c_uint8, c_uint
                     c_void_p)
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libfinitewave_b200.so"
+# FWB_LIB selects another build of the same library (A/B measurements of kernel variants,
+# scripts/gpu_variants.sh); there is still no fallback if it is missing
+LIB_PATH = Path(os.environ["FWB_LIB"]).resolve() if os.environ.get("FWB_LIB") \
+    else _PKG / "libfinitewave_b200.so"
 _lib = None
 
 MODEL_IDS = {"aliev_panfilov": 0, "barkley": 1, "mitchell_schaeffer": 2, "fenton_karma": 3,
@@ -67,6 +72,9 @@ def _sig(L):
                                          c_double, p, c_int64, POINTER(c_double), c_int64]
     L.fwb_sim_stim_passed.argtypes = [p, c_int]
     L.fwb_sim_set_stim_passed.argtypes = [p, c_int, c_int]
+    L.fwb_sim_stim_fired.argtypes = [p, c_int]
+    L.fwb_sim_stim_fired.restype = c_int64
+    L.fwb_sim_set_stim_fired.argtypes = [p, c_int, c_int64]
     L.fwb_sim_clear_trackers.argtypes = [p]
     L.fwb_sim_add_tracker_act.argtypes = [p, p, c_double, c_double, c_double, c_int64]
     L.fwb_sim_add_tracker_ecg.argtypes = [p, p, c_int, c_double, c_double, c_double,

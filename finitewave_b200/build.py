@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 BUILD = PKG / "_build"
 LIB = PKG / "libfinitewave_b200.so"
 
-SOURCES = ["sim.cu", "aux_kernels.cu", "weights.cu", "halo.cu", "step_nomodel.cu", "step_ap.cu",
+SOURCES = ["sim.cu", "aux_kernels.cu", "weights.cu", "step_nomodel.cu", "step_ap.cu",
            "step_barkley.cu", "step_ms.cu", "step_fk.cu", "step_bo.cu", "step_lr91.cu", "step_tp06.cu", "step_court.cu"]
 
 NVCC_FLAGS = [
@@ -82,6 +82,37 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(suffix, flags, sources=("step_tp06.cu",)):
+    """A second library for A/B measurements: `sources` recompiled with extra `flags`,
+    every other object shared with the default build -> libfinitewave_b200_<suffix>.so
+    (select it with FWB_LIB=<path>)."""
+    build()
+    objs = []
+    for src in SOURCES:
+        if src in sources:
+            obj = BUILD / src.replace(".cu", f"_{suffix}.o")
+            cmd = [nvcc(), *NVCC_FLAGS, *flags, "-c", str(CSRC / src), "-o", str(obj)]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src} [{suffix}]:\n{p.stdout}\n{p.stderr}")
+            (BUILD / f"{src}.{suffix}.ptxas.log").write_text(p.stderr)
+        else:
+            obj = BUILD / src.replace(".cu", ".o")
+        objs.append(str(obj))
+    lib = PKG / f"libfinitewave_b200_{suffix}.so"
+    cmd = [nvcc(), "-shared", "-o", str(lib), *objs,
+           "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+           "-Xlinker", "--no-undefined"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(lib)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2].split()))
+    else:
+        lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+        print(lib)

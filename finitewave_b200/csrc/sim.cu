@@ -366,6 +366,18 @@ extern "C" int fwb_sim_set_stim_passed(FwbSim *s, int id, int passed)
     return 0;
 }
 
+extern "C" int64_t fwb_sim_stim_fired(const FwbSim *s, int id)
+{
+    if (!s || id < 0 || id >= (int)s->stims.size()) return FWB_E_ARG;
+    return s->stims[id].fired;
+}
+extern "C" int fwb_sim_set_stim_fired(FwbSim *s, int id, int64_t fired)
+{
+    if (!s || id < 0 || id >= (int)s->stims.size() || fired < 0) return FWB_E_ARG;
+    s->stims[id].fired = fired;
+    return 0;
+}
+
 extern "C" int fwb_sim_clear_trackers(FwbSim *s)
 {
     if (!s) return FWB_E_ARG;

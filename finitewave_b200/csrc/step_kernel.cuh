@@ -288,6 +288,10 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
     double *const staged_w = reinterpret_cast<double *>(dyn_smem);              // [K][TMA_SEG] (mode 2)
     double *const staged = staged_w + (STAGED == 2 ? K * TMA_SEG : 0);          // [NSR][TMA_SEG]
     __shared__ uint64_t staged_full[2];                                         // state, weights
+#ifdef FWB_EXP_SMEM
+    exp_table_to_smem();
+    if (!STAGED) __syncthreads();          // STAGED: the barrier after mbar_init below
+#endif
     if (STAGED) {
         if (threadIdx.x == 0) {
             mbar_init(&staged_full[0], 1);
@@ -511,6 +515,7 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)NSTAGE * STAGE_D);
 
     const int64_t n_tiles = g.n_work / WARPS_PER_BLOCK;
+    exp_table_to_smem();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1);

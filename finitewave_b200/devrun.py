@@ -23,7 +23,6 @@ import torch
 
 from . import _lib
 from .engine import Engine
-from .stencil import AsymmetricStencil2D
 
 
 class _Shim:
@@ -61,12 +60,20 @@ class DeviceSimulation:
         eng.set_tissue(mesh, halo=self.halo)
         if stencil is None:
             stencil = model.stencil
-        aniso = fibers is not None if stencil is None else isinstance(stencil, AsymmetricStencil2D)
+        # the stencil's own kind (a SymmetricStencil2D is an AsymmetricStencil2D subclass
+        # with different weights); without a stencil object: by the presence of fibres
+        if stencil is None:
+            kind = _lib.STENCIL_ISO if fibers is None else _lib.STENCIL_ANISO
+        else:
+            kind = getattr(stencil, "_KIND", None)
+            if kind is None:
+                raise ValueError("DeviceSimulation takes the built-in Stencil classes only")
+        aniso = kind != _lib.STENCIL_ISO
         if aniso and fibers is None:
             raise ValueError("Fibers must be provided for anisotropic diffusion.")
         D_al = getattr(stencil, "D_al", 1) if stencil is not None else 1
         D_ac = getattr(stencil, "D_ac", 1 / 9) if stencil is not None else 1 / 9
-        eng.compute_weights(_lib.STENCIL_ANISO if aniso else _lib.STENCIL_ISO, conductivity,
+        eng.compute_weights(kind, conductivity,
                             fibers if aniso else None, D_al, D_ac, model.D_model, self.dt, self.dr)
         eng.allocate(len(self.state_names), staging=False, peer=any(self.halo))
         eng.ubuf[0].fill_(float(model.init_u))

@@ -126,7 +126,7 @@ class Engine:
             sb = special_boundaries
             sb = sb.to(dev) if isinstance(sb, torch.Tensor) else torch.from_numpy(
                 np.ascontiguousarray(sb)).to(dev)
-            update = tissue & (sb == 0)
+            update = update & (sb == 0)     # ghost slices stay excluded
         self.tissue = tissue.to(torch.uint8).contiguous()
         self.update = update.to(torch.uint8).contiguous()
         self.chunk_bits = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)

@@ -198,8 +198,6 @@ class CardiacModel:
             eng.allocate(len(self._STATE))
         if not eng.sim:
             eng.create_sim(_lib.MODEL_IDS[self._MODEL], self._param_vector(), self.dt)
-            if getattr(self, "_live", None):
-                self._register_native()
         else:
             p = self._param_vector()
             arr = (ctypes.c_double * len(p))(*p)
@@ -214,6 +212,21 @@ class CardiacModel:
         # state rows only exist for updated nodes; where the host arrays hold something
         # else than init_* on the other nodes, downloads must preserve it
         self._keep_offnodes = [c != 0 for c in eng.off_fill()]
+
+    def _partition(self):
+        """Who handles what, from the sequences as they are NOW (the reference re-reads them
+        every step, so a Command may add, remove, re-arm or replace stimuli and trackers):
+        built-in stimuli / trackers run on the device, the rest are host hooks."""
+        stims = list(self.stim_sequence.sequence) if self.stim_sequence else []
+        native_stims = bool(self.stim_sequence) and self.stim_sequence.all_native()
+        trackers = list(self.tracker_sequence.sequence) if self.tracker_sequence else []
+        native_tr = [tr for tr in trackers if getattr(tr, "_native", False)]
+        dev_tr = [tr for tr in trackers if getattr(tr, "_device_hook", False)]
+        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)
+                   and not getattr(tr, "_device_hook", False)]
+        commands = self.command_sequence.sequence if self.command_sequence else []
+        self._live.update(stims=stims, native_stims=native_stims, native_tr=native_tr)
+        return stims, native_stims, native_tr, dev_tr, host_tr, commands
 
     def _register_native(self):
         """(Re-)register the built-in stimuli and trackers with the device runner."""
@@ -236,7 +249,13 @@ class CardiacModel:
             tr._collect(eng)
         if live["native_stims"]:
             for i, st in enumerate(live["stims"]):
-                st.passed = bool(eng.L.fwb_sim_stim_passed(eng.sim, i))
+                rc = eng.L.fwb_sim_stim_passed(eng.sim, i)
+                if rc < 0:
+                    raise _lib.FwbError(f"fwb_sim_stim_passed({i}) failed (rc={rc}): stimulus "
+                                        "sequence and device registration are out of step")
+                st.passed = bool(rc)
+                if hasattr(st, "_collect"):
+                    st._collect(eng, i)      # StimVoltageListMatrix3D: its own step counter
 
     def _host_array(self, name):
         a = self.__dict__[name]
@@ -292,21 +311,10 @@ class CardiacModel:
             self._rebuild_device_side()
         eng = self._engine
 
-        stims = self.stim_sequence.sequence if self.stim_sequence else []
-        native_stims = bool(self.stim_sequence) and self.stim_sequence.all_native()
-        trackers = self.tracker_sequence.sequence if self.tracker_sequence else []
-        native_tr = [tr for tr in trackers if getattr(tr, "_native", False)]
-        dev_tr = [tr for tr in trackers if getattr(tr, "_device_hook", False)]
-        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)
-                   and not getattr(tr, "_device_hook", False)]
-        commands = self.command_sequence.sequence if self.command_sequence else []
-        self._live = dict(stims=stims, native_stims=native_stims, native_tr=native_tr,
-                          iters=iters, done=0)
+        self._live = dict(iters=iters, done=0)
+        stims, native_stims, native_tr, dev_tr, host_tr, commands = self._partition()
         self._upload()
-        if eng.sim and not eng._keep and (native_tr or (native_stims and stims)):
-            self._register_native()
-        elif eng.sim:
-            self._register_native()
+        self._register_native()
         launches0 = eng.launch_count()
         eng.set_time(self.t, self.step)
 
@@ -380,8 +388,16 @@ class CardiacModel:
                 if any((not c.passed) and self.t >= c.t for c in commands):
                     if not host_view_valid:
                         self._download()
+                    # host objects first catch up with the device (samples taken so far,
+                    # which stimuli have passed), then the command runs, then everything it
+                    # may have touched -- arrays, parameters, the stimulus and tracker
+                    # sequences themselves -- goes back to the device
+                    if eng.sim:
+                        self._collect_native()
                     self.command_sequence.execute_next()
-                    self._upload()           # commands may have edited anything
+                    stims, native_stims, native_tr, dev_tr, host_tr, commands = self._partition()
+                    self._upload()
+                    self._register_native()
                     host_view_valid = True
                 if self.state_saver and self._saver_due(self.t):
                     if not self._save_async(host_view_valid):

@@ -133,6 +133,10 @@ class _NodesMixin:
             ctypes.c_void_p(t_nodes.data_ptr()), len(nodes), vals_p, n_vals)
         if rc < 0:
             check(rc, "fwb_sim_add_stim_nodes")
+        if mode == _lib.STIM_VOLTAGE_LIST:
+            # the list index lives in the stimulus object (`self.step`), as in the reference
+            check(engine.L.fwb_sim_set_stim_fired(engine.sim, rc, int(self.step)),
+                  "fwb_sim_set_stim_fired")
         return rc
 
 
@@ -255,6 +259,11 @@ class StimVoltageListMatrix3D(_MatrixMixin, StimVoltage):
 
     def _mode_value(self):
         return _lib.STIM_VOLTAGE_LIST, 0.0
+
+    def _collect(self, engine, sid):
+        fired = int(engine.L.fwb_sim_stim_fired(engine.sim, sid))
+        if fired >= 0:
+            self.step = fired
 
     def stimulate(self, model):
         model.u[self._mask(model)] = self.volt_value[self.step]

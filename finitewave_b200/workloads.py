@@ -72,19 +72,22 @@ def uniform_fibers_2d(shape, alpha, device):
     return f
 
 
-def rotating_fibers_3d(shape, device, k0=0, nk_total=None):
-    """examples/basics/3D/slab_with_fibers_3d.py:64-70; ``k0``/``nk_total`` select a
-    z-slab [k0, k0 + shape[2]) of a taller tissue."""
-    n_i, n_j, n_k = shape
-    nk_total = nk_total or n_k
-    phi = torch.linspace(-math.pi / 3, math.pi / 2, nk_total - 2, dtype=torch.float64, device=device)
-    full = torch.zeros(nk_total, 2, dtype=torch.float64, device=device)
+def rotating_fibers_3d(shape, device, s0=0, n_total=None):
+    """The rotating-fibre slab of examples/basics/3D/slab_with_fibers_3d.py:64-70 with the
+    rotation axis ("z" there) stored as axis 0 -- the slowest axis, along which slabs are cut,
+    so that a halo slice is one contiguous block: the in-plane fibre angle goes from -pi/3 to
+    pi/2 across the interior slices of the whole tissue, fibres lie in the (axis 1, axis 2)
+    plane.  ``s0`` / ``n_total`` select the slab [s0, s0 + shape[0]) of a thicker tissue."""
+    n_s, n_j, n_k = shape
+    n_total = n_total or n_s
+    phi = torch.linspace(-math.pi / 3, math.pi / 2, n_total - 2, dtype=torch.float64, device=device)
+    full = torch.zeros(n_total, 2, dtype=torch.float64, device=device)
     full[1:-1, 0] = torch.cos(phi)
     full[1:-1, 1] = torch.sin(phi)
-    sl = full[k0:k0 + n_k]
-    f = torch.zeros((n_i, n_j, n_k, 3), dtype=torch.float64, device=device)
-    f[..., 0] = sl[:, 0]
-    f[..., 1] = sl[:, 1]
+    sl = full[s0:s0 + n_s]
+    f = torch.zeros((n_s, n_j, n_k, 3), dtype=torch.float64, device=device)
+    f[..., 1] = sl[:, 0].view(-1, 1, 1)
+    f[..., 2] = sl[:, 1].view(-1, 1, 1)
     return f
 
 
@@ -141,7 +144,7 @@ def build(name, device, scale=1.0, rank=0, world=1, dist=None):
     elif name in ("c3", "c4"):
         n = r32(512)
         own, rest, dim = n, (n, n), 3
-    elif name == "c5":
+    elif name in ("c5", "c5t"):
         n = r32(1024)
         own, rest, dim = r32(128), (n, n), 3
     elif name == "lr91":
@@ -190,13 +193,21 @@ def build(name, device, scale=1.0, rank=0, world=1, dist=None):
                              "fibres, 19-pt", model="tp06", K=19)
     else:
         mesh = fibrosis_mesh(shape, 0.0, 0, device, lo, halo)
-        fib = rotating_fibers_3d(shape, device)
+        fib = rotating_fibers_3d(shape, device, lo, n_global)
         sim = DeviceSimulation(_cfg(_m.TP063D()), mesh, fibers=fib, **kw)
         del fib
-        sim.add_stim(StimVoltageCoord3D(0, -20, 0, 5, 0, n, 0, n))
-        info = dict(workload=f"C5 TP06 3D {n_global}x{n}x{n} aniso 19-pt slab "
-                             f"({own} slices per GPU; 1024^3 at 8 GPUs), rotating fibres, "
+        # a face perpendicular to the cut: the wave runs along every slab at once
+        sim.add_stim(StimVoltageCoord3D(0, -20, 0, n_global, 0, 5, 0, n))
+        info = dict(workload=f"C5 TP06 3D {n_global}x{n}x{n} aniso 19-pt slab, cut along the "
+                             f"fibre-rotation axis ({own} slices per GPU; 1024^3 at 8 GPUs), "
                              "face stimulus", model="tp06", K=19)
+        if name == "c5t":
+            # TP06 as it runs in practice: with the activation-time map sampled every step
+            tr = ActivationTime3DTracker()
+            tr.threshold, tr.step = -40, 1
+            sim.add_tracker(tr, 0)
+            info["workload"] += " + ActivationTime3DTracker every step"
+            info["tracker_bytes"] = 8
     info["shape"] = list(sim.shape)
     info["n_myo"] = int(sim.n_myo)
     info["bytes_per_node"] = BYTES_PER_NODE[(info["model"], info["K"])] + info.get("tracker_bytes", 0)

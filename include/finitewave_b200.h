@@ -293,6 +293,11 @@ FWB_API int fwb_sim_add_stim_nodes(FwbSim *sim, int mode, double t, double durat
                            const double *values, int64_t n_values);
 FWB_API int fwb_sim_stim_passed(const FwbSim *sim, int stim_id);
 FWB_API int fwb_sim_set_stim_passed(FwbSim *sim, int stim_id, int passed);
+/* FWB_STIM_VOLTAGE_LIST: index of the next list entry (the reference keeps it in the
+ * stimulus object, `self.step`, stim_voltage_list_matrix_3d.py:60-72, so it survives a
+ * re-registration, a continued run and a mid-run rebuild of the simulation). */
+FWB_API int64_t fwb_sim_stim_fired(const FwbSim *sim, int stim_id);
+FWB_API int fwb_sim_set_stim_fired(FwbSim *sim, int stim_id, int64_t fired);
 
 /* ---- native trackers ---------------------------------------------------- */
 FWB_API int fwb_sim_clear_trackers(FwbSim *sim);
