@@ -47,6 +47,9 @@ def _sig(L):
                                      POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), p]
     L.fwb_order_compact.argtypes = [p, c_int64, p, c_int64, p, p, p, POINTER(c_int64), p]
     L.fwb_sim_set_tile_base.argtypes = [p, p, p]
+    L.fwb_sim_set_tiles.argtypes = [p, p, p]
+    L.fwb_order_tiles.argtypes = [c_int, POINTER(c_int64), c_int, c_int, c_int64, c_int64, p, p, p,
+                                  c_int64, p, p, p, p]
     L.fwb_gather_compact.argtypes = [p, p, c_int64, p, p, p]
     L.fwb_scatter_compact.argtypes = [p, p, c_double, c_int64, p, p, p]
     L.fwb_scatter_compact_keep.argtypes = [p, p, c_int64, p, p, p]
@@ -86,10 +89,14 @@ def _sig(L):
     L.fwb_sim_run.argtypes = [p, c_int64]
     L.fwb_sim_launch_count.argtypes = [p]
     L.fwb_sim_launch_count.restype = c_int64
+    L.fwb_sim_device_steps.argtypes = [p]
+    L.fwb_sim_device_steps.restype = c_int64
     L.fwb_last_step_variant.restype = c_int
     L.fwb_devmath.argtypes = [c_int, p, p, c_int64, p]
     L.fwb_diffuse.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_int64, p, c_int64,
                               p, p, p, p]
+    L.fwb_ecg.argtypes = [c_int, c_int, POINTER(c_int64), p, p, c_int64, p, c_int64, p, p, p, p,
+                          c_int, c_double, p, p]
     L.fwb_dev_alloc.argtypes = [POINTER(c_void_p), c_int64]
     L.fwb_dev_free.argtypes = [p]
     L.fwb_ipc_handle_size.restype = c_int

@@ -1,5 +1,6 @@
 // aux_kernels.cu -- index structures, layout conversions, stimuli, tracker helpers.
 #include "aux_kernels.cuh"
+#define FWB_NO_EXP_SMEM   // devmath_kernel measures the helpers with the table in global memory
 #include "fexp.cuh"
 
 namespace fwb {
@@ -134,8 +135,21 @@ __global__ void worklist_mark_kernel(WlSeg sg, const uint8_t *mask, int32_t *can
         for (int l = 0; l < cnt; ++l) on |= mask[n0 + l];
         on = on ? 1u : 0u;
     }
-    cand[q] = (int32_t)chunk;
+    // TILE granularity: the 8 positions of a tile (8 consecutive q, hence 8 neighbouring
+    // lanes) are listed together as soon as one of them holds tissue; positions without
+    // tissue (or outside the grid) are listed as -1.  A block of the step kernel therefore
+    // owns exactly one spatial tile, which is what lets it fetch the tile's u brick with one
+    // tensor-TMA copy and number its nodes compactly.
+    cand[q] = on ? (int32_t)chunk : -1;
     flag[q] = on;
+}
+__global__ void worklist_tileflag_kernel(int64_t n_pos, uint32_t *flag)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t on = q < n_pos ? flag[q] : 0u;
+    const unsigned b = __ballot_sync(0xffffffffu, on != 0);
+    const unsigned lane = threadIdx.x & 31u;
+    if (q < n_pos) flag[q] = ((b >> (lane & ~7u)) & 0xffu) ? 1u : 0u;
 }
 
 __global__ void worklist_scatter_kernel(int64_t n_pos, const int32_t *cand, const uint32_t *flag,
@@ -168,6 +182,48 @@ __global__ void order_scatter_kernel(const int32_t *wl, int64_t n_work, const ui
     // what the TMA kernel needs per work-list entry: chunk id, update bits, compact
     // index of the chunk's first node, compact index of the tile's first node
     if (records) records[i] = make_uint4((uint32_t)c, tmp_bits[i], ord[i], ord[i & ~(int64_t)7]);
+}
+
+// per tile {compact base, node count, chunk id of the tile's slot 0, 0} and per node its
+// position inside the tile (slot << 5 | lane): what the compact-lane tile kernel needs to
+// map thread -> node (step_kernel_tile in step_kernel.cuh)
+struct TileGeo {
+    int dim, tiled, halo_lo, halo_hi;
+    int64_t S, R, cpl;           // slices, rows per slice (1 in 2D), chunks per line
+    int64_t n_lo_tiles, n_hi_tiles;
+};
+__device__ __forceinline__ int64_t tile_slot_offset(const TileGeo &tg, bool bnd, int w)
+{
+    // chunk-id offset of slot w from slot 0 (mirrors worklist_mark_kernel / fwb_build_worklist)
+    if (!tg.tiled) return w;
+    int ts, tr, tc;
+    if (tg.dim == 3) { if (bnd) { ts = 1; tr = 8; tc = 1; } else { ts = 2; tr = 4; tc = 1; } }
+    else { if (bnd) { ts = 1; tr = 1; tc = 8; } else { ts = 8; tr = 1; tc = 1; } }
+    (void)ts;
+    const int ws = w / (tr * tc), wr = (w / tc) % tr, wc = w % tc;
+    return (int64_t)ws * tg.R * tg.cpl + (int64_t)wr * tg.cpl + wc;
+}
+__global__ void order_tiles_kernel(TileGeo tg, const int32_t *wl, int64_t n_tiles,
+                                   const uint32_t *bits, const uint32_t *chunk_base,
+                                   const uint32_t *tile_base, uint4 *tile_rec, uint8_t *pos_of)
+{
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp per tile
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_tiles) return;
+    const bool bnd = gw < tg.n_lo_tiles + tg.n_hi_tiles;
+    int64_t origin = -1;
+    for (int w = 0; w < 8; ++w) {
+        const int32_t c = wl[gw * 8 + w];
+        if (c < 0) continue;
+        if (origin < 0) origin = (int64_t)c - tile_slot_offset(tg, bnd, w);
+        const uint32_t b = bits[c];
+        if ((b >> lane) & 1u)
+            pos_of[chunk_base[c] + __popc(b & ((1u << lane) - 1u))] = (uint8_t)((w << 5) | lane);
+    }
+    if (lane == 0) {
+        const uint32_t c0 = tile_base[gw], c1 = tile_base[gw + 1];
+        tile_rec[gw] = make_uint4(c0, c1 - c0, (uint32_t)(origin < 0 ? 0 : origin), bnd ? 1u : 0u);
+    }
 }
 
 // slab halo: hold the stream until both neighbours have finished step `epoch - 1`
@@ -484,6 +540,8 @@ extern "C" int fwb_build_worklist(int dim, const int64_t *shape, const uint8_t *
         const unsigned nb = (unsigned)cdiv(g.n_pos, 256);
         worklist_mark_kernel<<<nb, 256, 0, s>>>(g, active, cand, flag);
         FWB_KERNEL_CHECK("worklist_mark_kernel");
+        worklist_tileflag_kernel<<<nb, 256, 0, s>>>(g.n_pos, flag);
+        FWB_KERNEL_CHECK("worklist_tileflag_kernel");
         unsigned long long total = 0;
         int rc = scan_popc(flag, g.n_pos, base, &total, s);
         if (rc) return rc;
@@ -540,6 +598,34 @@ extern "C" int fwb_order_compact(const uint32_t *chunk_bits, int64_t n_chunks,
     }
     FWB_CUDA(cudaStreamSynchronize(s));
     if (n_myo) *n_myo = (int64_t)total;
+    return 0;
+}
+
+extern "C" int fwb_order_tiles(int dim, const int64_t *shape, int halo_lo, int halo_hi,
+                               int64_t n_lo_blocks, int64_t n_hi_blocks,
+                               const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                               const int32_t *worklist, int64_t n_work, const uint32_t *tile_base,
+                               uint32_t *tile_rec, uint8_t *pos_of, fwb_stream_t stream)
+{
+    if (!shape || (dim != 2 && dim != 3) || !chunk_bits || !chunk_base || !worklist || !tile_base ||
+        !tile_rec || !pos_of || n_work < 0 || n_work % 8 != 0) {
+        set_error("fwb_order_tiles: bad argument");
+        return FWB_E_ARG;
+    }
+    if (n_work == 0) return 0;
+    TileGeo tg;
+    memset(&tg, 0, sizeof(tg));
+    const int64_t line = shape[dim - 1];
+    tg.dim = dim; tg.tiled = line % 32 == 0;
+    tg.halo_lo = halo_lo; tg.halo_hi = halo_hi;
+    tg.S = shape[0]; tg.R = dim == 3 ? shape[1] : 1; tg.cpl = tg.tiled ? line / 32 : 0;
+    tg.n_lo_tiles = halo_lo ? n_lo_blocks : 0; tg.n_hi_tiles = halo_hi ? n_hi_blocks : 0;
+    const int64_t n_tiles = n_work / 8;
+    const unsigned nb = (unsigned)cdiv(n_tiles * 32, 256);
+    order_tiles_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(
+        tg, worklist, n_tiles, chunk_bits, chunk_base, tile_base,
+        reinterpret_cast<uint4 *>(tile_rec), pos_of);
+    FWB_KERNEL_CHECK("order_tiles_kernel");
     return 0;
 }
 

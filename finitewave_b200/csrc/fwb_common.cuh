@@ -17,8 +17,10 @@ constexpr int MAX_STATE = 21;
 // thread-local last error (fwb_last_error)
 void set_error(const char *fmt, ...);
 // which step kernel the last launch used (fwb_last_step_variant): 0 = one block per tile,
-// plain loads; 1 = state rows by TMA; 2 = state + weight rows by TMA; 3 = persistent TMA ring
+// plain loads; 3 = persistent TMA ring; 4 = compact-lane tile kernel, plain u loads; 5 = the
+// same with the u brick by tensor TMA
 void note_step_variant(int v);
+int last_step_launches();
 int cuda_fail(cudaError_t e, const char *what);
 
 #define FWB_CUDA(call)                                   \

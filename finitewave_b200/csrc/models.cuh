@@ -364,17 +364,32 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         var += dt * (inf - var) / tau;
         return var;
     }
+    static constexpr bool HAS_FAST = true;
+    // the rearranged path needs |u| < 300 mV and a positive, normal cai (flog); NaNs fail
+    // the comparisons and take the reference statement
+    template <class IO> FWB_HD static bool fast_ok(double u, const IO &io, const Consts &)
+    {
+        const double cai = io.ld(6);
+        return fabs(u) < FAST_MATH_U_LIMIT && cai > 1e-300 && cai < 1e300;
+    }
+    template <class IO>
+    FWB_HD static void ionic_fastpath(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_fast(u, un, io, c, io.ld(6));
+    }
+    template <class IO>
+    FWB_HD static void ionic_ref(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_impl<IO, LibMath>(u, un, io, c, io.ld(6));
+    }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        const double cai = io.ld(6);
 #ifdef __CUDA_ARCH__
-        // the rearranged path needs |u| < 300 mV and a positive, normal cai (flog); NaNs fail
-        // the comparisons and take the reference statement
-        if (fabs(u) < FAST_MATH_U_LIMIT && cai > 1e-300 && cai < 1e300) ionic_fast(u, un, io, c, cai);
+        if (fast_ok(u, io, c)) ionic_fastpath(u, un, io, c);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c, cai);
+            ionic_ref(u, un, io, c);
     }
 
     // ------------------------------------------------------------------------------------
@@ -546,7 +561,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_TP06> {
 #ifndef FWB_TP06_MIN_BLOCKS
-#define FWB_TP06_MIN_BLOCKS 4
+#define FWB_TP06_MIN_BLOCKS 3      // 80 registers: no spills in any instantiation (4 -> 64 regs spills 90-150 B)
 #endif
     static constexpr int NS = 19, NP = 49, MIN_BLOCKS = FWB_TP06_MIN_BLOCKS;
     static constexpr bool USE_TMA = false;   // step_kernel_tma for HBM-bound models
@@ -568,10 +583,12 @@ template <> struct Model<FWB_MODEL_TP06> {
         int fast_ok;       // parameters allow the rearranged path (positive concentrations)
         double km1, km2, kj1, kd1, kd2, kd3, kf1, kf2, kf3, kf4, kf5, kr1, ks1, ks2;
         double kx1, kx2, kx3, kx4, kx5, kxs1, kxs2, kxs3;
+        double ec[8];      // fexp's reduction / polynomial constants (fexp_fill_consts)
     };
     static bool derive(const double *p, double dt, Consts &c)
     {
         derive_fast(p, c);
+        fexp_fill_consts(c.ec);
         const double ko = p[0], cao = p[1], nao = p[2], Vc = p[3], Vsr = p[4], Vss = p[5],
                      R = p[24], F = p[25], T = p[26], gkr = p[29], pKNa = p[30],
                      KmK = p[34], knak = p[36], knaca = p[39], KmNai = p[40], KmCa = p[41];
@@ -624,23 +641,35 @@ template <> struct Model<FWB_MODEL_TP06> {
         if (E::FUSE_RATE) return inf - (inf - x) * E::en(-dt * rate);
         return inf - (inf - x) * E::en(-dt / (1.0 / rate));
     }
+    // The rearranged path (ionic_fast) needs |u| < 300 mV (fexp) and positive, normal
+    // concentrations (flog, branch-free reciprocals); anything else -- NaNs included, they
+    // fail every comparison -- takes the reference statement (ionic_ref).  The tile kernel
+    // asks fast_ok() for the whole block and hands tiles with an ineligible node to a second,
+    // cold kernel, so the hot kernel carries the fast path only.
+    static constexpr bool HAS_FAST = true;
+    template <class IO> FWB_HD static bool fast_ok(double u, const IO &io, const Consts &c)
+    {
+        return c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(io.ld(0)) &&
+               conc_ok(io.ld(3)) && conc_ok(io.ld(4));
+    }
+    template <class IO>
+    FWB_HD static void ionic_fastpath(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_fast(u, un, io, c, io.ld(0), io.ld(3), io.ld(4));
+    }
+    template <class IO>
+    FWB_HD static void ionic_ref(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_impl<IO, LibMath>(u, un, io, c, io.ld(0), io.ld(3), io.ld(4));
+    }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        const double cai = io.ld(0), nai = io.ld(3), Ki = io.ld(4);
 #ifdef __CUDA_ARCH__
-        // the rearranged path needs |u| < 300 mV (fexp) and positive, normal concentrations
-        // (flog, branch-free reciprocals); anything else -- NaNs included, they fail every
-        // comparison -- takes the reference statement
-#ifdef FWB_EXP_FASTONLY
-        ionic_fast(u, un, io, c, cai, nai, Ki);
-        return;
-#endif
-        if (c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(cai) && conc_ok(nai) && conc_ok(Ki))
-            ionic_fast(u, un, io, c, cai, nai, Ki);
+        if (fast_ok(u, io, c)) ionic_fastpath(u, un, io, c);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c, cai, nai, Ki);
+            ionic_ref(u, un, io, c);
     }
     FWB_HD static bool conc_ok(double x) { return x > 1e-300 && x < 1e300; }
 
@@ -665,23 +694,32 @@ template <> struct Model<FWB_MODEL_TP06> {
     {
         return fma(x - inf, fexp_fast_neg(-dt * rtau), inf);
     }
-#ifdef FWB_TP06_DIET
     template <class IO>
     FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double cai,
                                   double nai, double Ki)
     {
         const double dt = c.dt;
+        const double *ec = c.ec;       // kernel-parameter bank -> uniform registers
+        auto EX = [ec](double x) { return fexp_fast_p(x, ec); };
+        auto EXC = [ec](double x) {
+            x = x < -700.0 ? -700.0 : x;
+            return fexp_fast_p(x > 700.0 ? 700.0 : x, ec);
+        };
+        auto RL = [ec](double inf, double x, double dt_, double rtau) {
+            const double a = -dt_ * rtau;
+            return fma(x - inf, fexp_fast_p(a < -700.0 ? -700.0 : a, ec), inf);
+        };
         const double Ek = c.RTONF * (c.l_ko - flog(Ki));
         const double Ena = c.RTONF * (c.l_nao - flog(nai));
         const double Eks = c.RTONF * (c.l_kpn - flog(fma(c.pKNa, nai, Ki)));
         const double Eca = c.half_RTONF * (c.l_cao - flog(cai));
 
         // shared exponentials of u
-        const double g20 = fexp_fast(u * 0.05), g10 = g20 * g20, g5 = g10 * g10;
+        const double g20 = EX(u * 0.05), g10 = g20 * g20, g5 = g10 * g10;
         const double i20 = frcp3(g20), i10 = i20 * i20;
-        const double g14 = fexp_fast(u * (1. / 14.)), g7 = g14 * g14;
-        const double g15 = fexp_fast(u * (1. / 15.)), g75 = g15 * g15;
-        const double n24 = fexp_fast(u * (-1. / 24.)), n12 = n24 * n24, n6 = n12 * n12;
+        const double g14 = EX(u * (1. / 14.)), g7 = g14 * g14;
+        const double g15 = EX(u * (1. / 15.)), g75 = g15 * g15;
+        const double n24 = EX(u * (-1. / 24.)), n12 = n24 * n24, n6 = n12 * n12;
 
         // the twelve membrane currents are accumulated as they appear (sum for u_new, the
         // sodium and the potassium balance) instead of being kept live to the end
@@ -690,29 +728,29 @@ template <> struct Model<FWB_MODEL_TP06> {
         {
             const double A = g5 + c.km1;                  // alpha_m = g5 / A
             const double B = fma(c.km2, g5, 1.);          // beta_m = 0.1 / B + 0.1 / C
-            const double C = 1. + fexp_fast((u - 50.) * (1. / 200.));
+            const double C = 1. + EX((u - 50.) * (1. / 200.));
             const double rtau_m = A * B * C * frcp3(0.1 * g5 * (B + C));
-            const double em = 1. + fexp_fast((-56.86 - u) * (1. / 9.03));
+            const double em = 1. + EX((-56.86 - u) * (1. / 9.03));
             const double m_inf = frcp3(em * em);
-            const double eh = 1. + fexp_fast((u + 71.55) * (1. / 7.43));
+            const double eh = 1. + EX((u + 71.55) * (1. / 7.43));
             const double h_inf = frcp3(eh * eh);
             double rate_h, rate_j;
             if (u >= -40.) {
-                rate_h = 0.77 * frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
-                rate_j = 0.6 * fexp_fast(0.057 * u) * g10 * frcp3(g10 + c.kj1);
+                rate_h = 0.77 * frcp3(0.13 * (1. + EX((u + 10.66) * (-1. / 11.1))));
+                rate_j = 0.6 * EX(0.057 * u) * g10 * frcp3(g10 + c.kj1);
             } else {
-                rate_h = 0.057 * fexp_fast((u + 80.) * (-1. / 6.8)) +
-                         (2.7 * fexp_fast(0.079 * u) + 3.1e5 * fexp_fast(0.3485 * u));
-                const double a = 1. + fexp_fast(0.311 * (u + 79.23));
-                const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
-                const double na = (-2.5428e4 * fexp_fast(0.2444 * u) -
-                                   6.948e-6 * fexp_fast(-0.04391 * u)) * (u + 37.78);
-                const double nb = 0.02424 * fexp_fast(-0.01052 * u);
+                rate_h = 0.057 * EX((u + 80.) * (-1. / 6.8)) +
+                         (2.7 * EX(0.079 * u) + 3.1e5 * EX(0.3485 * u));
+                const double a = 1. + EX(0.311 * (u + 79.23));
+                const double b = 1. + EX(-0.1378 * (u + 40.14));
+                const double na = (-2.5428e4 * EX(0.2444 * u) -
+                                   6.948e-6 * EX(-0.04391 * u)) * (u + 37.78);
+                const double nb = 0.02424 * EX(-0.01052 * u);
                 rate_j = fma(na, b, nb * a) * frcp3(a * b);
             }
-            const double m = rlf(m_inf, io.ld(5), dt, rtau_m);
-            const double h = rlf(h_inf, io.ld(6), dt, rate_h);
-            const double j = rlf(h_inf, io.ld(7), dt, rate_j);
+            const double m = RL(m_inf, io.ld(5), dt, rtau_m);
+            const double h = RL(h_inf, io.ld(6), dt, rate_h);
+            const double j = RL(h_inf, io.ld(7), dt, rate_j);
             io.st(5, m); io.st(6, h); io.st(7, j);
             const double uEna = u - Ena;
             const double ina = c.gna * m * m * m * h * j * uEna;
@@ -726,42 +764,42 @@ template <> struct Model<FWB_MODEL_TP06> {
         double ical;
         {
             const double d_inf = g75 * frcp3(g75 + c.kd1);
-            const double A = 1. + fexp_fast((-35. - u) * (1. / 13.));   // Ad = 1.4 / A + 0.25
+            const double A = 1. + EX((-35. - u) * (1. / 13.));   // Ad = 1.4 / A + 0.25
             const double B = fma(c.kd2, g5, 1.);                        // Bd = 1.4 / B
             const double Cn = g20 + c.kd3;                              // Cd = g20 / Cn
             const double P = fma(0.25, A, 1.4) * 1.4;                   // Ad Bd = P / (A B)
             const double AB = A * B;
             const double rtau_d = AB * Cn * frcp3(fma(P, Cn, g20 * AB));
-            const double d = rlf(d_inf, io.ld(13), dt, rtau_d);
+            const double d = RL(d_inf, io.ld(13), dt, rtau_d);
             io.st(13, d);
 
             const double E30 = fma(c.kf3, g10, 1.);
             const double f_inf = frcp3(fma(c.kf1, g7, 1.));
-            const double Af = 1102.5 * fexp_fast(-(u + 27.) * (u + 27.) * (1. / 225.));
+            const double Af = 1102.5 * EX(-(u + 27.) * (u + 27.) * (1. / 225.));
             const double Bn = g10 + c.kf2;                              // Bf = 200 g10 / Bn
             const double Df = Bn * E30;                                 // Cf = 180 / E30 + 20
             const double Nf = fma(200. * g10, E30, 180. * Bn);
             const double rtau_f = Df * frcp3(fma(Af + 20., Df, Nf));
-            const double f = rlf(f_inf, io.ld(14), dt, rtau_f);
+            const double f = RL(f_inf, io.ld(14), dt, rtau_f);
             io.st(14, f);
 
             const double f2_inf = fma(0.67, frcp3(fma(c.kf4, g7, 1.)), 0.33);
-            const double Af2 = 600. * fexp_fast(-(u + 25.) * (u + 25.) * (1. / 170.));
+            const double Af2 = 600. * EX(-(u + 25.) * (u + 25.) * (1. / 170.));
             const double Bn2 = g10 + c.kf5;                             // Bf2 = 31 g10 / Bn2
             const double Df2 = Bn2 * E30;                               // Cf2 = 16 / E30
             const double Nf2 = fma(31. * g10, E30, 16. * Bn2);
             const double rtau_f2 = Df2 * frcp3(fma(Af2, Df2, Nf2));
-            const double f2 = rlf(f2_inf, io.ld(15), dt, rtau_f2);
+            const double f2 = RL(f2_inf, io.ld(15), dt, rtau_f2);
             io.st(15, f2);
 
             const double cs = cass * (1. / 0.05);
             const double cq = fma(cs, cs, 1.);
             const double fcass_inf = fma(0.6, frcp3(cq), 0.4);
             const double rtau_fcass = cq * frcp3(fma(2., cq, 80.));
-            const double fcass = rlf(fcass_inf, io.ld(16), dt, rtau_fcass);
+            const double fcass = RL(fcass_inf, io.ld(16), dt, rtau_fcass);
             io.st(16, fcass);
 
-            const double e2 = fexp_fast(2. * (u - 15.) * c.F_RT);
+            const double e2 = EX(2. * (u - 15.) * c.F_RT);
             ical = c.gcal * d * f * f2 * fcass * 4. * (u - 15.) * c.FF_RT *
                    fma(0.25 * e2, cass, -c.cao) * frcp3(e2 - 1.);
             s_u += ical;
@@ -773,12 +811,12 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double r_inf = frcp3(fma(c.kr1, n6, 1.));
             const double s_inf = frcp3(fma(c.ks1, g5, 1.));
             const double rtau_r =
-                frcp3(fma(9.5, fexp_fast(-(u + 40.) * (u + 40.) * (1. / 1800.)), 0.8));
-            const double G = fma(85., fexp_fast(-(u + 45.) * (u + 45.) * (1. / 320.)), 3.);
+                frcp3(fma(9.5, EX(-(u + 40.) * (u + 40.) * (1. / 1800.)), 0.8));
+            const double G = fma(85., EX(-(u + 45.) * (u + 45.) * (1. / 320.)), 3.);
             const double S2 = fma(c.ks2, g5, 1.);                       // tau_s = G + 5 / S2
             const double rtau_s = S2 * frcp3(fma(G, S2, 5.));
-            const double sg = rlf(s_inf, io.ld(12), dt, rtau_s);
-            const double r = rlf(r_inf, io.ld(11), dt, rtau_r);
+            const double sg = RL(s_inf, io.ld(12), dt, rtau_s);
+            const double r = RL(r_inf, io.ld(11), dt, rtau_r);
             io.st(11, r); io.st(12, sg);
             s_k = c.gto * r * sg * y;
         }
@@ -787,13 +825,13 @@ template <> struct Model<FWB_MODEL_TP06> {
         {
             const double xr1_inf = g7 * frcp3(g7 + c.kx1);
             // tau_xr1 = 450 g10 / (g10 + kx2) * 6 / (1 + e115)
-            const double e115 = fexp_fast((u + 30.) * (1. / 11.5));
+            const double e115 = EX((u + 30.) * (1. / 11.5));
             const double rtau_xr1 = (g10 + c.kx2) * (1. + e115) * (i10 * (1. / 2700.));
             const double xr2_inf = n24 * frcp3(n24 + c.kx3);
             // tau_xr2 = 3 g20 / (g20 + kx4) * 1.12 / (1 + kx5 g20)
             const double rtau_xr2 = (g20 + c.kx4) * fma(c.kx5, g20, 1.) * (i20 * (1. / 3.36));
-            const double xr1 = rlf(xr1_inf, io.ld(8), dt, rtau_xr1);
-            const double xr2 = rlf(xr2_inf, io.ld(9), dt, rtau_xr2);
+            const double xr1 = RL(xr1_inf, io.ld(8), dt, rtau_xr1);
+            const double xr2 = RL(xr2_inf, io.ld(9), dt, rtau_xr2);
             io.st(8, xr1); io.st(9, xr2);
             s_k += c.gkr_sqrt * xr1 * xr2 * y;
         }
@@ -804,23 +842,23 @@ template <> struct Model<FWB_MODEL_TP06> {
             const double sq = fsqrt(fma(c.kxs2, n6, 1.));                // Axs = 1400 / sq
             const double sb = sq * fma(c.kxs3, g15, 1.);                // Bxs = 1 / (1 + kxs3 g15)
             const double rtau_xs = sb * frcp3(fma(80., sb, 1400.));      // tau_xs = 1400 / sb + 80
-            const double xs = rlf(xs_inf, io.ld(10), dt, rtau_xs);
+            const double xs = RL(xs_inf, io.ld(10), dt, rtau_xs);
             io.st(10, xs);
             s_k += c.gks * xs * xs * (u - Eks);
         }
 
         // ---- I_K1 (calc_ik1 :488-514): rec = ak1 / (ak1 + bk1), ak1 = 0.1 / a, bk1 = n / b
         {
-            const double a = 1. + fexp_fast_clamped(0.06 * (y - 200.));
-            const double b = 0.1 * (1. + fexp_fast_clamped(-0.5 * y));
-            const double n = fma(3., fexp_fast_clamped(0.0002 * (y + 100.)),
-                                 fexp_fast_clamped(0.1 * (y - 10.)));
+            const double a = 1. + EXC(0.06 * (y - 200.));
+            const double b = 0.1 * (1. + EXC(-0.5 * y));
+            const double n = fma(3., EXC(0.0002 * (y + 100.)),
+                                 EXC(0.1 * (y - 10.)));
             s_k += c.gk1 * (b * frcp3(fma(n, a, b))) * y;
         }
         // ---- I_NaCa (calc_inaca :517-565), I_NaK (calc_inak :568-604)
         const double x = u * c.F_RT;
-        const double e_nm1 = fexp_fast(c.n_m1 * x);
-        const double en01 = fexp_fast(-0.1 * x);
+        const double e_nm1 = EX(c.n_m1 * x);
+        const double en01 = EX(-0.1 * x);
         const double en02 = en01 * en01, en04 = en02 * en02, en08 = en04 * en04;
         const double en_x = en08 * en02;                                // exp(-x)
         const double nai3 = nai * nai * nai;
@@ -831,7 +869,7 @@ template <> struct Model<FWB_MODEL_TP06> {
                             frcp3((nai + c.KmNa) * fma(0.0353, en_x, fma(0.1245, en01, 1.)));
         // ---- I_pCa, I_pK (:607-670)
         const double ipca = c.gpca * cai * frcp3(c.KpCa + cai);
-        const double ipk = c.gpk * frcp3(1. + fexp_fast((25. - u) * (1. / 5.98))) * y;
+        const double ipk = c.gpk * frcp3(1. + EX((25. - u) * (1. / 5.98))) * y;
 
         // calc_nai :928-953, calc_ki :956-984 (old nai, Ki)
         {
@@ -880,219 +918,6 @@ template <> struct Model<FWB_MODEL_TP06> {
         }
     }
 
-#else
-    template <class IO>
-    FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double cai,
-                                  double nai, double Ki)
-    {
-        const double dt = c.dt;
-        const double Ek = c.RTONF * (c.l_ko - flog(Ki));
-        const double Ena = c.RTONF * (c.l_nao - flog(nai));
-        const double Eks = c.RTONF * (c.l_kpn - flog(fma(c.pKNa, nai, Ki)));
-        const double Eca = c.half_RTONF * (c.l_cao - flog(cai));
-
-        // shared exponentials of u
-        const double g20 = fexp_fast(u * 0.05), g10 = g20 * g20, g5 = g10 * g10;
-        const double i20 = frcp3(g20), i10 = i20 * i20;
-        const double g14 = fexp_fast(u * (1. / 14.)), g7 = g14 * g14;
-        const double g15 = fexp_fast(u * (1. / 15.)), g75 = g15 * g15;
-        const double n24 = fexp_fast(u * (-1. / 24.)), n12 = n24 * n24, n6 = n12 * n12;
-
-        // ---- I_Na (calc_ina :242-318)
-        double ina;
-        {
-            const double A = g5 + c.km1;                  // alpha_m = g5 / A
-            const double B = fma(c.km2, g5, 1.);          // beta_m = 0.1 / B + 0.1 / C
-            const double C = 1. + fexp_fast((u - 50.) * (1. / 200.));
-            const double rtau_m = A * B * C * frcp3(0.1 * g5 * (B + C));
-            const double em = 1. + fexp_fast((-56.86 - u) * (1. / 9.03));
-            const double m_inf = frcp3(em * em);
-            const double eh = 1. + fexp_fast((u + 71.55) * (1. / 7.43));
-            const double h_inf = frcp3(eh * eh);
-            double rate_h, rate_j;
-            if (u >= -40.) {
-                rate_h = 0.77 * frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
-                rate_j = 0.6 * fexp_fast(0.057 * u) * g10 * frcp3(g10 + c.kj1);
-            } else {
-                rate_h = 0.057 * fexp_fast((u + 80.) * (-1. / 6.8)) +
-                         (2.7 * fexp_fast(0.079 * u) + 3.1e5 * fexp_fast(0.3485 * u));
-                const double a = 1. + fexp_fast(0.311 * (u + 79.23));
-                const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
-                const double na = (-2.5428e4 * fexp_fast(0.2444 * u) -
-                                   6.948e-6 * fexp_fast(-0.04391 * u)) * (u + 37.78);
-                const double nb = 0.02424 * fexp_fast(-0.01052 * u);
-                rate_j = fma(na, b, nb * a) * frcp3(a * b);
-            }
-            const double m = rlf(m_inf, io.ld(5), dt, rtau_m);
-            const double h = rlf(h_inf, io.ld(6), dt, rate_h);
-            const double j = rlf(h_inf, io.ld(7), dt, rate_j);
-            io.st(5, m); io.st(6, h); io.st(7, j);
-            ina = c.gna * m * m * m * h * j * (u - Ena);
-        }
-
-        // ---- I_CaL (calc_ical :321-380)
-        const double cass = io.ld(2);
-        double ical;
-        {
-            const double d_inf = g75 * frcp3(g75 + c.kd1);
-            const double A = 1. + fexp_fast((-35. - u) * (1. / 13.));   // Ad = 1.4 / A + 0.25
-            const double B = fma(c.kd2, g5, 1.);                        // Bd = 1.4 / B
-            const double Cn = g20 + c.kd3;                              // Cd = g20 / Cn
-            const double P = fma(0.25, A, 1.4) * 1.4;                   // Ad Bd = P / (A B)
-            const double AB = A * B;
-            const double rtau_d = AB * Cn * frcp3(fma(P, Cn, g20 * AB));
-            const double d = rlf(d_inf, io.ld(13), dt, rtau_d);
-            io.st(13, d);
-
-            const double E30 = fma(c.kf3, g10, 1.);
-            const double f_inf = frcp3(fma(c.kf1, g7, 1.));
-            const double Af = 1102.5 * fexp_fast(-(u + 27.) * (u + 27.) * (1. / 225.));
-            const double Bn = g10 + c.kf2;                              // Bf = 200 g10 / Bn
-            const double Df = Bn * E30;                                 // Cf = 180 / E30 + 20
-            const double Nf = fma(200. * g10, E30, 180. * Bn);
-            const double rtau_f = Df * frcp3(fma(Af + 20., Df, Nf));
-            const double f = rlf(f_inf, io.ld(14), dt, rtau_f);
-            io.st(14, f);
-
-            const double f2_inf = fma(0.67, frcp3(fma(c.kf4, g7, 1.)), 0.33);
-            const double Af2 = 600. * fexp_fast(-(u + 25.) * (u + 25.) * (1. / 170.));
-            const double Bn2 = g10 + c.kf5;                             // Bf2 = 31 g10 / Bn2
-            const double Df2 = Bn2 * E30;                               // Cf2 = 16 / E30
-            const double Nf2 = fma(31. * g10, E30, 16. * Bn2);
-            const double rtau_f2 = Df2 * frcp3(fma(Af2, Df2, Nf2));
-            const double f2 = rlf(f2_inf, io.ld(15), dt, rtau_f2);
-            io.st(15, f2);
-
-            const double cs = cass * (1. / 0.05);
-            const double cq = fma(cs, cs, 1.);
-            const double fcass_inf = fma(0.6, frcp3(cq), 0.4);
-            const double rtau_fcass = cq * frcp3(fma(2., cq, 80.));
-            const double fcass = rlf(fcass_inf, io.ld(16), dt, rtau_fcass);
-            io.st(16, fcass);
-
-            const double e2 = fexp_fast(2. * (u - 15.) * c.F_RT);
-            ical = c.gcal * d * f * f2 * fcass * 4. * (u - 15.) * c.FF_RT *
-                   fma(0.25 * e2, cass, -c.cao) * frcp3(e2 - 1.);
-        }
-
-        // ---- I_to (calc_ito :383-413)
-        double ito;
-        {
-            const double r_inf = frcp3(fma(c.kr1, n6, 1.));
-            const double s_inf = frcp3(fma(c.ks1, g5, 1.));
-            const double rtau_r =
-                frcp3(fma(9.5, fexp_fast(-(u + 40.) * (u + 40.) * (1. / 1800.)), 0.8));
-            const double G = fma(85., fexp_fast(-(u + 45.) * (u + 45.) * (1. / 320.)), 3.);
-            const double S2 = fma(c.ks2, g5, 1.);                       // tau_s = G + 5 / S2
-            const double rtau_s = S2 * frcp3(fma(G, S2, 5.));
-            const double sg = rlf(s_inf, io.ld(12), dt, rtau_s);
-            const double r = rlf(r_inf, io.ld(11), dt, rtau_r);
-            io.st(11, r); io.st(12, sg);
-            ito = c.gto * r * sg * (u - Ek);
-        }
-
-        // ---- I_Kr (calc_ikr :416-452)
-        double ikr;
-        {
-            const double xr1_inf = g7 * frcp3(g7 + c.kx1);
-            // tau_xr1 = 450 g10 / (g10 + kx2) * 6 / (1 + e115)
-            const double e115 = fexp_fast((u + 30.) * (1. / 11.5));
-            const double rtau_xr1 = (g10 + c.kx2) * (1. + e115) * (i10 * (1. / 2700.));
-            const double xr2_inf = n24 * frcp3(n24 + c.kx3);
-            // tau_xr2 = 3 g20 / (g20 + kx4) * 1.12 / (1 + kx5 g20)
-            const double rtau_xr2 = (g20 + c.kx4) * fma(c.kx5, g20, 1.) * (i20 * (1. / 3.36));
-            const double xr1 = rlf(xr1_inf, io.ld(8), dt, rtau_xr1);
-            const double xr2 = rlf(xr2_inf, io.ld(9), dt, rtau_xr2);
-            io.st(8, xr1); io.st(9, xr2);
-            ikr = c.gkr_sqrt * xr1 * xr2 * (u - Ek);
-        }
-
-        // ---- I_Ks (calc_iks :455-485)
-        double iks;
-        {
-            const double xs_inf = g14 * frcp3(g14 + c.kxs1);
-            const double sq = fsqrt(fma(c.kxs2, n6, 1.));                // Axs = 1400 / sq
-            const double sb = sq * fma(c.kxs3, g15, 1.);                // Bxs = 1 / (1 + kxs3 g15)
-            const double rtau_xs = sb * frcp3(fma(80., sb, 1400.));      // tau_xs = 1400 / sb + 80
-            const double xs = rlf(xs_inf, io.ld(10), dt, rtau_xs);
-            io.st(10, xs);
-            iks = c.gks * xs * xs * (u - Eks);
-        }
-
-        // ---- I_K1 (calc_ik1 :488-514): rec = ak1 / (ak1 + bk1), ak1 = 0.1 / a, bk1 = n / b
-        const double y = u - Ek;
-        double ik1;
-        {
-            const double a = 1. + fexp_fast_clamped(0.06 * (y - 200.));
-            const double b = 0.1 * (1. + fexp_fast_clamped(-0.5 * y));
-            const double n = fma(3., fexp_fast_clamped(0.0002 * (y + 100.)),
-                                 fexp_fast_clamped(0.1 * (y - 10.)));
-            ik1 = c.gk1 * (b * frcp3(fma(n, a, b))) * y;
-        }
-        // ---- I_NaCa (calc_inaca :517-565), I_NaK (calc_inak :568-604)
-        const double x = u * c.F_RT;
-        const double e_nm1 = fexp_fast(c.n_m1 * x);
-        const double en01 = fexp_fast(-0.1 * x);
-        const double en02 = en01 * en01, en04 = en02 * en02, en08 = en04 * en04;
-        const double en_x = en08 * en02;                                // exp(-x)
-        const double nai3 = nai * nai * nai;
-        const double inaca = c.inaca_pref * e_nm1 *
-                             fma(-2.5 * (c.nao * c.nao * c.nao) * cai, en_x, nai3 * c.cao) *
-                             frcp3(en_x * fma(c.ksat, e_nm1, 1.));
-        const double inak = c.knak_pref * nai *
-                            frcp3((nai + c.KmNa) * fma(0.0353, en_x, fma(0.1245, en01, 1.)));
-        // ---- I_pCa, I_pK, I_bNa, I_bCa (:607-697)
-        const double ipca = c.gpca * cai * frcp3(c.KpCa + cai);
-        const double ipk = c.gpk * frcp3(1. + fexp_fast((25. - u) * (1. / 5.98))) * y;
-        const double ibna = c.gbna * (u - Ena);
-        const double ibca = c.gbca * (u - Eca);
-
-        // calc_nai :928-953, calc_ki :956-984 (old nai, Ki)
-        {
-            const double dNai = -(ina + ibna + 3 * inak + 3 * inaca) * c.inverseVcF * c.CAPACITANCE;
-            io.st(3, fma(dt, dNai, nai));
-            const double dKi = -(ik1 + ito + ikr + iks - 2 * inak + ipk) * c.inverseVcF * c.CAPACITANCE;
-            io.st(4, fma(dt, dKi, Ki));
-        }
-        un -= dt * (ikr + iks + ik1 + ito + ina + ibna + ical + ibca + inak + inaca + ipca + ipk);
-
-        // ---- calcium handling (calc_irel :700-730 ... calc_cass :831-872)
-        const double casr = io.ld(1);
-        const double cass2 = cass * cass;
-        double irel;
-        {
-            double rr = io.ld(17);
-            const double casr2 = casr * casr;
-            const double kCaSR = fma(-c.maxsr_m_minsr * casr2, frcp3(casr2 + c.EC2), c.maxsr);
-            const double k2 = c.k2_ * kCaSR;
-            rr = fma(dt, fma(c.k4, 1. - rr, -(k2 * cass * rr)), rr);
-            const double k1c = c.k1_ * cass2;
-            const double oo = k1c * rr * frcp3(fma(c.k3, kCaSR, k1c));
-            irel = c.Vrel * oo * (casr - cass);
-            io.st(17, rr); io.st(18, oo);
-        }
-        const double ileak = c.Vleak * (casr - cai);
-        const double cai2 = cai * cai;
-        const double iup = c.Vmaxup * cai2 * frcp3(cai2 + c.Kup2);
-        const double ixfer = c.Vxfer * (cass - cai);
-        {
-            const double CaCSQN = c.Bufsr * casr * frcp3(casr + c.Kbufsr);
-            const double dCaSR = dt * (iup - irel - ileak);
-            const double bjsr = c.Bufsr - CaCSQN - dCaSR - casr + c.Kbufsr;
-            const double cjsr = c.Kbufsr * (CaCSQN + dCaSR + casr);
-            io.st(1, (fsqrt(fma(bjsr, bjsr, 4 * cjsr)) - bjsr) * 0.5);
-        }
-        {
-            const double CaSSBuf = c.Bufss * cass * frcp3(cass + c.Kbufss);
-            const double dCaSS = dt * (-ixfer * c.Vc_Vss + irel * c.Vsr_Vss +
-                                       (-ical * c.inversevssF2 * c.CAPACITANCE));
-            const double bcss = c.Bufss - CaSSBuf - dCaSS - cass + c.Kbufss;
-            const double ccss = c.Kbufss * (CaSSBuf + dCaSS + cass);
-            io.st(2, (fsqrt(fma(bcss, bcss, 4 * ccss)) - bcss) * 0.5);
-        }
-    }
-
-#endif
     template <class IO, class E>
     FWB_HD static void ionic_impl(double u, double &un, IO &io, const Consts &c, double cai,
                                   double nai, double Ki)
@@ -1298,7 +1123,10 @@ template <> struct Model<FWB_MODEL_TP06> {
 // (slot 14 is the I_Ks gate, slot 15 the I_Kr gate); calc_ikr ignores the gkr parameter.
 // ---------------------------------------------------------------------------
 template <> struct Model<FWB_MODEL_COURTEMANCHE> {
-    static constexpr int NS = 21, NP = 39, MIN_BLOCKS = 4;
+#ifndef FWB_COURT_MIN_BLOCKS
+#define FWB_COURT_MIN_BLOCKS 3
+#endif
+    static constexpr int NS = 21, NP = 39, MIN_BLOCKS = FWB_COURT_MIN_BLOCKS;
     static constexpr bool USE_TMA = false;
     static constexpr uint32_t READ_MASK = 0x1fffff, WRITE_MASK = 0x1fffff;
     struct Consts {
@@ -1347,18 +1175,32 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
     {
         return x_inf - (x_inf - x) * E::en(-dt / tau_x);
     }
+    static constexpr bool HAS_FAST = true;
+    // the rearranged path needs |u| < 300 mV and positive, normal nai / ki / cai (flog,
+    // branch-free reciprocals); NaNs fail the comparisons and take the reference statement
+    template <class IO> FWB_HD static bool fast_ok(double u, const IO &io, const Consts &c)
+    {
+        return c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(io.ld(0)) &&
+               conc_ok(io.ld(1)) && conc_ok(io.ld(2));
+    }
+    template <class IO>
+    FWB_HD static void ionic_fastpath(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_fast(u, un, io, c, io.ld(0), io.ld(1), io.ld(2));
+    }
+    template <class IO>
+    FWB_HD static void ionic_ref(double u, double &un, IO &io, const Consts &c)
+    {
+        ionic_impl<IO, LibMath>(u, un, io, c, io.ld(0), io.ld(1), io.ld(2));
+    }
     template <class IO>
     FWB_HD static void ionic(double u, double &un, IO &io, const Consts &c)
     {
-        const double nai = io.ld(0), ki = io.ld(1), cai = io.ld(2);
 #ifdef __CUDA_ARCH__
-        // the rearranged path needs |u| < 300 mV and positive, normal nai / ki / cai (flog,
-        // branch-free reciprocals); NaNs fail the comparisons and take the reference statement
-        if (c.fast_ok && fabs(u) < FAST_MATH_U_LIMIT && conc_ok(nai) && conc_ok(ki) && conc_ok(cai))
-            ionic_fast(u, un, io, c, nai, ki, cai);
+        if (fast_ok(u, io, c)) ionic_fastpath(u, un, io, c);
         else
 #endif
-            ionic_impl<IO, LibMath>(u, un, io, c, nai, ki, cai);
+            ionic_ref(u, un, io, c);
     }
     FWB_HD static bool conc_ok(double x) { return x > 1e-300 && x < 1e300; }
     FWB_HD static double rlf(double inf, double x, double e) { return fma(x - inf, e, inf); }

@@ -10,8 +10,11 @@
 // Host hooks (commands, state savers, user trackers) are the caller's business:
 // it asks for exactly as many steps as may run before the next hook is due.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
+
+#include <cudaTypedefs.h>
 
 #include "aux_kernels.cuh"
 #include "step_kernel.cuh"
@@ -114,8 +117,16 @@ struct FwbSim {
     double *ecg_partial;
     int64_t ecg_partial_cap;
     int64_t launches;
+    int64_t device_steps;            // time steps advanced by device kernels
     const uint32_t *tile_base;
     const uint32_t *records;
+    // compact-lane tile kernel: tile records, node positions, deferred-tile list, u bricks
+    const uint32_t *tile_rec;
+    const uint8_t *pos_of;
+    uint32_t *defer;                 // [n_tiles + 2]: list, then {count, finished blocks}
+    int32_t *node_of;                // [n_myo] compact index -> flat node (multi-step kernel)
+    bool brick_ok;
+    alignas(64) CUtensorMap tmap[2]; // of buf[0] / buf[1]
     // slab halo
     bool halo_on;
     unsigned epoch;
@@ -195,8 +206,10 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
         set_error("fwb_sim_create: model %d has a zero or non-finite divisor parameter", model);
         return FWB_E_ARG;
     }
-    s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0;
+    s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0; s->device_steps = 0;
     s->tile_base = nullptr; s->records = nullptr;
+    s->tile_rec = nullptr; s->pos_of = nullptr; s->defer = nullptr; s->brick_ok = false;
+    s->node_of = nullptr;
     s->halo_on = false; s->epoch = 0; s->flags = nullptr;
     memset(s->peer_u, 0, sizeof(s->peer_u));
     memset(s->peer_flags, 0, sizeof(s->peer_flags));
@@ -210,6 +223,8 @@ extern "C" int fwb_sim_destroy(FwbSim *s)
 {
     if (!s) return 0;
     if (s->ecg_partial) cudaFree(s->ecg_partial);
+    if (s->defer) cudaFree(s->defer);
+    if (s->node_of) cudaFree(s->node_of);
     delete s;
     return 0;
 }
@@ -254,6 +269,66 @@ extern "C" int fwb_sim_set_tile_base(FwbSim *s, const uint32_t *tile_base,
     }
     s->tile_base = tile_base;
     s->records = records;
+    return 0;
+}
+
+// tensor map of one dense u buffer for the tile kernel's brick copies: box = tile + 1-node
+// halo ((2+2) x (4+2) x (32+4) doubles in 3D, (8+2) x (32+4) in 2D: a box must start on a
+// 16-byte boundary, so two columns on either side); out-of-range elements of
+// a box at the grid edge read as zero (they are never used: the outer ring is not tissue)
+static bool make_u_tensor_map(CUtensorMap *map, const double *u, int dim, const Grid &g)
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    if (dim == 3) {
+        dims[0] = (cuuint64_t)g.line; dims[1] = (cuuint64_t)g.rows; dims[2] = (cuuint64_t)g.planes;
+        strides[0] = (cuuint64_t)g.s_row * 8; strides[1] = (cuuint64_t)g.s_plane * 8;
+        box[0] = Brick<3>::L; box[1] = Brick<3>::R; box[2] = Brick<3>::P;
+    } else {
+        dims[0] = (cuuint64_t)g.line; dims[1] = (cuuint64_t)g.rows;
+        strides[0] = (cuuint64_t)g.s_row * 8;
+        box[0] = Brick<2>::L; box[1] = Brick<2>::R;
+    }
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)dim,
+                              const_cast<double *>(u), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+extern "C" int fwb_sim_set_tiles(FwbSim *s, const uint32_t *tile_rec, const uint8_t *pos_of)
+{
+    if (!s || ((tile_rec == nullptr) != (pos_of == nullptr))) {
+        set_error("fwb_sim_set_tiles: bad argument");
+        return FWB_E_ARG;
+    }
+    s->tile_rec = tile_rec;
+    s->pos_of = pos_of;
+    s->brick_ok = false;
+    if (!tile_rec) return 0;
+    const int64_t n_tiles = s->g.n_work / WARPS_PER_BLOCK;
+    if (!s->defer) {
+        FWB_CUDA(cudaMalloc((void **)&s->defer, sizeof(uint32_t) * (n_tiles + 2)));
+        FWB_CUDA(cudaMemsetAsync(s->defer, 0, sizeof(uint32_t) * (n_tiles + 2), s->stream));
+    }
+    // bricks need a line length that is a multiple of 32 nodes (16-B aligned rows, tiles that
+    // are boxes) and 16-B aligned buffers; FWB_NO_BRICK=1 keeps plain loads (A/B measurements)
+    const char *no = getenv("FWB_NO_BRICK");
+    if ((s->g.line & 31) == 0 && !(no && no[0] == '1') &&
+        ((uintptr_t)s->buf[0] & 15) == 0 && ((uintptr_t)s->buf[1] & 15) == 0)
+        s->brick_ok = make_u_tensor_map(&s->tmap[0], s->buf[0], s->dim, s->g) &&
+                      make_u_tensor_map(&s->tmap[1], s->buf[1], s->dim, s->g);
     return 0;
 }
 
@@ -435,9 +510,16 @@ extern "C" int64_t fwb_sim_tracker_samples(const FwbSim *s, int id)
 }
 
 extern "C" int64_t fwb_sim_launch_count(const FwbSim *s) { return s ? s->launches : FWB_E_ARG; }
+extern "C" int64_t fwb_sim_device_steps(const FwbSim *s) { return s ? s->device_steps : FWB_E_ARG; }
 
 static thread_local int g_step_variant = -1;
-namespace fwb { void note_step_variant(int v) { g_step_variant = v; } }
+static thread_local int g_step_launches = 1;
+namespace fwb {
+// variants 4 / 5 (tile kernel) launch two kernels per step: the fast one and the
+// reference-statement one for the tiles it hands over
+void note_step_variant(int v) { g_step_variant = v; g_step_launches = (v == 4 || v == 5) ? 2 : 1; }
+int last_step_launches() { return g_step_launches; }
+}
 extern "C" int fwb_last_step_variant(void) { return g_step_variant; }
 
 static inline bool gate(const Tracker &tr, double t, int64_t step)
@@ -447,11 +529,111 @@ static inline bool gate(const Tracker &tr, double t, int64_t step)
     return step % tr.every == 0;
 }
 
+// compact index -> flat node, from the work list (one thread per work-list entry and lane)
+__global__ void node_of_kernel(const int32_t *wl, int64_t n_work, const uint32_t *bits,
+                               const uint32_t *base, int32_t *node_of)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_work) return;
+    const int32_t c = wl[i];
+    if (c < 0) return;
+    const uint32_t b = bits[c];
+    if ((b >> lane) & 1u) node_of[base[c] + __popc(b & ((1u << lane) - 1u))] = c * 32 + lane;
+}
+
+// Tiny tissues (README quick start: 100 x 100): how many of the next steps can run inside ONE
+// launch of the multi-step cluster kernel -- no stimulus fires, nothing but (at most one,
+// primed) activation-time tracker samples.  Returns 0 when the per-step path must take the
+// next step.  `fused` receives that tracker, `samples` how often its gate passes.
+static int64_t small_run_length(FwbSim *s, int64_t max_steps, Tracker **fused, int64_t *samples)
+{
+    *fused = nullptr; *samples = 0;
+    if (!s->entry->launch_small || s->entry->n_state > 4 || s->halo_on) return 0;
+    if (s->n_myo < 1 || s->n_myo > (int64_t)SMALL_MAX_CTAS * SMALL_THREADS * SMALL_MAX_NPT) return 0;
+    if (s->g.n_nodes >= ((int64_t)1 << 31)) return 0;
+    const char *off = getenv("FWB_NO_SMALL_KERNEL");
+    if (off && off[0] == '1') return 0;
+    Tracker *act = nullptr;
+    for (Tracker &tr : s->trackers) {
+        if (tr.kind != TR_ACT) continue;
+        if (act) return 0;                     // a second activation tracker: per-step path
+        act = &tr;
+    }
+    double t = s->t;
+    int64_t step = s->step, m = 0, hits = 0;
+    while (m < max_steps) {
+        for (const Stim &sm : s->stims)
+            if (t >= sm.t && !sm.passed) goto done;
+        for (const Tracker &tr : s->trackers) {
+            if (!gate(tr, t, step)) continue;
+            if (tr.kind != TR_ACT || !tr.primed) goto done;
+            ++hits;
+        }
+        t += s->dt; ++step; ++m;
+    }
+done:
+    *fused = act; *samples = hits;
+    return m;
+}
+
+static int run_small(FwbSim *s, int64_t m, Tracker *act, int64_t samples)
+{
+    cudaStream_t st = s->stream;
+    if (!s->node_of) {
+        FWB_CUDA(cudaMalloc((void **)&s->node_of, sizeof(int32_t) * (s->n_myo > 0 ? s->n_myo : 1)));
+        const unsigned nb = (unsigned)((s->g.n_work * 32 + 255) / 256);
+        node_of_kernel<<<nb, 256, 0, st>>>(s->g.worklist, s->g.n_work, s->g.chunk_bits,
+                                           s->g.chunk_base, s->node_of);
+        FWB_KERNEL_CHECK("node_of_kernel");
+    }
+    StepCommon k;
+    memset(&k, 0, sizeof(k));
+    k.g = s->g; k.w = s->weights; k.state = s->state;
+    SmallArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.node_of = s->node_of;
+    sa.buf[0] = s->buf[0]; sa.buf[1] = s->buf[1];
+    sa.cur = s->cur; sa.n_steps = (int)m; sa.n_myo = s->n_myo;
+    const int64_t per = (int64_t)SMALL_MAX_CTAS * SMALL_THREADS;
+    sa.npt = (int)((s->n_myo + per - 1) / per);
+    if (s->n_myo <= SMALL_THREADS) sa.npt = 1;
+    sa.step0 = s->step; sa.t0 = s->t;
+    if (act) {
+        sa.act_t = act->act_t; sa.act_thr = act->thr;
+        sa.act_start = act->start; sa.act_end = act->end; sa.act_every = act->every;
+    } else {
+        sa.act_every = 1;
+    }
+    int rc = s->entry->launch_small(s->dim, s->stencil, k, s->consts, sa, st);
+    if (rc) return rc;
+    s->launches++;
+    if (act) act->samples += samples;
+    for (int64_t i = 0; i < m; ++i) s->t += s->dt;     // the reference's float accumulation
+    s->step += m;
+    s->device_steps += m;
+    if (m & 1) s->cur ^= 1;
+    return 0;
+}
+
 extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
 {
     if (!s || n_steps < 0) { set_error("fwb_sim_run: bad argument"); return FWB_E_ARG; }
     cudaStream_t st = s->stream;
     for (int64_t it = 0; it < n_steps; ++it) {
+        {
+            // launch-bound sizes: as many steps as possible inside one cluster-kernel launch
+            Tracker *act = nullptr;
+            int64_t samples = 0;
+            const int64_t m = small_run_length(s, n_steps - it > 100000 ? 100000 : n_steps - it,
+                                               &act, &samples);
+            if (m >= 4) {
+                int rc = run_small(s, m, act, samples);
+                if (rc) return rc;
+                it += m - 1;
+                continue;
+            }
+        }
         double *u = s->buf[s->cur];
         double *u_new = s->buf[s->cur ^ 1];
         const double t = s->t;
@@ -488,6 +670,10 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
                 s->launches++;
                 sm.fired++;
                 sm.passed = t >= sm.t + sm.duration;   // Stim.update_status
+                // nodes the solver does not update (special boundaries) change only through
+                // stimuli: the activation trackers' next sample covers the whole grid again
+                for (Tracker &tr : s->trackers)
+                    if (tr.kind == TR_ACT) tr.primed = false;
             }
         }
 
@@ -498,6 +684,15 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         k.t = t;
         k.tile_base = s->tile_base;
         k.records = reinterpret_cast<const uint4 *>(s->records);
+        k.tile_rec = reinterpret_cast<const uint4 *>(s->tile_rec);
+        k.pos_of = s->pos_of;
+        if (s->defer) {
+            const int64_t n_tiles = s->g.n_work / WARPS_PER_BLOCK;
+            k.defer_list = s->defer;
+            k.defer_ctr = s->defer + n_tiles;
+        }
+        k.brick = s->brick_ok ? 1 : 0;
+        k.tmap_host = &s->tmap[s->cur];
         if (s->halo_on) {
             Halo &h = k.halo;
             h.on = 1; h.slice = slow_stride(s->g); h.epoch = s->epoch;
@@ -537,7 +732,7 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         }
         int rc = s->entry->launch(s->dim, s->stencil, track, k, s->consts, st);
         if (rc) return rc;
-        s->launches++;
+        s->launches += last_step_launches();
         if (ecg) {
             rc = launch_ecg_finalize(s->ecg_partial, step_blocks(s->g), ecg->n_leads,
                                      ecg->out + ecg->samples * ecg->n_leads, st);
@@ -567,6 +762,7 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         // 4. advance
         s->t += s->dt;
         s->step += 1;
+        s->device_steps += 1;
         s->cur ^= 1;
         if (s->halo_on) s->epoch += 1;
     }
@@ -605,4 +801,42 @@ extern "C" int fwb_diffuse(int dim, int stencil, const int64_t *shape,
     k.u = u; k.u_new = u_new; k.w = weights; k.state = nullptr;
     NoModel::Consts c{0.0};
     return model_entry(FWB_N_MODELS)->launch(dim, stencil, false, k, &c, (cudaStream_t)stream);
+}
+
+// ECG{2,3}DTracker.calc_ecg by hand (cpuwave2D/tracker/ecg_2d_tracker.py:61-79,
+// cpuwave3D/tracker/ecg_3d_tracker.py:51-69): u_tr = W u on the updated nodes, then per lead
+// sum (u_tr - u) / (d * dr) -- the fused kernel's own reduction (deterministic order),
+// stand-alone.  out: [n_leads] on the device.
+extern "C" int fwb_ecg(int dim, int stencil, const int64_t *shape, const uint32_t *chunk_bits,
+                       const uint32_t *chunk_base, int64_t ld, const int32_t *worklist,
+                       int64_t n_work, const double *u, double *u_tr, const double *weights,
+                       const double *coords, int n_leads, double dr, double *out,
+                       fwb_stream_t stream)
+{
+    if (!shape || !chunk_bits || !chunk_base || !u || !u_tr || !weights || !worklist || !coords ||
+        !out || n_leads <= 0 || n_work < 0 || n_work % WARPS_PER_BLOCK != 0 ||
+        fwb_stencil_k(dim, stencil) < 0) {
+        set_error("fwb_ecg: bad argument");
+        return FWB_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    StepCommon k;
+    memset(&k, 0, sizeof(k));
+    k.g = make_grid(dim, shape, chunk_bits, chunk_base, ld);
+    k.g.worklist = worklist; k.g.n_work = n_work;
+    k.u = u; k.u_new = u_tr; k.w = weights; k.state = nullptr;
+    const int64_t blocks = step_blocks(k.g);
+    if (blocks <= 0) {
+        FWB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_leads, st));
+        return 0;
+    }
+    double *partial = nullptr;
+    FWB_CUDA(cudaMallocAsync((void **)&partial, sizeof(double) * blocks * n_leads, st));
+    k.do_ecg = 1; k.n_leads = n_leads; k.ecg_coords = coords; k.dr = dr; k.ecg_partial = partial;
+    NoModel::Consts c{0.0};
+    int rc = model_entry(FWB_N_MODELS)->launch(dim, stencil == FWB_STENCIL_SYM ? FWB_STENCIL_ANISO : stencil,
+                                               true, k, &c, st);
+    if (!rc) rc = launch_ecg_finalize(partial, blocks, n_leads, out, st);
+    cudaFreeAsync(partial, st);
+    return rc;
 }

@@ -37,6 +37,9 @@
 // (NVLink), and the last of them to finish raises the neighbour's flag for the
 // next step.  Interior blocks never wait: the exchange overlaps the interior.
 #pragma once
+#include <map>
+#include <mutex>
+
 #include "fwb_common.cuh"
 #include "models.cuh"
 
@@ -80,6 +83,13 @@ struct StepCommon {
     Halo halo;
     const uint32_t *tile_base;  // [n_work/8 + 1] compact index of each tile's first node, or NULL
     const uint4 *records;       // [n_work] {chunk, bits, chunk base, tile base} (TMA kernel)
+    // compact-lane tile kernel (step_kernel_tile)
+    const uint4 *tile_rec;      // [n_work/8] {compact base, count, chunk id of slot 0, boundary}
+    const uint8_t *pos_of;      // [ld] (slot << 5) | lane of each compact node inside its tile
+    uint32_t *defer_list;       // [n_work/8] tiles handed to the reference-statement kernel
+    uint32_t *defer_ctr;        // [0] entries in defer_list, [1] finished blocks of that kernel
+    int brick;                  // the launch carries a tensor map of u (interior tiles use it)
+    const void *tmap_host;      // HOST pointer to that CUtensorMap (read by the launcher only)
 };
 
 // "no model": diffusion only (fwb_diffuse, ECG re-application)
@@ -145,6 +155,9 @@ template <> struct Stencil<3, FWB_STENCIL_ANISO> {
 };
 
 #ifdef __CUDACC__
+}  // namespace fwb
+#include <cuda.h>      // CUtensorMap (driver API type only; the encoder is fetched at run time)
+namespace fwb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -220,21 +233,29 @@ template <class M> struct StateIOTma {
     const double *sm;     // this node's column in the staged state rows
     double *gp;           // this node's column in the global compact state
     int64_t stride;
+    bool on = true;       // false: a shadow lane of a partially filled warp (computes, never stores)
     // (__popc of a constant folds; the constexpr recursion of tma_slot() does not when q
     // only becomes a constant after inlining, and costs a 150-instruction loop per load)
     __device__ __forceinline__ double ld(int q) const
     {
         return sm[__popc(M::READ_MASK & ((1u << q) - 1u)) * TMA_SEG];
     }
-    __device__ __forceinline__ void st(int q, double v) const { st_stream(gp + (int64_t)q * stride, v); }
+    __device__ __forceinline__ void st(int q, double v) const
+    {
+        if (on) st_stream(gp + (int64_t)q * stride, v);
+    }
 };
 
 // state accessor of one node: slot q lives at state[q * ld + c]
 struct StateIO {
     double *base;
     int64_t stride;
+    bool on = true;
     __device__ __forceinline__ double ld(int q) const { return ld_stream(base + (int64_t)q * stride); }
-    __device__ __forceinline__ void st(int q, double v) const { st_stream(base + (int64_t)q * stride, v); }
+    __device__ __forceinline__ void st(int q, double v) const
+    {
+        if (on) st_stream(base + (int64_t)q * stride, v);
+    }
     // pull every row this node will read towards the SM without holding registers: the
     // models with many state arrays load them where they are used (register budget), and
     // would otherwise pay the full HBM latency at each of those points
@@ -274,7 +295,9 @@ template <class M, int K, int STAGED> struct StageCfg {
 };
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO, int STAGED = 0>
-__global__ void __launch_bounds__(BLOCK_THREADS, (StageCfg<M, Stencil<DIM, ST>::K, STAGED>::BLOCKS))
+// (LR91 / TP06 / Courtemanche normally run step_kernel_tile; this kernel is their fallback for
+// callers without the tile layout and carries both of their paths: 2 blocks per SM, no spills)
+__global__ void __launch_bounds__(BLOCK_THREADS, (stage_state<M>() ? 2 : StageCfg<M, Stencil<DIM, ST>::K, STAGED>::BLOCKS))
 step_kernel(const __grid_constant__ StepArgs<M> A)
 {
     using S = Stencil<DIM, ST>;
@@ -483,6 +506,321 @@ step_kernel(const __grid_constant__ StepArgs<M> A)
 
 
 // ---------------------------------------------------------------------------
+// step_kernel_tile: LR91 / TP06 / Courtemanche -- the FP64-heavy models
+//
+// One block per SPATIAL tile of the tile-granular work list (3D: 2 planes x 4 rows x 32 nodes,
+// 2D: 8 rows x 32 nodes; slab-boundary tiles 1 x 8 x 32 / 1 x 256).
+//  * compact lanes: thread r of the block owns the r-th updated node of the tile (`pos_of`
+//    gives its slot and lane), so a warp is 32 myocytes whatever the tissue looks like --
+//    a ventricle wall or 30 % fibrosis no longer leaves lanes idle while the warp issues the
+//    whole FP64 instruction stream of the model
+//  * the tile's u neighbourhood arrives as ONE brick ((2+2) x (4+2) x (32+4) doubles in 3D,
+//    (8+2) x (32+4) in 2D) by a tensor-TMA copy (cp.async.bulk.tensor -> UTMALDG) into shared
+//    memory; the 5 ... 19 stencil operands are shared-memory reads at compile-time offsets.
+//    Slab-boundary tiles (which read ghost values a peer GPU stored) and grids whose line
+//    length is not a multiple of 32 take plain loads instead
+//  * the tile's state rows (contiguous in the tile-ordered compact layout) arrive by 1-D TMA
+//    bulk copies on the same mbarrier; the weight rows are coalesced streaming loads straight
+//    into registers (they are consumed once, right away)
+//  * the hot kernel carries the model's rearranged fast path ONLY.  A tile with a node that
+//    is not eligible for it (|u| >= 300 mV, a non-positive or non-finite concentration, NaN)
+//    is appended to `defer_list` and left untouched; step_kernel_tile<..., SLOW = true>, launched
+//    right after, recomputes those tiles from scratch with the reference statement.  The
+//    cold code no longer sets the hot kernel's register count (TP06: 64 registers, 4 blocks
+//    per SM, against 80 / 3 with both paths in one kernel)
+// ---------------------------------------------------------------------------
+template <int DIM> struct Brick;
+// (the box of a tensor-TMA copy must START on a 16-byte boundary of the line -- an odd fp64
+// column is an "illegal instruction" -- so the brick starts two columns left of the tile and
+// is 36 columns wide: X0 = 2)
+template <> struct Brick<3> {
+    static constexpr int P = 4, R = 6, L = 36, X0 = 2, N = P * R * L;
+    // brick index of the node at tile slot q, lane ln (interior tile: 2 planes x 4 rows)
+    __device__ static int centre(int q, int ln) { return (((q >> 2) + 1) * R + (q & 3) + 1) * L + ln + X0; }
+    __host__ __device__ static constexpr int off(const Off o) { return (o.p * R + o.r) * L + o.l; }
+};
+template <> struct Brick<2> {
+    static constexpr int P = 1, R = 10, L = 36, X0 = 2, N = R * L;
+    __device__ static int centre(int q, int ln) { return (q + 1) * L + ln + X0; }
+    __host__ __device__ static constexpr int off(const Off o) { return o.r * L + o.l; }
+};
+constexpr int BRICK_BYTES_MAX = ((Brick<3>::N * 8 + 127) / 128) * 128;
+
+template <class M, bool BRICK> struct TileCfg {
+    static constexpr int NSR = tma_popc(M::READ_MASK);
+    static constexpr size_t STATE = (size_t)NSR * TMA_SEG * sizeof(double);
+    static constexpr size_t SMEM = STATE + (BRICK ? BRICK_BYTES_MAX : 0);
+};
+
+// flat node of tile slot q, lane ln (mirrors worklist_mark_kernel)
+template <int DIM>
+__device__ __forceinline__ int64_t tile_node(const Grid &g, bool tiled, bool bnd, int64_t n0, int q, int ln)
+{
+    if (!tiled) return n0 + q * 32 + ln;
+    if (DIM == 3) return bnd ? n0 + (int64_t)q * g.s_row + ln
+                             : n0 + (int64_t)(q >> 2) * g.s_plane + (int64_t)(q & 3) * g.s_row + ln;
+    return bnd ? n0 + q * 32 + ln : n0 + (int64_t)q * g.s_row + ln;
+}
+
+__device__ __forceinline__ void tma_load_brick3(void *dst, const CUtensorMap *map, int c0, int c1,
+                                                int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_brick2(void *dst, const CUtensorMap *map, int c0, int c1,
+                                                uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// one tile: everything between fetching the tile record and the tracker reductions
+template <class M, int DIM, int ST, bool TRACK, bool HALO, bool BRICK, bool SLOW>
+__device__ __forceinline__ void tile_body(const StepArgs<M> &A, const CUtensorMap *tmap,
+                                          const uint32_t t, double *brick, double *staged,
+                                          uint64_t *full_p, double (*red)[32])
+{
+    using S = Stencil<DIM, ST>;
+    using B = Brick<DIM>;
+    constexpr int K = S::K;
+    constexpr int NSR = tma_popc(M::READ_MASK);
+    const StepCommon &P = A.k;
+    const Grid &g = P.g;
+    const int tid = threadIdx.x;
+    const bool tiled = (g.line & 31) == 0;
+    uint64_t &full = *full_p;
+    const uint4 rec = __ldg(P.tile_rec + t);
+    const uint32_t c0 = rec.x, cnt = rec.y;
+    const int64_t n0 = (int64_t)rec.z * 32;
+    const bool bnd = HALO && rec.w != 0;
+    const bool use_brick = BRICK && !SLOW && !bnd;   // (BRICK kernels: tiled grids only)
+    const uint32_t c0a = c0 & ~1u;
+
+    if (!SLOW && tid == 0) {
+        const unsigned bytes = cnt ? (((c0 + cnt - c0a) + 1u) & ~1u) * 8u : 0u;
+        mbar_arrive_expect_tx(&full, bytes * NSR + (use_brick ? (unsigned)(B::N * 8) : 0u));
+        if (use_brick) {
+            // tile origin (plane, row, column) from the chunk id of its slot 0
+            const int64_t cpl = g.line >> 5;
+            const int64_t o = rec.z;
+            const int col0 = (int)(o % cpl) * 32;
+            if (DIM == 3) {
+                const int row0 = (int)((o / cpl) % g.rows), pl0 = (int)(o / (cpl * g.rows));
+                tma_load_brick3(brick, tmap, col0 - B::X0, row0 - 1, pl0 - 1, &full);
+            } else {
+                tma_load_brick2(brick, tmap, col0 - B::X0, (int)(o / cpl) - 1, &full);
+            }
+        }
+        if (bytes) {
+#pragma unroll
+            for (int q = 0; q < NSR; ++q)
+                tma_load_1d(staged + q * TMA_SEG,
+                            P.state + (int64_t)tma_nth(M::READ_MASK, q) * g.ld + c0a, bytes, &full);
+        }
+    }
+
+    // which slab boundary (if any) this tile belongs to
+    const HaloSide *side = nullptr;
+    if (HALO) {
+        if (P.halo.lo.on && t - P.halo.lo.first_block < P.halo.lo.n_blocks) side = &P.halo.lo;
+        else if (P.halo.hi.on && t - P.halo.hi.first_block < P.halo.hi.n_blocks) side = &P.halo.hi;
+        if (side) {
+            if (tid == 0)
+                while (ld_acquire_sys(side->flag) < P.halo.epoch) __nanosleep(64);
+            __syncthreads();
+        }
+    }
+
+    // compact lanes: thread r owns the r-th updated node of the tile.  A partially
+    // filled warp runs whole (its spare lanes shadow the tile's last node and never
+    // store); warps beyond the node count skip the arithmetic altogether.
+    const bool act = (uint32_t)tid < cnt;
+    const bool wact = (uint32_t)(tid & ~31) < cnt;
+    const uint32_t c = c0 + (act ? (uint32_t)tid : cnt - 1u);
+    int64_t n = 0;
+    int q = 0, ln = 0;
+    double acc = 0.0, uc = 0.0;
+    if (wact) {
+        const unsigned pos = __ldg(P.pos_of + c);
+        q = pos >> 5; ln = pos & 31;
+        n = tile_node<DIM>(g, tiled, bnd, n0, q, ln);
+        // diffusion: left-to-right sum in slot order, no FMA contraction (-fmad=false).
+        // Brick tiles: the weights are requested first (one coalesced streaming load per
+        // slot, all in flight together), the u operands are shared-memory reads once the
+        // brick has landed.  Other tiles: both operands are plain loads, issued ahead by
+        // the compiler as far as the registers allow.
+        const double *__restrict__ w = P.w + c;
+        if (use_brick) {
+            double wn[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) wn[k] = ld_stream(w + (int64_t)k * g.ld);
+            mbar_wait(&full, 0u);     // (the fast kernel owns a single tile: phase 0)
+            const double *bc = brick + B::centre(q, ln);
+            acc = mul(bc[B::off(S::at(0))], wn[0]);
+#pragma unroll
+            for (int k = 1; k < K; ++k) acc = add(acc, mul(bc[B::off(S::at(k))], wn[k]));
+            uc = bc[0];
+        } else {
+            const double *__restrict__ u = P.u + n;
+            const bool ghost = HALO && side;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const Off o = S::at(k);
+                const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
+                                    (int64_t)o.r * g.s_row + o.l;
+                // ghost values were stored by a peer GPU: not through the non-coherent path
+                const double uk = ghost ? __ldcg(u + off) : __ldg(u + off);
+                const double pk = mul(uk, ld_stream(w + (int64_t)k * g.ld));
+                acc = k == 0 ? pk : add(acc, pk);
+                if (o.p == 0 && o.r == 0 && o.l == 0) uc = uk;
+            }
+            if (!SLOW) mbar_wait(&full, 0u);
+        }
+    }
+    const double diff = acc - uc;      // u_tr - u of this node (ECG)
+
+    bool handled = true;
+    if (SLOW) {
+        if (wact) {
+            StateIO io{P.state + c, g.ld, act};
+            M::ionic_ref(uc, acc, io, A.c);
+        }
+    } else {
+        StateIOTma<M> io{staged + (c - (int64_t)c0a), P.state + c, g.ld, act};
+        const bool ok = !wact || M::fast_ok(uc, io, A.c);
+        if (__syncthreads_or(!ok)) {
+            // not this kernel's business: the reference-statement kernel redoes the tile
+            if (tid == 0) P.defer_list[atomicAdd(P.defer_ctr, 1u)] = t;
+            handled = false;
+        } else if (wact) {
+            M::ionic_fastpath(uc, acc, io, A.c);
+        }
+    }
+    if (!handled) return;
+
+    if (act) {
+        if (TRACK && P.do_act) {
+            // ActivationTime{2,3}DTracker._track on the updated nodes (strict >); nodes the
+            // solver never updates are covered by the full-grid samples (sim.cu)
+            const double a = P.act_t[n];
+            if (a < 0 && uc > P.act_thr) P.act_t[n] = P.t;
+        }
+        P.u_new[n] = acc;
+        if (HALO && side) side->peer_dst[n - side->first] = acc;
+    }
+
+    if (HALO && side) {
+        // publish: all of this block's peer stores are visible system-wide before the
+        // block is counted; the last block of the side raises the neighbour's flag
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned done = atomicAdd(side->counter, 1u) + 1u;
+            if (done == side->n_blocks) {
+                *side->counter = 0;
+                __threadfence_system();
+                st_release_sys(side->peer_flag, P.halo.epoch + 1u);
+            }
+        }
+    }
+
+    if (TRACK && P.do_ecg) {
+        // ECG{2,3}DTracker: per lead sum over updated nodes of (u_tr - u) / (d * dr),
+        // d = squared index distance, d == 0 skipped; deterministic order (warp tree ->
+        // fixed-order sum over warps -> per-tile partial, summed by ecg_finalize)
+        const int lane = tid & 31, warp = tid >> 5;
+        double ci = 0, cj = 0, ck = 0;
+        if (act) {
+            if (DIM == 3) {
+                const int64_t i = n / g.s_plane, rem = n % g.s_plane;
+                ci = (double)(i + g.slow_offset);
+                cj = (double)(rem / g.s_row); ck = (double)(rem % g.s_row);
+            } else {
+                ci = (double)(n / g.s_row + g.slow_offset); cj = (double)(n % g.s_row);
+            }
+        }
+        for (int l0 = 0; l0 < P.n_leads; l0 += 32) {
+            const int nl = min(32, P.n_leads - l0);
+            for (int l = 0; l < nl; ++l) {
+                const double x = __ldg(P.ecg_coords + 3 * (l0 + l));
+                const double y = __ldg(P.ecg_coords + 3 * (l0 + l) + 1);
+                const double z = __ldg(P.ecg_coords + 3 * (l0 + l) + 2);
+                double v = 0.0;
+                if (act) {
+                    const double d = (DIM == 3)
+                        ? (x - ci) * (x - ci) + (y - cj) * (y - cj) + (z - ck) * (z - ck)
+                        : (x - ci) * (x - ci) + (y - cj) * (y - cj) + z * z;
+                    if (d > 0) v = diff / (d * P.dr);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp][l] = v;
+            }
+            __syncthreads();
+            if (tid < nl) {
+                double sum = 0.0;
+                for (int wq = 0; wq < WARPS_PER_BLOCK; ++wq) sum += red[wq][tid];
+                P.ecg_partial[(int64_t)t * P.n_leads + l0 + tid] = sum;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <class M, int DIM, int ST, bool TRACK, bool HALO, bool BRICK, bool SLOW>
+__global__ void __launch_bounds__(BLOCK_THREADS, (SLOW ? 1 : M::MIN_BLOCKS))
+step_kernel_tile(const __grid_constant__ StepArgs<M> A, const __grid_constant__ CUtensorMap tmap)
+{
+    const StepCommon &P = A.k;
+    const int tid = threadIdx.x;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    double *const brick = reinterpret_cast<double *>(dyn_smem);                       // [Brick::N]
+    double *const staged = reinterpret_cast<double *>(dyn_smem + (BRICK ? BRICK_BYTES_MAX : 0));
+    __shared__ uint64_t full;
+    __shared__ double red[TRACK ? WARPS_PER_BLOCK : 1][32];
+
+    if (!SLOW) {
+        // the fast kernel: block b owns tile b
+#ifdef FWB_EXP_SMEM
+        exp_table_to_smem();
+#endif
+        if (tid == 0) {
+            mbar_init(&full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        tile_body<M, DIM, ST, TRACK, HALO, BRICK, SLOW>(A, &tmap, blockIdx.x, brick, staged, &full, red);
+    } else {
+        // the reference-statement kernel walks the list of handed-over tiles (normally empty)
+        const uint32_t n_def = *reinterpret_cast<volatile const uint32_t *>(P.defer_ctr);
+        for (uint32_t it = blockIdx.x; it < n_def; it += gridDim.x) {
+            tile_body<M, DIM, ST, TRACK, HALO, BRICK, SLOW>(A, &tmap, P.defer_list[it], brick, staged,
+                                                            &full, red);
+            __syncthreads();
+        }
+        // the last block to finish empties the list for the next step
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(P.defer_ctr + 1, 1u) + 1u;
+            if (done == gridDim.x) {
+                P.defer_ctr[0] = 0;
+                P.defer_ctr[1] = 0;
+                __threadfence();
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
 // step_kernel_tma: persistent, TMA-fed variant (see the header comment)
 // ---------------------------------------------------------------------------
 
@@ -646,6 +984,27 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
 
 inline int64_t step_blocks(const Grid &g) { return (g.n_work + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property of a kernel: set
+// it once per (kernel, device), whichever thread or GPU the caller drives
+inline int ensure_dyn_smem_impl(const void *kern, size_t bytes)
+{
+    // keyed by the kernel's ADDRESS (instantiations of one template share a pointer type)
+    static std::mutex mu;
+    static std::map<const void *, unsigned long long> done;   // bit d: set on device d
+    int dev = 0;
+    FWB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long &mask = done[kern];
+    if (dev < 64 && ((mask >> dev) & 1ull)) return 0;
+    FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev < 64) mask |= 1ull << dev;
+    return 0;
+}
+template <class Kern> static int ensure_dyn_smem(Kern kern, size_t bytes)
+{
+    return ensure_dyn_smem_impl(reinterpret_cast<const void *>(kern), bytes);
+}
+
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
 static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
 {
@@ -655,27 +1014,30 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     const int64_t blocks = step_blocks(k.g);
     if (blocks <= 0) return 0;
     if constexpr (stage_state<M>()) {
-        if (k.tile_base && k.records) {
-            // everything by TMA when three such blocks fit an SM and no ECG sample is due
-            // (its reduction buffer would cost the third block); else the state rows only
-            constexpr int K = Stencil<DIM, ST>::K;
-            constexpr bool FULL = !TRACK && stage_weights<M>() && StageCfg<M, K, 2>::FIT >= 3;
-            if constexpr (FULL) {
-                auto kern = step_kernel<M, DIM, ST, TRACK, HALO, 2>;
-                static bool attr = false;
-                if (!attr) {
-                    FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)StageCfg<M, K, 2>::SMEM));
-                    attr = true;
-                }
-                kern<<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 2>::SMEM, s>>>(a);
-                note_step_variant(2);
+        if (k.tile_rec && k.pos_of && k.defer_list && k.defer_ctr) {
+            // compact-lane tile kernel (fast path only) + the reference-statement kernel for
+            // the tiles it hands over (normally none: that launch returns at once)
+            CUtensorMap none;
+            memset(&none, 0, sizeof(none));
+            const bool brick = k.brick && k.tmap_host && (k.g.line & 31) == 0;
+            int rc;
+            if (brick) {
+                auto kern = step_kernel_tile<M, DIM, ST, TRACK, HALO, true, false>;
+                if ((rc = ensure_dyn_smem(kern, TileCfg<M, true>::SMEM))) return rc;
+                kern<<<(unsigned)blocks, BLOCK_THREADS, TileCfg<M, true>::SMEM, s>>>(
+                    a, *reinterpret_cast<const CUtensorMap *>(k.tmap_host));
+                note_step_variant(5);
             } else {
-                step_kernel<M, DIM, ST, TRACK, HALO, 1>
-                    <<<(unsigned)blocks, BLOCK_THREADS, StageCfg<M, K, 1>::SMEM, s>>>(a);
-                note_step_variant(1);
+                auto kern = step_kernel_tile<M, DIM, ST, TRACK, HALO, false, false>;
+                if ((rc = ensure_dyn_smem(kern, TileCfg<M, false>::SMEM))) return rc;
+                kern<<<(unsigned)blocks, BLOCK_THREADS, TileCfg<M, false>::SMEM, s>>>(a, none);
+                note_step_variant(4);
             }
-            FWB_KERNEL_CHECK("step_kernel (staged)");
+            FWB_KERNEL_CHECK("step_kernel_tile");
+            const int64_t slow_blocks = blocks < 296 ? blocks : 296;
+            step_kernel_tile<M, DIM, ST, TRACK, HALO, false, true>
+                <<<(unsigned)slow_blocks, BLOCK_THREADS, 0, s>>>(a, none);
+            FWB_KERNEL_CHECK("step_kernel_tile (reference statement)");
             return 0;
         }
     }
@@ -685,22 +1047,205 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// step_kernel_small: tissues of a few thousand nodes (the README quick start is 100 x 100)
+//
+// At this size one time step is ~2 us of launch latency around ~0.2 us of work.  This kernel
+// runs MANY steps in one launch: a single thread-block cluster (<= 8 CTAs x 1024 threads,
+// distributed over 8 SMs) owns the whole tissue, every thread keeps the state of its (<= 4)
+// nodes in shared memory for the whole run, reads the stencil's u operands from the L2-
+// resident ping-pong buffers (ld.global.cg: another CTA of the cluster wrote them), and the
+// steps are separated by a hardware cluster barrier (release / acquire at cluster scope)
+// instead of a kernel boundary.  The arithmetic is the per-step kernels' own (same slot
+// order, same Model::ionic), so the result is bit-identical; the host (fwb_sim_run) only
+// uses it for runs of steps in which no stimulus fires and only the activation-time tracker
+// samples.  t advances by the same repeated fp64 addition as on the host.
+// ---------------------------------------------------------------------------
+struct SmallArgs {
+    const int32_t *node_of;    // [n_myo] flat node of each compact index
+    double *buf[2];            // the two u buffers; buf[cur] is u at the first step
+    int cur;
+    int n_steps;
+    int npt;                   // nodes per thread
+    int64_t n_myo;
+    int64_t step0;
+    double t0;
+    // activation-time tracker (at most one, already primed)
+    double *act_t;
+    double act_thr, act_start, act_end;
+    int64_t act_every;
+};
+constexpr int SMALL_THREADS = 1024, SMALL_MAX_CTAS = 8, SMALL_MAX_NPT = 4;
+
+// state of one node in shared memory: slot q of node-slot j of thread tid
+struct StateIOSmem {
+    double *s;                 // &smem[(j * NS + 0) * SMALL_THREADS + tid]
+    __device__ __forceinline__ double ld(int q) const { return s[q * SMALL_THREADS]; }
+    __device__ __forceinline__ void st(int q, double v) const { s[q * SMALL_THREADS] = v; }
+};
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <class M, int DIM, int ST>
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+step_kernel_small(const __grid_constant__ StepArgs<M> A, const __grid_constant__ SmallArgs sa)
+{
+    using S = Stencil<DIM, ST>;
+    constexpr int K = S::K;
+    constexpr int NS = M::NS > 0 ? M::NS : 1;
+    const StepCommon &P = A.k;
+    const Grid &g = P.g;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double *const st_sm = reinterpret_cast<double *>(dyn_smem);      // [npt][NS][SMALL_THREADS]
+    const int tid = threadIdx.x;
+    const int64_t T = (int64_t)gridDim.x * SMALL_THREADS;
+    const int64_t gt = (int64_t)blockIdx.x * SMALL_THREADS + tid;
+    exp_table_to_smem();
+    __syncthreads();
+
+    // state -> shared memory
+    for (int j = 0; j < sa.npt; ++j) {
+        const int64_t c = gt + j * T;
+        if (c < sa.n_myo) {
+#pragma unroll
+            for (int q = 0; q < M::NS; ++q)
+                st_sm[(j * NS + q) * SMALL_THREADS + tid] = P.state[(int64_t)q * g.ld + c];
+        }
+    }
+
+    double t = sa.t0;
+    int cur = sa.cur;
+    for (int it = 0; it < sa.n_steps; ++it) {
+        const double *__restrict__ u = sa.buf[cur];
+        double *__restrict__ u_new = sa.buf[cur ^ 1];
+        const bool do_act = sa.act_t && !(sa.act_start > t || t > sa.act_end) &&
+                            (sa.step0 + it) % sa.act_every == 0;
+        for (int j = 0; j < sa.npt; ++j) {
+            const int64_t c = gt + j * T;
+            if (c >= sa.n_myo) break;
+            const int64_t n = __ldg(sa.node_of + c);
+            const double *__restrict__ up = u + n;
+            const double *__restrict__ w = P.w + c;
+            double un[K], wn[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const Off o = S::at(k);
+                const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
+                                    (int64_t)o.r * g.s_row + o.l;
+                un[k] = __ldcg(up + off);
+                wn[k] = __ldg(w + (int64_t)k * g.ld);
+            }
+            double acc = mul(un[0], wn[0]);
+#pragma unroll
+            for (int k = 1; k < K; ++k) acc = add(acc, mul(un[k], wn[k]));
+            double uc = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (S::at(k).p == 0 && S::at(k).r == 0 && S::at(k).l == 0) uc = un[k];
+            if (do_act) {
+                const double a = sa.act_t[n];
+                if (a < 0 && uc > sa.act_thr) sa.act_t[n] = t;
+            }
+            StateIOSmem io{st_sm + (j * NS) * SMALL_THREADS + tid};
+            M::ionic(uc, acc, io, A.c);
+            __stcg(u_new + n, acc);
+        }
+        t += A.c.dt;
+        cur ^= 1;
+        cluster_sync_all();
+    }
+
+    // state back to the compact rows
+    for (int j = 0; j < sa.npt; ++j) {
+        const int64_t c = gt + j * T;
+        if (c < sa.n_myo) {
+#pragma unroll
+            for (int q = 0; q < M::NS; ++q)
+                if ((M::WRITE_MASK >> q) & 1u)
+                    P.state[(int64_t)q * g.ld + c] = st_sm[(j * NS + q) * SMALL_THREADS + tid];
+        }
+    }
+}
+
+template <class M, int DIM, int ST>
+static int launch_small_one(const StepCommon &k, const void *consts, const SmallArgs &sa,
+                            cudaStream_t s)
+{
+    StepArgs<M> a;
+    a.k = k;
+    a.c = *reinterpret_cast<const typename M::Consts *>(consts);
+    const int64_t per_cta = (int64_t)SMALL_THREADS * sa.npt;
+    int ctas = (int)((sa.n_myo + per_cta - 1) / per_cta);
+    if (ctas < 1) ctas = 1;
+    if (ctas > SMALL_MAX_CTAS) { set_error("step_kernel_small: tissue too large"); return FWB_E_UNSUPPORTED; }
+    constexpr int NS = M::NS > 0 ? M::NS : 1;
+    const size_t smem = (size_t)sa.npt * NS * SMALL_THREADS * sizeof(double);
+    auto kern = step_kernel_small<M, DIM, ST>;
+    int rc;
+    if ((rc = ensure_dyn_smem(kern, (size_t)SMALL_MAX_NPT * NS * SMALL_THREADS * sizeof(double)))) return rc;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(SMALL_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FWB_CUDA(cudaLaunchKernelEx(&cfg, kern, a, sa));
+    note_step_variant(6);
+    return 0;
+}
+
+template <class M>
+static int launch_small_model(int dim, int stencil, const StepCommon &k, const void *consts,
+                              const SmallArgs &sa, cudaStream_t s)
+{
+    if constexpr (M::NS <= 4) {
+        if (dim == 2 && stencil == FWB_STENCIL_ISO) return launch_small_one<M, 2, FWB_STENCIL_ISO>(k, consts, sa, s);
+        if (dim == 2 && stencil == FWB_STENCIL_ANISO) return launch_small_one<M, 2, FWB_STENCIL_ANISO>(k, consts, sa, s);
+        if (dim == 3 && stencil == FWB_STENCIL_ISO) return launch_small_one<M, 3, FWB_STENCIL_ISO>(k, consts, sa, s);
+        if (dim == 3 && stencil == FWB_STENCIL_ANISO) return launch_small_one<M, 3, FWB_STENCIL_ANISO>(k, consts, sa, s);
+    }
+    set_error("step_kernel_small: unsupported model / stencil");
+    return FWB_E_UNSUPPORTED;
+}
+
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
 static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
 {
     using C = TmaCfg<M, Stencil<DIM, ST>::K>;
     auto kern = step_kernel_tma<M, DIM, ST, TRACK, HALO>;
-    static int resident = 0;      // blocks of this instantiation the device holds at once
-    if (resident == 0) {
-        FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)C::SMEM));
-        int dev = 0, sms = 0, per_sm = 0;
-        FWB_CUDA(cudaGetDevice(&dev));
-        FWB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS,
-                                                               C::SMEM));
-        if (per_sm < 1) { set_error("step_kernel_tma does not fit on an SM"); return FWB_E_UNSUPPORTED; }
-        resident = sms * per_sm;
+    // blocks of this instantiation each device holds at once (per device: a process may
+    // drive several GPUs, from several threads)
+    static std::mutex mu;
+    static int resident_of[64] = {0};
+    int dev = 0;
+    FWB_CUDA(cudaGetDevice(&dev));
+    int resident = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || resident_of[dev] == 0) {
+            FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)C::SMEM));
+            int sms = 0, per_sm = 0;
+            FWB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            FWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS,
+                                                                   C::SMEM));
+            if (per_sm < 1) { set_error("step_kernel_tma does not fit on an SM"); return FWB_E_UNSUPPORTED; }
+            resident = sms * per_sm;
+            if (dev < 64) resident_of[dev] = resident;
+        } else {
+            resident = resident_of[dev];
+        }
     }
     StepArgs<M> a;
     a.k = k;
@@ -761,11 +1306,15 @@ template <class M> static bool derive_model(const double *p, double dt, void *ou
 typedef int (*LaunchFn)(int dim, int stencil, bool track, const StepCommon &k,
                         const void *consts, cudaStream_t s);
 typedef bool (*DeriveFn)(const double *p, double dt, void *consts_out);
+struct SmallArgs;
+typedef int (*LaunchSmallFn)(int dim, int stencil, const StepCommon &k, const void *consts,
+                             const SmallArgs &sa, cudaStream_t s);
 struct ModelEntry {
     int n_state, n_params;
     uint32_t read_mask, write_mask;
     LaunchFn launch;
     DeriveFn derive;
+    LaunchSmallFn launch_small;    // multi-step cluster kernel for tiny tissues (light models)
 };
 constexpr int CONSTS_BYTES = 1024;
 
@@ -774,6 +1323,7 @@ const ModelEntry *model_entry(int model);   // NULL if unknown; index FWB_N_MODE
 #define FWB_DEFINE_MODEL_ENTRY(NAME, M)                                                   \
     static_assert(sizeof(M::Consts) <= fwb::CONSTS_BYTES, "Consts too large");            \
     extern const fwb::ModelEntry NAME = {M::NS, M::NP, M::READ_MASK, M::WRITE_MASK,       \
-                                         &fwb::launch_model<M>, &fwb::derive_model<M>};
+                                         &fwb::launch_model<M>, &fwb::derive_model<M>,     \
+                                         &fwb::launch_small_model<M>};
 
 }  // namespace fwb

@@ -168,6 +168,17 @@ class Engine:
                                        _ptr(self.records), ctypes.byref(n_myo), _stream()),
               "fwb_order_compact")
         assert int(n_myo.value) == self.n_myo
+        # tile view for the compact-lane tile kernel: per tile {compact base, count, origin
+        # chunk, boundary}, per compact node its position inside the tile
+        self.tile_rec = torch.zeros((max(self.n_work // 8, 1), 4), dtype=torch.int32,
+                                    device=self.device)
+        self.pos_of = torch.zeros(self.ld, dtype=torch.uint8, device=self.device)
+        check(self.L.fwb_order_tiles(self.dim, shp, int(halo[0]), int(halo[1]),
+                                     self.halo_blocks[0], self.halo_blocks[1],
+                                     _ptr(self.chunk_bits), _ptr(self.chunk_base),
+                                     _ptr(self.worklist), self.n_work, _ptr(self.tile_base),
+                                     _ptr(self.tile_rec), _ptr(self.pos_of), _stream()),
+              "fwb_order_tiles")
 
     # ---- weights --------------------------------------------------------
     def compute_weights(self, stencil, conductivity, fibers, D_al, D_ac, D_model, dt, dr):
@@ -348,6 +359,8 @@ class Engine:
         if use_tma:
             check(self.L.fwb_sim_set_tile_base(sim, _ptr(self.tile_base), _ptr(self.records)),
                   "fwb_sim_set_tile_base")
+            check(self.L.fwb_sim_set_tiles(sim, _ptr(self.tile_rec), _ptr(self.pos_of)),
+                  "fwb_sim_set_tiles")
 
     def destroy_sim(self):
         if self.sim:
@@ -376,6 +389,9 @@ class Engine:
 
     def launch_count(self):
         return int(self.L.fwb_sim_launch_count(self.sim))
+
+    def device_steps(self):
+        return int(self.L.fwb_sim_device_steps(self.sim))
 
     def keep(self, t):
         self._keep.append(t)

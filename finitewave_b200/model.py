@@ -64,6 +64,7 @@ class CardiacModel:
         self._engine = None
         self._engine_key = None
         self.gpu_launches = 0       # kernels launched by the last run()
+        self.gpu_steps = 0          # time steps the device kernels advanced in the last run()
 
     # ------------------------------------------------------------------ engine
     def _engine_for(self, tissue):
@@ -231,6 +232,7 @@ class CardiacModel:
     def _register_native(self):
         """(Re-)register the built-in stimuli and trackers with the device runner."""
         eng, live = self._engine, self._live
+        live["registered"] = True
         _lib.check(eng.L.fwb_sim_clear_stims(eng.sim))
         _lib.check(eng.L.fwb_sim_clear_trackers(eng.sim))
         eng._keep = []
@@ -243,7 +245,13 @@ class CardiacModel:
             tr._register(eng, self, remaining // max(1, int(tr.step)) + 2)
 
     def _collect_native(self):
+        """Samples and stimulus flags from the device into the host objects -- once per
+        registration (a Command that calls compute_weights() right after the loop has
+        collected must not append the same samples twice)."""
         eng, live = self._engine, self._live
+        if not live.get("registered") or not eng.sim:
+            return
+        live["registered"] = False
         eng.synchronize()
         for tr in live["native_tr"]:
             tr._collect(eng)
@@ -316,6 +324,7 @@ class CardiacModel:
         self._upload()
         self._register_native()
         launches0 = eng.launch_count()
+        dsteps0 = eng.device_steps()
         eng.set_time(self.t, self.step)
 
         bar = None
@@ -424,6 +433,7 @@ class CardiacModel:
             if hasattr(tr, "_finish"):
                 tr._finish()                  # streamed frames are complete on return
         self.gpu_launches = eng.launch_count() - launches0
+        self.gpu_steps = eng.device_steps() - dsteps0
         self._live = None
 
     def _save_async(self, host_view_valid):

@@ -20,7 +20,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from ._lib import check
+from ._lib import check, shape_arr
 
 
 class Tracker:
@@ -149,8 +149,35 @@ class ECG2DTracker(Tracker):
         self.ecg = []
         self._taken = 0
 
+    def calc_ecg(self):
+        """The ECG signal of the model's current potential (reference: ecg_2d_tracker.py:61-79,
+        ecg_3d_tracker.py:51-69), evaluated on the device by the stand-alone entry fwb_ecg:
+        ``self.u_tr`` becomes W u on the myocytes, the return value is one number per lead."""
+        model = self.model
+        eng = getattr(model, "_engine", None)
+        if eng is None or eng.weights is None:
+            raise RuntimeError("calc_ecg() needs an initialised model (device weights)")
+        dev = eng.device
+        u = torch.from_numpy(np.ascontiguousarray(model.u, dtype=np.float64)).to(dev)
+        u_tr = torch.zeros_like(u)
+        coords = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(self.measure_coords),
+                                                       dtype=np.float64)).to(dev)
+        if coords.shape[1] != 3:
+            raise ValueError("measure_coords must have 3 components (x, y, z) per lead")
+        out = torch.zeros(coords.shape[0], dtype=torch.float64, device=dev)
+        vp = ctypes.c_void_p
+        check(eng.L.fwb_ecg(eng.dim, eng.stencil, shape_arr(eng.shape), vp(eng.chunk_bits.data_ptr()),
+                            vp(eng.chunk_base.data_ptr()), eng.ld, vp(eng.worklist.data_ptr()),
+                            eng.n_work, vp(u.data_ptr()), vp(u_tr.data_ptr()),
+                            vp(eng.weights.data_ptr()), vp(coords.data_ptr()), int(coords.shape[0]),
+                            float(model.dr), vp(out.data_ptr()),
+                            vp(torch.cuda.current_stream().cuda_stream)), "fwb_ecg")
+        self.u_tr = u_tr.cpu().numpy()
+        return out.cpu().numpy()
+
     def _track(self):
-        raise NotImplementedError("ECG is evaluated inside the device step kernel")
+        """By hand (the run loop samples inside the fused step kernel instead)."""
+        self.ecg.append(self.calc_ecg())
 
     def _register(self, engine, model, max_samples):
         self._coords_dev = engine.keep(torch.from_numpy(np.ascontiguousarray(

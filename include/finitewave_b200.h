@@ -138,6 +138,20 @@ FWB_API int fwb_order_compact(const uint32_t *chunk_bits, int64_t n_chunks,
                       uint32_t *tile_base, uint32_t *records, int64_t *n_myo,
                       fwb_stream_t stream);
 
+/* Tile view of the work list for the compact-lane tile kernel (LR91 / TP06 / Courtemanche):
+ * since a listed tile is a whole SPATIAL tile (8 work-list entries, -1 where a chunk holds no
+ * tissue), a block can number the tile's nodes compactly (thread r <-> r-th updated node of
+ * the tile: no idle lanes on sparse tissue) and fetch the tile's u neighbourhood as one brick.
+ *   tile_rec  [n_work/8][4]  out: {compact index of the tile's first node, node count,
+ *                            chunk id of the tile's slot 0, 1 if slab-boundary tile}
+ *   pos_of    [ld] uint8     out: per compact node, (slot << 5) | lane inside its tile
+ * call after fwb_order_compact with its tile_base; n_lo/n_hi_blocks from fwb_build_worklist */
+FWB_API int fwb_order_tiles(int dim, const int64_t *shape, int halo_lo, int halo_hi,
+                    int64_t n_lo_blocks, int64_t n_hi_blocks,
+                    const uint32_t *chunk_bits, const uint32_t *chunk_base,
+                    const int32_t *worklist, int64_t n_work, const uint32_t *tile_base,
+                    uint32_t *tile_rec, uint8_t *pos_of, fwb_stream_t stream);
+
 /* dense (*shape) <-> compact [ld] conversions of one array.
  * gather:  compact[c] = dense[n]            for update nodes
  * scatter: dense[n] = update ? compact[c] : fill   (all n < n_nodes)        */
@@ -275,6 +289,10 @@ FWB_API int fwb_sim_current_buffer(const FwbSim *sim);
  * records from fwb_order_compact (NULL = one-block-per-tile kernel with plain loads) */
 FWB_API int fwb_sim_set_tile_base(FwbSim *sim, const uint32_t *tile_base,
                           const uint32_t *records);
+/* enable the compact-lane tile kernel for LR91 / TP06 / Courtemanche: tile_rec and pos_of
+ * from fwb_order_tiles (NULL, NULL = off).  Also builds the tensor maps of the two u buffers
+ * for the kernel's brick copies when the line length is a multiple of 32 nodes. */
+FWB_API int fwb_sim_set_tiles(FwbSim *sim, const uint32_t *tile_rec, const uint8_t *pos_of);
 /* rebind after the caller re-uploaded / recomputed arrays (same sizes) */
 FWB_API int fwb_sim_set_weights(FwbSim *sim, const double *weights);
 FWB_API int fwb_sim_set_params(FwbSim *sim, const double *params, int n_params, double dt);
@@ -325,6 +343,9 @@ FWB_API int64_t fwb_sim_tracker_samples(const FwbSim *sim, int tracker_id);
 FWB_API int fwb_sim_run(FwbSim *sim, int64_t n_steps);
 /* kernel launches issued by fwb_sim_run so far */
 FWB_API int64_t fwb_sim_launch_count(const FwbSim *sim);
+/* time steps advanced by device kernels so far (one launch of the multi-step cluster kernel
+ * for tiny tissues advances many) */
+FWB_API int64_t fwb_sim_device_steps(const FwbSim *sim);
 /* diagnostics: evaluate one of the fast-path math helpers of csrc/fexp.cuh on the device,
  * y[i] = f(x[i]); op 0 fexp, 1 fexp_fast, 2 flog, 3 frcp, 4 frcp3, 5 fsqrt (accuracy tests) */
 FWB_API int fwb_devmath(int op, const double *x, double *y, int64_t n, fwb_stream_t stream);
@@ -383,6 +404,16 @@ FWB_API int fwb_diffuse(int dim, int stencil, const int64_t *shape,
                 const int32_t *worklist, int64_t n_work,
                 const double *u, double *u_new, const double *weights,
                 fwb_stream_t stream);
+/* ECG{2,3}DTracker.calc_ecg() by hand (cpuwave2D/tracker/ecg_2d_tracker.py:61-79 +
+ * compute_ecg :114-152; cpuwave3D/tracker/ecg_3d_tracker.py:51-69, :99-140): u_tr = W u on
+ * the updated nodes (dense buffer, other nodes untouched), then per lead the sum over the
+ * updated nodes of (u_tr - u) / (d * dr), d = squared index distance to the lead (2D: + z^2),
+ * d == 0 skipped -- the fused kernel's deterministic reduction, stand-alone.
+ *   coords [n_leads][3] device, out [n_leads] device */
+FWB_API int fwb_ecg(int dim, int stencil, const int64_t *shape, const uint32_t *chunk_bits,
+            const uint32_t *chunk_base, int64_t ld, const int32_t *worklist, int64_t n_work,
+            const double *u, double *u_tr, const double *weights, const double *coords,
+            int n_leads, double dr, double *out, fwb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -158,6 +158,9 @@ class OracleEngine:
             s.cur ^= 1
             s.launches += 1
 
+    def device_steps(self):
+        return self.launch_count()
+
     def launch_count(self):
         return self.sim.launches if self.sim else 0
 

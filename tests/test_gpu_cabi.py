@@ -167,11 +167,13 @@ def test_unknown_model_or_missing_fibers_raise(env):
         lib.check(rc, "fwb_sim_create")
 
 
-def test_public_api_runs_the_tma_kernels():
+def test_public_api_runs_the_tma_kernels(monkeypatch):
     """The host API lays the tissue out tile-ordered, so the step must take the TMA paths:
-    the persistent ring for the HBM-bound models (variant 3), staged state + weight rows for
-    the FP64-bound ones (2; state rows only, 1, on steps that sample the activation tracker).
-    Guards against silently falling back to the plain-load kernel (variant 0)."""
+    the persistent ring for the HBM-bound models (variant 3; tissues of a few thousand nodes
+    run many steps per launch in the cluster kernel instead, variant 6), the compact-lane
+    tile kernel for the FP64-bound ones (4; 5 when the line length is a multiple of 32 nodes
+    and the u brick comes by tensor TMA).  Guards against silently falling back to the
+    plain-load kernel (variant 0)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
@@ -179,14 +181,32 @@ def test_public_api_runs_the_tma_kernels():
     from finitewave_b200 import _lib
     from tests.cases import build_model, case_by_name
     L = _lib.lib()
-    for name, want in (("c2_fk2d_aniso_fib", 3), ("c3_ms3d_iso_focal", 3),
-                       ("tp06_3d_iso_current", 2), ("lr91_2d_iso", 2),
-                       ("court2d_iso_current", 2), ("c5_tp06_3d_aniso_slab", 1)):
+    for name, want in (("c2_fk2d_aniso_fib", 6), ("c3_ms3d_iso_focal", 6),
+                       ("tp06_3d_iso_current", 4), ("lr91_2d_iso", 4),
+                       ("court2d_iso_current", 4), ("c5_tp06_3d_aniso_slab", 4)):
         case = dict(case_by_name(name))
         case["t_max"] = 0.2
         model, _ = build_model(fw, case)
         model.run()
         assert L.fwb_last_step_variant() == want, (name, L.fwb_last_step_variant())
+    # without the multi-step kernel the light models take the persistent ring
+    monkeypatch.setenv("FWB_NO_SMALL_KERNEL", "1")
+    for name in ("c2_fk2d_aniso_fib", "c3_ms3d_iso_focal"):
+        case = dict(case_by_name(name))
+        case["t_max"] = 0.2
+        model, _ = build_model(fw, case)
+        model.run()
+        assert L.fwb_last_step_variant() == 3, (name, L.fwb_last_step_variant())
+    # a tiled grid (line length 64): TP06 with the u brick by tensor TMA
+    tissue = fw.CardiacTissue3D([6, 12, 64])
+    model = fw.TP063D()
+    model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 0.05, False
+    model.cardiac_tissue = tissue
+    seq = fw.StimSequence()
+    seq.add_stim(fw.StimVoltageCoord3D(0, -20, 1, 5, 1, 11, 1, 6))
+    model.stim_sequence = seq
+    model.run()
+    assert L.fwb_last_step_variant() == 5, L.fwb_last_step_variant()
 
 
 def test_device_math_helpers_accuracy():

@@ -144,3 +144,27 @@ def test_public_track_tip_line_and_cross_threshold():
         activated = np.where(want, True, activated)
         activated = np.where((model.u < 0.4) & activated, False, activated)
         assert np.array_equal(lat.cross_threshold(), want)
+
+
+def test_calc_ecg_by_hand_matches_live_reference():
+    """ECG{2,3}DTracker.calc_ecg() called by hand (stand-alone C-ABI entry fwb_ecg) on the
+    final state of the two ECG cases, against the live reference's own calc_ecg() on the
+    same potential (tests/golden/make_calc_ecg_golden.py): lead values to 1e-12 (the
+    reference's reduction order is unspecified), u_tr = W u bit for bit."""
+    import finitewave_b200 as fw
+    from tests.cases import build_model, case_by_name, max_rel_err
+    from tests.golden.make_calc_ecg_golden import CASES as ECG_CASES
+    g = np.load(GOLDEN / "calc_ecg.npz")
+    for name in ECG_CASES:
+        case = dict(case_by_name(name))
+        model, trackers = build_model(fw, case)
+        model.initialize()
+        tr = [t for _, t in trackers if hasattr(t, "calc_ecg")][0]
+        model.u[...] = g[name + "__u"]
+        ecg = tr.calc_ecg()
+        assert max_rel_err(ecg, g[name + "__ecg"]) <= 1e-12, name
+        want = g[name + "__u_tr"]
+        myo = model.cardiac_tissue.mesh == 1
+        assert np.array_equal(tr.u_tr[myo], want[myo]), name
+        tr._track()                      # by hand: appends one sample
+        assert len(tr.output) == 1 and max_rel_err(tr.output[0], g[name + "__ecg"]) <= 1e-12
