@@ -103,6 +103,8 @@ def _sig(L):
     L.fwb_ipc_get_handle.argtypes = [p, p]
     L.fwb_ipc_open_handle.argtypes = [p, POINTER(c_void_p)]
     L.fwb_ipc_close_handle.argtypes = [p]
+    L.fwb_enable_peer_access.argtypes = [c_int, c_int]
+    L.fwb_multi_run.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64]
     L.fwb_sim_set_halo.argtypes = [p, p, p, p, c_int64, p, c_int64, p, p, c_int64, p, c_int64]
     L.fwb_sim_set_slow_offset.argtypes = [p, c_int64]
     L.fwb_sim_halo_sync.argtypes = [p]

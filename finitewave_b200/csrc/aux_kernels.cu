@@ -393,6 +393,29 @@ static inline unsigned warp_blocks(int64_t n_chunks, int threads)
     return (unsigned)((n_chunks * 32 + threads - 1) / threads);
 }
 
+// CUDA loads a kernel lazily at its first launch, and that load can wait for the device to go
+// idle.  In a slab run a kernel of one slab may be spinning on a flag that only a later launch
+// of its neighbour raises -- if that launch is a kernel's FIRST (two slabs in one process share
+// the context), the load never returns.  Everything the step loop can launch is therefore
+// loaded up front when a halo is wired (cudaFuncGetAttributes forces the load).
+template <class K> static int preload_one(K kern)
+{
+    cudaFuncAttributes a;
+    FWB_CUDA(cudaFuncGetAttributes(&a, kern));
+    return 0;
+}
+int preload_aux_kernels()
+{
+    int rc;
+    if ((rc = preload_one(stim_box_kernel))) return rc;
+    if ((rc = preload_one(stim_nodes_kernel))) return rc;
+    if ((rc = preload_one(act_kernel))) return rc;
+    if ((rc = preload_one(ecg_finalize_kernel))) return rc;
+    if ((rc = preload_one(point_gather_kernel))) return rc;
+    if ((rc = preload_one(halo_wait_kernel))) return rc;
+    return 0;
+}
+
 int launch_stim_box(double *u, const uint8_t *tissue, const StimBox &b, int mode, double value,
                     double dt_value, int has_u_max, double u_max, cudaStream_t s)
 {
@@ -662,6 +685,23 @@ extern "C" int fwb_ipc_open_handle(const void *handle, void **ptr_out)
 extern "C" int fwb_ipc_close_handle(void *ptr)
 {
     if (ptr) FWB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+// slabs of ONE process on several devices: let kernels on `device` store into / read flags in
+// memory of `peer` (NVLink peer mapping); a pair that is already enabled is not an error
+extern "C" int fwb_enable_peer_access(int device, int peer)
+{
+    if (device == peer) return 0;
+    int can = 0;
+    FWB_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) { set_error("device %d cannot access device %d", device, peer); return FWB_E_UNSUPPORTED; }
+    int prev = 0;
+    FWB_CUDA(cudaGetDevice(&prev));
+    FWB_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fwb::cuda_fail(e, "cudaDeviceEnablePeerAccess");
     return 0;
 }
 

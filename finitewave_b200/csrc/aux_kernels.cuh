@@ -22,6 +22,7 @@ int launch_ecg_finalize(const double *partial, int64_t n_blocks, int n_leads, do
                         cudaStream_t s);
 int launch_halo_wait(const unsigned *flag_lo, const unsigned *flag_hi, unsigned epoch,
                      cudaStream_t s);
+int preload_aux_kernels();
 int launch_point_gather(const int64_t *items, const double *fill, int n_items, const double *u,
                         const double *state, int64_t ld, double *out, cudaStream_t s);
 

@@ -111,6 +111,7 @@ struct FwbSim {
     double t;
     int64_t step;
     cudaStream_t stream;
+    int device;                // the device the simulation was created on
     alignas(16) unsigned char consts[CONSTS_BYTES];
     std::vector<Stim> stims;
     std::vector<Tracker> trackers;
@@ -200,6 +201,8 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
     s->weights = weights; s->state = state;
     s->dt = dt; s->t = 0.0; s->step = 0;
     s->stream = (cudaStream_t)stream;
+    s->device = 0;
+    cudaGetDevice(&s->device);
     memset(s->consts, 0, sizeof(s->consts));
     if (!e->derive(params, dt, s->consts)) {
         delete s;
@@ -357,6 +360,12 @@ extern "C" int fwb_sim_set_halo(FwbSim *s, uint32_t *local_flags,
         return FWB_E_UNSUPPORTED;
     }
     s->halo_on = lo || hi;
+    if (s->halo_on) {
+        // nothing may be loaded lazily while a neighbour's kernel spins on one of our flags
+        int rc = preload_aux_kernels();
+        if (!rc) rc = s->entry->preload(s->dim, s->stencil == FWB_STENCIL_SYM ? FWB_STENCIL_ANISO : s->stencil);
+        if (rc) return rc;
+    }
     s->flags = local_flags;
     s->peer_u[0][0] = peer_lo_u0; s->peer_u[0][1] = peer_lo_u1;
     s->peer_u[1][0] = peer_hi_u0; s->peer_u[1][1] = peer_hi_u1;
@@ -838,5 +847,34 @@ extern "C" int fwb_ecg(int dim, int stencil, const int64_t *shape, const uint32_
                                                true, k, &c, st);
     if (!rc) rc = launch_ecg_finalize(partial, blocks, n_leads, out, st);
     cudaFreeAsync(partial, st);
+    return rc;
+}
+
+// Slabs of ONE process (CardiacModel.run on several GPUs, finitewave_b200/multi.py): advance all
+// of them by n_steps from a single host thread.  The steps are enqueued round-robin in short
+// chunks, so a slab's boundary blocks never wait for a neighbour launch that is still behind
+// a full launch queue, and no host thread is ever in the middle of anything else (an
+// allocation, a free) while a kernel of another slab spins on a flag.  Ends with the
+// neighbours' last halo stores landed on every slab (fwb_sim_halo_sync).
+extern "C" int fwb_multi_run(FwbSim **sims, int n_sims, int64_t n_steps, int64_t chunk)
+{
+    if (!sims || n_sims < 1 || n_steps < 0) { set_error("fwb_multi_run: bad argument"); return FWB_E_ARG; }
+    if (chunk < 1) chunk = 8;
+    int prev = 0;
+    FWB_CUDA(cudaGetDevice(&prev));
+    int rc = 0;
+    for (int64_t done = 0; done < n_steps && !rc; done += chunk) {
+        const int64_t k = n_steps - done < chunk ? n_steps - done : chunk;
+        for (int i = 0; i < n_sims && !rc; ++i) {
+            if (!sims[i]) { set_error("fwb_multi_run: NULL simulation"); rc = FWB_E_ARG; break; }
+            cudaSetDevice(sims[i]->device);
+            rc = fwb_sim_run(sims[i], k);
+        }
+    }
+    for (int i = 0; i < n_sims && !rc; ++i) {
+        cudaSetDevice(sims[i]->device);
+        rc = fwb_sim_halo_sync(sims[i]);
+    }
+    cudaSetDevice(prev);
     return rc;
 }

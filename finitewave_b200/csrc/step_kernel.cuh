@@ -1296,6 +1296,46 @@ static int launch_model(int dim, int stencil, bool track, const StepCommon &k,
     return FWB_E_UNSUPPORTED;
 }
 
+// load every instantiation the step loop can launch for (dim, stencil) -- see
+// preload_aux_kernels() in aux_kernels.cu for why
+template <class K> static int preload_kernel(K kern)
+{
+    cudaFuncAttributes a;
+    FWB_CUDA(cudaFuncGetAttributes(&a, kern));
+    return 0;
+}
+template <class M, int DIM, int ST, bool TRACK, bool HALO> static int preload_variants()
+{
+    int rc;
+    if ((rc = preload_kernel(step_kernel<M, DIM, ST, TRACK, HALO, 0>))) return rc;
+    if constexpr (M::USE_TMA) {
+        if ((rc = preload_kernel(step_kernel_tma<M, DIM, ST, TRACK, HALO>))) return rc;
+    }
+    if constexpr (stage_state<M>()) {
+        if ((rc = preload_kernel(step_kernel_tile<M, DIM, ST, TRACK, HALO, true, false>))) return rc;
+        if ((rc = preload_kernel(step_kernel_tile<M, DIM, ST, TRACK, HALO, false, false>))) return rc;
+        if ((rc = preload_kernel(step_kernel_tile<M, DIM, ST, TRACK, HALO, false, true>))) return rc;
+    }
+    return 0;
+}
+template <class M, int DIM, int ST> static int preload_stencil()
+{
+    int rc;
+    if ((rc = preload_variants<M, DIM, ST, false, false>())) return rc;
+    if ((rc = preload_variants<M, DIM, ST, true, false>())) return rc;
+    if ((rc = preload_variants<M, DIM, ST, false, true>())) return rc;
+    if ((rc = preload_variants<M, DIM, ST, true, true>())) return rc;
+    return 0;
+}
+template <class M> static int preload_model(int dim, int stencil)
+{
+    if (dim == 2 && stencil == FWB_STENCIL_ISO) return preload_stencil<M, 2, FWB_STENCIL_ISO>();
+    if (dim == 2 && stencil == FWB_STENCIL_ANISO) return preload_stencil<M, 2, FWB_STENCIL_ANISO>();
+    if (dim == 3 && stencil == FWB_STENCIL_ISO) return preload_stencil<M, 3, FWB_STENCIL_ISO>();
+    if (dim == 3 && stencil == FWB_STENCIL_ANISO) return preload_stencil<M, 3, FWB_STENCIL_ANISO>();
+    return 0;
+}
+
 template <class M> static bool derive_model(const double *p, double dt, void *out)
 {
     return M::derive(p, dt, *reinterpret_cast<typename M::Consts *>(out));
@@ -1315,6 +1355,7 @@ struct ModelEntry {
     LaunchFn launch;
     DeriveFn derive;
     LaunchSmallFn launch_small;    // multi-step cluster kernel for tiny tissues (light models)
+    int (*preload)(int dim, int stencil);   // force-load every step kernel of (dim, stencil)
 };
 constexpr int CONSTS_BYTES = 1024;
 
@@ -1324,6 +1365,6 @@ const ModelEntry *model_entry(int model);   // NULL if unknown; index FWB_N_MODE
     static_assert(sizeof(M::Consts) <= fwb::CONSTS_BYTES, "Consts too large");            \
     extern const fwb::ModelEntry NAME = {M::NS, M::NP, M::READ_MASK, M::WRITE_MASK,       \
                                          &fwb::launch_model<M>, &fwb::derive_model<M>,     \
-                                         &fwb::launch_small_model<M>};
+                                         &fwb::launch_small_model<M>, &fwb::preload_model<M>};
 
 }  // namespace fwb

@@ -263,13 +263,26 @@ class Engine:
         """which: 0/1 = the two u buffers (creation order)."""
         self.ubuf[which].copy_(_as_tensor(host), non_blocking=True)
 
-    def download_dense(self, which, host_out):
-        _as_tensor(host_out).copy_(self.ubuf[which], non_blocking=True)
+    def download_dense(self, which, host_out, rows=None):
+        """rows = (r0, r1): only those slices of axis 0 (host_out has that many)."""
+        src = self.ubuf[which] if rows is None else self.ubuf[which][rows[0]:rows[1]]
+        _as_tensor(host_out).copy_(src, non_blocking=True)
 
-    def upload_state(self, slot, host, fill=None):
+    def needs_allocation(self, n_state):
+        return (self.state is None or self.ubuf[0] is None
+                or self.state.shape != (max(n_state, 1), self.ld))
+
+    def upload_state(self, slot, host, fill=None, rows=None):
         """Dense host array -> compact device row.  With `fill`, also counts (on the
-        device) the non-updated nodes whose value differs from it, see off_fill()."""
-        self._staging().copy_(_as_tensor(host), non_blocking=True)
+        device) the non-updated nodes whose value differs from it, see off_fill().
+        rows = (r0, r1): `host` only covers those slices of axis 0 (a slab's owned range);
+        the other slices (ghost slices: never gathered) are set to `fill`."""
+        if rows is None:
+            self._staging().copy_(_as_tensor(host), non_blocking=True)
+        else:
+            st = self._staging()
+            st.fill_(0.0 if fill is None else float(fill))
+            st[rows[0]:rows[1]].copy_(_as_tensor(host), non_blocking=True)
         check(self.L.fwb_gather_compact(_ptr(self.staging), _ptr(self.state[slot]), self.n_nodes,
                                         _ptr(self.chunk_bits), _ptr(self.chunk_base), _stream()),
               "fwb_gather_compact")
@@ -287,12 +300,16 @@ class Engine:
         init_* constant (after a StateLoader, a Command or a mesh edit).  Synchronises."""
         return [] if self._offfill is None else self._offfill.cpu().tolist()
 
-    def download_state(self, slot, host_out, fill, keep=False):
+    def download_state(self, slot, host_out, fill, keep=False, rows=None):
         """Compact device row -> dense host array.  keep=False refills the nodes the solver
         does not update with `fill` (they cannot have changed); keep=True preserves the
-        values the host array holds there (one extra H2D of the array)."""
+        values the host array holds there (one extra H2D of the array).
+        rows = (r0, r1): host_out covers only those slices of axis 0."""
         if keep:
-            self._staging().copy_(_as_tensor(host_out), non_blocking=True)
+            if rows is None:
+                self._staging().copy_(_as_tensor(host_out), non_blocking=True)
+            else:
+                self._staging()[rows[0]:rows[1]].copy_(_as_tensor(host_out), non_blocking=True)
             check(self.L.fwb_scatter_compact_keep(_ptr(self.state[slot]), _ptr(self.staging),
                                                   self.n_nodes, _ptr(self.chunk_bits),
                                                   _ptr(self.chunk_base), _stream()),
@@ -302,7 +319,8 @@ class Engine:
                                              float(fill), self.n_nodes, _ptr(self.chunk_bits),
                                              _ptr(self.chunk_base), _stream()),
                   "fwb_scatter_compact")
-        _as_tensor(host_out).copy_(self.staging, non_blocking=True)
+        src = self.staging if rows is None else self.staging[rows[0]:rows[1]]
+        _as_tensor(host_out).copy_(src, non_blocking=True)
         # staging is reused by the next call on the same stream: ordering is by stream
 
     # ---- asynchronous checkpoints ---------------------
@@ -372,6 +390,10 @@ class Engine:
             self.destroy_sim()
         except Exception:
             pass
+
+    def set_params(self, p, dt):
+        arr = (ctypes.c_double * len(p))(*[float(x) for x in p])
+        check(self.L.fwb_sim_set_params(self.sim, arr, len(p), float(dt)), "fwb_sim_set_params")
 
     def current(self):
         return self.L.fwb_sim_current_buffer(self.sim)

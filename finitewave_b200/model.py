@@ -65,12 +65,31 @@ class CardiacModel:
         self._engine_key = None
         self.gpu_launches = 0       # kernels launched by the last run()
         self.gpu_steps = 0          # time steps the device kernels advanced in the last run()
+        self.devices = None         # e.g. [0, 1, 2, 3] or "all": slabs on several GPUs (multi.py);
+                                    # None: FWB_DEVICES, else the current device
 
     # ------------------------------------------------------------------ engine
     def _engine_for(self, tissue):
+        """The device side: one Engine, or -- when ``model.devices`` / FWB_DEVICES names
+        several GPUs and the tissue can be cut into slabs -- a MultiEngine (multi.py)."""
+        from . import multi
         shape = tuple(tissue.mesh.shape)
-        if self._engine is None or self._engine.shape != shape:
-            self._engine = Engine(shape)
+        devices = multi.requested_devices(self)
+        want_multi = False
+        if devices:
+            ok, why = multi.supported(self, shape, devices)
+            if ok:
+                want_multi = True
+            elif getattr(self, "_multi_note", None) != why:
+                self._multi_note = why
+                import warnings
+                warnings.warn(f"finitewave_b200: running on one GPU ({why})")
+        cur = self._engine
+        if (cur is None or cur.shape != shape or bool(getattr(cur, "multi", False)) != want_multi
+                or (want_multi and cur.devices != devices)):
+            if cur is not None:
+                cur.destroy_sim()
+            self._engine = multi.MultiEngine(shape, devices) if want_multi else Engine(shape)
         return self._engine
 
     def __deepcopy__(self, memo):
@@ -193,17 +212,13 @@ class CardiacModel:
         """Push u, u_new and every state array from model.__dict__ to the device
         (creating / re-creating the device simulation when needed)."""
         eng = self._engine
-        if (eng.state is None or eng.ubuf[0] is None
-                or eng.state.shape != (max(len(self._STATE), 1), eng.ld)):
+        if eng.needs_allocation(len(self._STATE)):
             eng.destroy_sim()
             eng.allocate(len(self._STATE))
         if not eng.sim:
             eng.create_sim(_lib.MODEL_IDS[self._MODEL], self._param_vector(), self.dt)
         else:
-            p = self._param_vector()
-            arr = (ctypes.c_double * len(p))(*p)
-            _lib.check(eng.L.fwb_sim_set_params(eng.sim, arr, len(p), float(self.dt)),
-                       "fwb_sim_set_params")
+            eng.set_params(self._param_vector(), self.dt)
         cur = eng.current()
         eng.upload_dense(cur, self._host_array("u"))
         eng.upload_dense(cur ^ 1, self._host_array("u_new"))
@@ -222,8 +237,14 @@ class CardiacModel:
         native_stims = bool(self.stim_sequence) and self.stim_sequence.all_native()
         trackers = list(self.tracker_sequence.sequence) if self.tracker_sequence else []
         native_tr = [tr for tr in trackers if getattr(tr, "_native", False)]
+        if getattr(self._engine, "multi", False):
+            # slab-decomposed: the field trackers run on the devices, point samplers (a few
+            # scalars of one slab) are sampled on the host like user-defined trackers
+            from .tracker import ActivationTime2DTracker, ECG2DTracker
+            native_tr = [tr for tr in native_tr
+                         if isinstance(tr, (ActivationTime2DTracker, ECG2DTracker))]
         dev_tr = [tr for tr in trackers if getattr(tr, "_device_hook", False)]
-        host_tr = [tr for tr in trackers if not getattr(tr, "_native", False)
+        host_tr = [tr for tr in trackers if tr not in native_tr
                    and not getattr(tr, "_device_hook", False)]
         commands = self.command_sequence.sequence if self.command_sequence else []
         self._live.update(stims=stims, native_stims=native_stims, native_tr=native_tr)
@@ -233,6 +254,9 @@ class CardiacModel:
         """(Re-)register the built-in stimuli and trackers with the device runner."""
         eng, live = self._engine, self._live
         live["registered"] = True
+        if getattr(eng, "multi", False):
+            eng.register_native(self, live)
+            return
         _lib.check(eng.L.fwb_sim_clear_stims(eng.sim))
         _lib.check(eng.L.fwb_sim_clear_trackers(eng.sim))
         eng._keep = []
@@ -252,6 +276,9 @@ class CardiacModel:
         if not live.get("registered") or not eng.sim:
             return
         live["registered"] = False
+        if getattr(eng, "multi", False):
+            eng.collect_native(self, live)
+            return
         eng.synchronize()
         for tr in live["native_tr"]:
             tr._collect(eng)
@@ -443,6 +470,8 @@ class CardiacModel:
         nodes the solver does not update.  Returns False to request the synchronous path."""
         from .hooks import AsyncCheckpointWriter, StateSaver, StateSaverCollection
         if host_view_valid or getattr(self, "async_checkpoints", True) is False:
+            return False
+        if getattr(self._engine, "multi", False):
             return False
         sv = self.state_saver
         savers = list(sv.savers) if isinstance(sv, StateSaverCollection) else [sv]

@@ -384,6 +384,13 @@ FWB_API int fwb_ipc_handle_size(void);
 FWB_API int fwb_ipc_get_handle(const void *ptr, void *handle_out);
 FWB_API int fwb_ipc_open_handle(const void *handle, void **ptr_out);
 FWB_API int fwb_ipc_close_handle(void *ptr);
+/* slabs of one process on several devices (CardiacModel.run with FWB_DEVICES): peer mapping
+ * device -> peer, so that `device`'s boundary blocks can store into `peer`'s ghost slice */
+FWB_API int fwb_enable_peer_access(int device, int peer);
+/* advance several slab simulations of ONE process (wired with fwb_sim_set_halo through raw
+ * pointers) by n_steps from a single host thread: round-robin in chunks of `chunk` steps
+ * (0 = default), then fwb_sim_halo_sync on each */
+FWB_API int fwb_multi_run(FwbSim **sims, int n_sims, int64_t n_steps, int64_t chunk);
 FWB_API int fwb_sim_set_halo(FwbSim *sim, uint32_t *local_flags,
                      double *peer_lo_u0, double *peer_lo_u1, int64_t peer_lo_slices,
                      uint32_t *peer_lo_flags, int64_t n_lo_blocks,

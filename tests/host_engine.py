@@ -94,6 +94,10 @@ class OracleEngine:
         self.state = np.zeros((max(n_state, 1), self.ld))     # only its shape is looked at
         self._off = [0] * n_state
 
+    def needs_allocation(self, n_state):
+        return (self.state is None or self.ubuf[0] is None
+                or self.state.shape != (max(n_state, 1), self.ld))
+
     def upload_dense(self, which, host):
         self.ubuf[which][...] = host
 
@@ -139,6 +143,10 @@ class OracleEngine:
 
     def destroy_sim(self):
         self.sim = None
+
+    def set_params(self, p, dt):
+        self.sim.params = np.array([float(x) for x in p], dtype=np.float64)
+        self.sim.dt = float(dt)
 
     def current(self):
         return self.sim.cur
