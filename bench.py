@@ -247,8 +247,9 @@ def time_device(sim, steps, warmup, dist=None, propagate=0):
     return ms, sim.launch_count() - l0
 
 
-def host_model(workload, scale=1.0):
-    """The workload through the PUBLIC host API (numpy tissue, model classes)."""
+def host_model(workload, scale=1.0, slices=None, devices=None):
+    """The workload through the PUBLIC host API (numpy tissue, model classes).  `slices`:
+    thickness along axis 0 (C5 family: 128 per GPU); `devices`: model.devices."""
     import finitewave_b200 as fw
 
     def r32(x, lo=32):
@@ -267,7 +268,7 @@ def host_model(workload, scale=1.0):
         seq = fw.StimSequence()
         seq.add_stim(fw.StimVoltageCoord2D(0, 1, 0, n, 0, 5))
     elif workload in ("c5", "c5t"):
-        s, n = r32(128), r32(1024)
+        s, n = (slices or r32(128)), r32(1024)
         tissue = fw.CardiacTissue3D([s, n, n])
         phi = np.linspace(-np.pi / 3, np.pi / 2, s - 2)
         f = np.zeros((s, n, n, 3))
@@ -288,13 +289,16 @@ def host_model(workload, scale=1.0):
     model.dt, model.dr, model.prog_bar = 0.01, 0.25, False
     model.cardiac_tissue = tissue
     model.stim_sequence = seq
+    if devices is not None:
+        model.devices = list(devices)
     return model
 
 
-def e2e_host_api(workload, steps_per_call, calls, scale=1.0):
-    """Public API with host buffers: CardiacModel.run() on numpy (pinned) arrays."""
+def e2e_host_api(workload, steps_per_call, calls, scale=1.0, slices=None, devices=None):
+    """Public API with host buffers: CardiacModel.run() on numpy (pinned) arrays; with
+    `devices` the one call drives a slab per GPU (finitewave_b200/multi.py)."""
     import torch
-    model = host_model(workload, scale)
+    model = host_model(workload, scale, slices, devices)
     if model is None:
         return None
     t_init = time.perf_counter()
@@ -314,7 +318,12 @@ def e2e_host_api(workload, steps_per_call, calls, scale=1.0):
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     name = type(model).__name__
+    if devices is not None:
+        name += f" (model.devices = {list(devices)}: one process, one slab per GPU)"
+        if not getattr(model._engine, "multi", False):
+            raise RuntimeError("the slab-decomposed engine did not engage")
     return {"value": n_myo * steps_per_call * calls / sec, "unit": UNIT,
+            "shape": list(model.cardiac_tissue.mesh.shape),
             "h2d_bytes_per_step": per_call, "d2h_bytes_per_step": per_call,
             "steps_per_call": steps_per_call, "calls": calls, "seconds": sec,
             "api": f"finitewave_b200.{name}.run(initialize=False) on pinned numpy arrays; one "
@@ -346,6 +355,34 @@ def e2e_slabs(sim, info, steps_per_call, calls, dist, device):
             "steps_per_call": steps_per_call, "calls": calls,
             "api": "finitewave_b200.devrun.DeviceSimulation upload_host -> run -> download_host "
                    "per rank (bytes are per rank and call); one e2e step = one call"}
+
+
+def e2e_multi_gpu(args, world):
+    """N > 1, rank 0 only, after the other ranks have exited: the C5 family through
+    `TP063D.run()` on `world` GPUs of this one process.  The slab thickness per GPU is the
+    device-timed workload's (128) when the host can hold the pinned arrays (21 arrays of
+    1024 x 1024 x 128 N doubles), else the largest power-of-two fraction that fits."""
+    import psutil
+    import torch
+    # wait until the other ranks' contexts are gone
+    for d in range(world):
+        for _ in range(200):
+            free, total = torch.cuda.mem_get_info(d)
+            if free > 0.9 * total:
+                break
+            time.sleep(0.1)
+    per_slice = 1024 * 1024 * 8 * 21
+    avail = psutil.virtual_memory().available
+    slices = int(round(128 * args.scale)) // 32 * 32 or 32
+    while slices > 32 and slices * world * per_slice * args.scale ** 2 * 1.35 > 0.6 * avail:
+        slices //= 2
+    out = e2e_host_api(args.workload, args.e2e_steps, 2, scale=args.scale, slices=slices * world,
+                       devices=list(range(world)))
+    out["slices_per_gpu"] = slices
+    if slices != 128:
+        out["note"] = (f"slab thickness reduced to {slices} slices per GPU for this leg: the "
+                       "host could not hold the pinned arrays of the full workload")
+    return out
 
 
 def c1_line(device):
@@ -408,10 +445,16 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
+    real_stdout = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: keep NCCL's banner / debug output off it
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") and debug
+        # output are written to file descriptor 1 by the library itself, so descriptor 1 is
+        # pointed at stderr for the duration of the run and the line goes to the saved one
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from finitewave_b200 import workloads
 
@@ -458,14 +501,27 @@ def run_b200(args):
                      "kernel": "fwb::step_kernel (fused diffusion + ionic + trackers)",
                      "kernel_ms": kernel_ms},
     }
-    if world > 1 and not args.no_e2e:
-        try:
-            e2e = e2e_slabs(sim, info, args.e2e_steps, 2, dist, device)
-        except Exception as e:
-            e2e = {"error": repr(e)}
-        line["e2e"] = e2e
     del sim
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
+    if world > 1:
+        # the device-timed part is done: the other ranks leave, and rank 0 measures the
+        # end-to-end number through the public API -- ONE process, `TP063D.run()` with
+        # model.devices = all N GPUs (one slab per GPU, finitewave_b200/multi.py)
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
+        if rank != 0:
+            return
+        print(f"[bench] device-timed part done ({value / 1e9:.2f} G upd/s); rank 0 continues alone",
+              file=sys.stderr, flush=True)
+        if not args.no_e2e:
+            try:
+                line["e2e"] = e2e_multi_gpu(args, world)
+            except BaseException as e:          # never lose the device number
+                line["e2e"] = {"error": repr(e)}
+            print(f"[bench] e2e leg: {line['e2e']}", file=sys.stderr, flush=True)
 
     if rank == 0 and world == 1:
         import gc
@@ -511,7 +567,11 @@ def run_b200(args):
                 line["cpu_baseline"] = {"error": repr(e)}
     line["wall_s"] = time.perf_counter() - t_wall0
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
