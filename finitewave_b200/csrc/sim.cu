@@ -125,7 +125,9 @@ struct FwbSim {
     const uint32_t *tile_rec;
     const uint8_t *pos_of;
     uint32_t *defer;                 // [n_tiles + 2]: list, then {count, finished blocks}
-    int32_t *node_of;                // [n_myo] compact index -> flat node (multi-step kernel)
+    int32_t *node_of;                // [n_myo] compact index -> flat node (multi-step kernel,
+                                     // packed mode of the tile kernel)
+    bool packed;                     // tile kernel in packed mode (sparse tissue, no halo)
     bool brick_ok;
     alignas(64) CUtensorMap tmap[2]; // of buf[0] / buf[1]
     // slab halo
@@ -212,7 +214,7 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
     s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0; s->device_steps = 0;
     s->tile_base = nullptr; s->records = nullptr;
     s->tile_rec = nullptr; s->pos_of = nullptr; s->defer = nullptr; s->brick_ok = false;
-    s->node_of = nullptr;
+    s->node_of = nullptr; s->packed = false;
     s->halo_on = false; s->epoch = 0; s->flags = nullptr;
     memset(s->peer_u, 0, sizeof(s->peer_u));
     memset(s->peer_flags, 0, sizeof(s->peer_flags));
@@ -332,6 +334,26 @@ extern "C" int fwb_sim_set_tiles(FwbSim *s, const uint32_t *tile_rec, const uint
         ((uintptr_t)s->buf[0] & 15) == 0 && ((uintptr_t)s->buf[1] & 15) == 0)
         s->brick_ok = make_u_tensor_map(&s->tmap[0], s->buf[0], s->dim, s->g) &&
                       make_u_tensor_map(&s->tmap[1], s->buf[1], s->dim, s->g);
+    return 0;
+}
+
+static int ensure_node_of(FwbSim *s);
+// blocks of the step kernel = per-block ECG partial sums of a sampling step
+static int64_t ecg_blocks(const FwbSim *s)
+{
+    const bool tile_kernel = s->entry->n_state > 4 && s->tile_rec && s->pos_of && s->defer;
+    if (tile_kernel && s->packed && !s->halo_on) return (s->n_myo + BLOCK_THREADS - 1) / BLOCK_THREADS;
+    return step_blocks(s->g);
+}
+
+extern "C" int fwb_sim_set_packed(FwbSim *s, int on)
+{
+    if (!s) return FWB_E_ARG;
+    if (!on) { s->packed = false; return 0; }
+    if (!s->tile_rec) { set_error("fwb_sim_set_packed: call fwb_sim_set_tiles first"); return FWB_E_STATE; }
+    int rc = ensure_node_of(s);
+    if (rc) return rc;
+    s->packed = true;
     return 0;
 }
 
@@ -586,15 +608,26 @@ done:
     return m;
 }
 
+static int ensure_node_of(FwbSim *s)
+{
+    if (s->node_of) return 0;
+    if (s->g.n_nodes >= ((int64_t)1 << 31)) { set_error("grid too large for 32-bit node ids"); return FWB_E_UNSUPPORTED; }
+    FWB_CUDA(cudaMalloc((void **)&s->node_of, sizeof(int32_t) * (s->n_myo > 0 ? s->n_myo : 1)));
+    const unsigned nb = (unsigned)((s->g.n_work * 32 + 255) / 256);
+    if (nb) {
+        node_of_kernel<<<nb, 256, 0, s->stream>>>(s->g.worklist, s->g.n_work, s->g.chunk_bits,
+                                                  s->g.chunk_base, s->node_of);
+        FWB_KERNEL_CHECK("node_of_kernel");
+    }
+    return 0;
+}
+
 static int run_small(FwbSim *s, int64_t m, Tracker *act, int64_t samples)
 {
     cudaStream_t st = s->stream;
-    if (!s->node_of) {
-        FWB_CUDA(cudaMalloc((void **)&s->node_of, sizeof(int32_t) * (s->n_myo > 0 ? s->n_myo : 1)));
-        const unsigned nb = (unsigned)((s->g.n_work * 32 + 255) / 256);
-        node_of_kernel<<<nb, 256, 0, st>>>(s->g.worklist, s->g.n_work, s->g.chunk_bits,
-                                           s->g.chunk_base, s->node_of);
-        FWB_KERNEL_CHECK("node_of_kernel");
+    {
+        int rc = ensure_node_of(s);
+        if (rc) return rc;
     }
     StepCommon k;
     memset(&k, 0, sizeof(k));
@@ -700,6 +733,7 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
             k.defer_list = s->defer;
             k.defer_ctr = s->defer + n_tiles;
         }
+        if (s->packed && !s->halo_on) { k.node_of = s->node_of; k.n_packed = s->n_myo; }
         k.brick = s->brick_ok ? 1 : 0;
         k.tmap_host = &s->tmap[s->cur];
         if (s->halo_on) {
@@ -743,7 +777,7 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         if (rc) return rc;
         s->launches += last_step_launches();
         if (ecg) {
-            rc = launch_ecg_finalize(s->ecg_partial, step_blocks(s->g), ecg->n_leads,
+            rc = launch_ecg_finalize(s->ecg_partial, ecg_blocks(s), ecg->n_leads,
                                      ecg->out + ecg->samples * ecg->n_leads, st);
             if (rc) return rc;
             s->launches++;

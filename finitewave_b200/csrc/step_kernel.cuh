@@ -88,6 +88,8 @@ struct StepCommon {
     const uint8_t *pos_of;      // [ld] (slot << 5) | lane of each compact node inside its tile
     uint32_t *defer_list;       // [n_work/8] tiles handed to the reference-statement kernel
     uint32_t *defer_ctr;        // [0] entries in defer_list, [1] finished blocks of that kernel
+    const int32_t *node_of;     // PACKED mode (sparse tissue): flat node of each compact index;
+    int64_t n_packed;           // block t owns compact nodes [256 t, 256 t + 256) of n_packed
     int brick;                  // the launch carries a tensor map of u (interior tiles use it)
     const void *tmap_host;      // HOST pointer to that CUtensorMap (read by the launcher only)
 };
@@ -596,11 +598,22 @@ __device__ __forceinline__ void tile_body(const StepArgs<M> &A, const CUtensorMa
     const int tid = threadIdx.x;
     const bool tiled = (g.line & 31) == 0;
     uint64_t &full = *full_p;
-    const uint4 rec = __ldg(P.tile_rec + t);
+    // tile mode: block t owns spatial tile t.  Packed mode (tissue that fills its tiles
+    // poorly -- a ventricle wall, heavy fibrosis; single GPU): block t owns the 256
+    // consecutive compact nodes [256 t, 256 t + 256), every warp is full, u by plain loads.
+    const bool packed = !HALO && P.node_of != nullptr;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (packed) {
+        rec.x = t * (uint32_t)BLOCK_THREADS;
+        const int64_t left = P.n_packed - (int64_t)rec.x;
+        rec.y = left >= BLOCK_THREADS ? (uint32_t)BLOCK_THREADS : (uint32_t)(left > 0 ? left : 0);
+    } else {
+        rec = __ldg(P.tile_rec + t);
+    }
     const uint32_t c0 = rec.x, cnt = rec.y;
     const int64_t n0 = (int64_t)rec.z * 32;
     const bool bnd = HALO && rec.w != 0;
-    const bool use_brick = BRICK && !SLOW && !bnd;   // (BRICK kernels: tiled grids only)
+    const bool use_brick = BRICK && !SLOW && !bnd;   // (BRICK kernels: tiled grids, tile mode)
     const uint32_t c0a = c0 & ~1u;
 
     if (!SLOW && tid == 0) {
@@ -648,9 +661,13 @@ __device__ __forceinline__ void tile_body(const StepArgs<M> &A, const CUtensorMa
     int q = 0, ln = 0;
     double acc = 0.0, uc = 0.0;
     if (wact) {
-        const unsigned pos = __ldg(P.pos_of + c);
-        q = pos >> 5; ln = pos & 31;
-        n = tile_node<DIM>(g, tiled, bnd, n0, q, ln);
+        if (packed) {
+            n = __ldg(P.node_of + c);
+        } else {
+            const unsigned pos = __ldg(P.pos_of + c);
+            q = pos >> 5; ln = pos & 31;
+            n = tile_node<DIM>(g, tiled, bnd, n0, q, ln);
+        }
         // diffusion: left-to-right sum in slot order, no FMA contraction (-fmad=false).
         // Brick tiles: the weights are requested first (one coalesced streaming load per
         // slot, all in flight together), the u operands are shared-memory reads once the
@@ -1011,15 +1028,18 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
     StepArgs<M> a;
     a.k = k;
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
-    const int64_t blocks = step_blocks(k.g);
+    int64_t blocks = step_blocks(k.g);
     if (blocks <= 0) return 0;
     if constexpr (stage_state<M>()) {
         if (k.tile_rec && k.pos_of && k.defer_list && k.defer_ctr) {
+            const bool packed = !HALO && k.node_of != nullptr;
+            if (packed) blocks = (k.n_packed + BLOCK_THREADS - 1) / BLOCK_THREADS;
+            if (blocks <= 0) return 0;
             // compact-lane tile kernel (fast path only) + the reference-statement kernel for
             // the tiles it hands over (normally none: that launch returns at once)
             CUtensorMap none;
             memset(&none, 0, sizeof(none));
-            const bool brick = k.brick && k.tmap_host && (k.g.line & 31) == 0;
+            const bool brick = !packed && k.brick && k.tmap_host && (k.g.line & 31) == 0;
             int rc;
             if (brick) {
                 auto kern = step_kernel_tile<M, DIM, ST, TRACK, HALO, true, false>;

@@ -8,6 +8,7 @@ Device layout: u, u_new, act_t dense; weights and state
 compact SoA in myocyte order; 1 bit + 1/8 byte of index structure per node.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -102,6 +103,7 @@ class Engine:
         first / last slice of the slowest axis is a ghost slice owned by a neighbour
         rank (its tissue feeds weights and stimuli, its nodes are never updated here)."""
         dev = self.device
+        self._halo = (bool(halo[0]), bool(halo[1]))
         self.destroy_sim()      # it borrows the index structures replaced below
         if isinstance(mesh, torch.Tensor):
             m = mesh.to(dev)
@@ -379,6 +381,14 @@ class Engine:
                   "fwb_sim_set_tile_base")
             check(self.L.fwb_sim_set_tiles(sim, _ptr(self.tile_rec), _ptr(self.pos_of)),
                   "fwb_sim_set_tiles")
+            # tissue that fills its spatial tiles poorly (a ventricle wall, heavy fibrosis):
+            # the tile kernel packs 256 consecutive compact nodes per block instead
+            fill = self.n_myo / max(1, self.n_work * 32)
+            packed = os.environ.get("FWB_PACKED")
+            packed = (fill < 0.85) if packed in (None, "") else packed == "1"
+            if packed and not any(getattr(self, "_halo", (False, False))) \
+                    and self.n_nodes < 2 ** 31:
+                check(self.L.fwb_sim_set_packed(sim, 1), "fwb_sim_set_packed")
 
     def destroy_sim(self):
         if self.sim:

@@ -293,6 +293,10 @@ FWB_API int fwb_sim_set_tile_base(FwbSim *sim, const uint32_t *tile_base,
  * from fwb_order_tiles (NULL, NULL = off).  Also builds the tensor maps of the two u buffers
  * for the kernel's brick copies when the line length is a multiple of 32 nodes. */
 FWB_API int fwb_sim_set_tiles(FwbSim *sim, const uint32_t *tile_rec, const uint8_t *pos_of);
+/* tile kernel in PACKED mode (single GPU; for tissue that fills its spatial tiles poorly --
+ * a ventricle wall, heavy fibrosis): a block owns 256 consecutive compact nodes instead of
+ * one spatial tile, so every warp is full; u operands by plain loads.  on = 0: tile mode. */
+FWB_API int fwb_sim_set_packed(FwbSim *sim, int on);
 /* rebind after the caller re-uploaded / recomputed arrays (same sizes) */
 FWB_API int fwb_sim_set_weights(FwbSim *sim, const double *weights);
 FWB_API int fwb_sim_set_params(FwbSim *sim, const double *params, int n_params, double dt);

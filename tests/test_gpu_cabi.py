@@ -198,6 +198,7 @@ def test_public_api_runs_the_tma_kernels(monkeypatch):
         model.run()
         assert L.fwb_last_step_variant() == 3, (name, L.fwb_last_step_variant())
     # a tiled grid (line length 64): TP06 with the u brick by tensor TMA
+    monkeypatch.setenv("FWB_PACKED", "0")
     tissue = fw.CardiacTissue3D([6, 12, 64])
     model = fw.TP063D()
     model.dt, model.dr, model.t_max, model.prog_bar = 0.01, 0.25, 0.05, False

@@ -33,19 +33,22 @@ def _tp06_tiled(shape, t_max, fibrosis=0.2):
                           dict(kind="ecg", coords=[[4, 8, 70], [1, 1, 1]], step=7)])
 
 
-@pytest.mark.parametrize("brick", [True, False], ids=["brick", "plain-loads"])
-def test_tp06_tracker_ecg_on_a_tiled_shape(fw, brick, monkeypatch):
+@pytest.mark.parametrize("mode", ["brick", "plain-loads", "packed"])
+def test_tp06_tracker_ecg_on_a_tiled_shape(fw, mode, monkeypatch):
     """TP06 + ActivationTime (every step) + ECG on 8 x 16 x 64 with 20 % fibrosis and random
-    fibres (19-point stencil): real tiles, most of them partially filled, 400 steps."""
+    fibres (19-point stencil): real tiles, most of them partially filled, 400 steps -- in tile
+    mode with the u brick by tensor TMA, in tile mode with plain loads, and in packed mode
+    (256 consecutive compact nodes per block: what a tissue this sparse gets by default)."""
     from oracle import oracle
-    if not brick:
+    monkeypatch.setenv("FWB_PACKED", "1" if mode == "packed" else "0")
+    if mode == "plain-loads":
         monkeypatch.setenv("FWB_NO_BRICK", "1")
     case = _tp06_tiled([8, 16, 64], 4.0)
     ref = oracle.simulate(case)
     out = build_and_run(fw, case)
     _check_outputs(case, out, ref, "oracle")
     from finitewave_b200 import _lib
-    assert _lib.lib().fwb_last_step_variant() == (5 if brick else 4)
+    assert _lib.lib().fwb_last_step_variant() == (5 if mode == "brick" else 4)
 
 
 def test_tp06_iso7_and_2d_tiled(fw):
