@@ -374,14 +374,16 @@ def e2e_multi_gpu(args, world):
     per_slice = 1024 * 1024 * 8 * 21
     avail = psutil.virtual_memory().available
     slices = int(round(128 * args.scale)) // 32 * 32 or 32
-    while slices > 32 and slices * world * per_slice * args.scale ** 2 * 1.35 > 0.6 * avail:
+    # (also bounded to ~64 GB of pinned arrays so that the leg stays within a minute or two)
+    while slices > 32 and (slices * world * per_slice * args.scale ** 2 * 1.35 > 0.6 * avail
+                           or slices * world * per_slice * args.scale ** 2 > 64e9):
         slices //= 2
     out = e2e_host_api(args.workload, args.e2e_steps, 2, scale=args.scale, slices=slices * world,
                        devices=list(range(world)))
     out["slices_per_gpu"] = slices
     if slices != 128:
-        out["note"] = (f"slab thickness reduced to {slices} slices per GPU for this leg: the "
-                       "host could not hold the pinned arrays of the full workload")
+        out["note"] = (f"slab thickness reduced to {slices} slices per GPU for this leg (the "
+                       "pinned host arrays of the whole tissue are bounded to ~64 GB / 60 % of RAM)")
     return out
 
 

@@ -152,7 +152,7 @@ def make_cases():
     # C3 reduced: MS 3D iso-7 focal + activation time every step
     cases.append(dict(
         name="c3_ms3d_iso_focal", model="mitchell_schaeffer", shape=[24, 24, 24],
-        dt=0.01, dr=0.25, t_max=6,
+        dt=0.01, dr=0.25, t_max=10,
         stims=[dict(kind="voltage_coord", t=0, value=1, box=[10, 14, 10, 14, 10, 14])],
         trackers=[dict(kind="activation_time", threshold=0.5, step=1)]))
 
@@ -230,7 +230,7 @@ def make_cases():
     vm, vf = ventricle_shell([20, 20, 24])
     cases.append(dict(
         name="c4_tp06_3d_ventricle", model="tp06", shape=[20, 20, 24],
-        dt=0.01, dr=0.25, t_max=5, mesh=vm, fibers=vf,
+        dt=0.01, dr=0.25, t_max=10, mesh=vm, fibers=vf,
         stims=[dict(kind="voltage_coord", t=0, value=-20, box=[0, 20, 0, 20, 0, 4])],
         trackers=[dict(kind="activation_time", step=1)]))
 

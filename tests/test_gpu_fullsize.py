@@ -100,16 +100,15 @@ def test_c2_4096sq_window_equals_small_oracle_run():
 def test_c5_tp06_slab_invariance_and_oracle_line():
     """C5 (one GPU's 128 x 1024 x 1024 share): TP06, 19-point, fibres rotating along axis 0
     (the slab axis), stimulus on the axis-0 face.  Nothing depends on j or k, so interior
-    lines along axis 0 are bit-identical; one of them is compared with an oracle run on a
-    128 x 40 x 64 strip (same fibre rotation, lateral boundaries farther away than the
-    stencil can reach in the steps taken)."""
+    lines along axis 0 are bit-identical; one of them is compared, after 240 steps, with an
+    oracle run on a 128 x 12 x 32 strip with the same fibre rotation."""
     import torch
     import finitewave_b200 as fw
     from finitewave_b200 import workloads
     from finitewave_b200.devrun import DeviceSimulation
     from oracle import oracle
 
-    steps = 16
+    steps = 240
     dev = torch.device("cuda")
     shape = (128, 1024, 1024)
     sim = DeviceSimulation(_cfg(fw.TP063D()), workloads.fibrosis_mesh(shape, 0.0, 0, dev),
@@ -119,7 +118,10 @@ def test_c5_tp06_slab_invariance_and_oracle_line():
     u = sim.u_device()
     a, b = u[:, 300, 400].cpu().numpy(), u[:, 700, 520].cpu().numpy()
     assert np.array_equal(a, b)
-    small = (128, 40, 64)
+    # fibres have no component along axis 0, so the lateral fluxes of a laterally uniform
+    # potential vanish at the strip's lateral (no-flux) boundaries exactly as in the interior
+    # of the full tissue: the strip may be narrow however many steps are taken
+    small = (128, 12, 32)
     phi = np.linspace(-np.pi / 3, np.pi / 2, small[0] - 2)
     f = np.zeros((*small, 3))
     f[1:-1, :, :, 1] = np.cos(phi)[:, None, None]
@@ -128,11 +130,11 @@ def test_c5_tp06_slab_invariance_and_oracle_line():
                 fibers=f, stims=[dict(kind="voltage_coord", t=0, value=-20,
                                       box=[0, 5, 0, small[1], 0, small[2]])])
     ref = oracle.simulate(case)
-    got, want = a, ref["u"][:, 20, 32]
+    got, want = a, ref["u"][:, 6, 16]
     assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want))
     for name in ("m", "cass", "Ki"):
         s = sim.state_host(name)[:, 300, 400]
-        w = ref[name][:, 20, 32]
+        w = ref[name][:, 6, 16]
         assert np.max(np.abs(s - w)) <= 1e-9 * max(np.max(np.abs(w)), 1e-300), name
     assert np.ptp(got) > 20
 
