@@ -18,7 +18,7 @@ constexpr int MAX_STATE = 21;
 void set_error(const char *fmt, ...);
 // which step kernel the last launch used (fwb_last_step_variant): 0 = one block per tile,
 // plain loads; 3 = persistent TMA ring; 4 = compact-lane tile kernel, plain u loads; 5 = the
-// same with the u brick by tensor TMA
+// same with the u brick by tensor TMA; 6 = multi-step cluster kernel; 7 = ring + u brick
 void note_step_variant(int v);
 int last_step_launches();
 int cuda_fail(cudaError_t e, const char *what);

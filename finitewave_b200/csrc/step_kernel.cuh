@@ -841,29 +841,41 @@ step_kernel_tile(const __grid_constant__ StepArgs<M> A, const __grid_constant__ 
 // step_kernel_tma: persistent, TMA-fed variant (see the header comment)
 // ---------------------------------------------------------------------------
 
-template <class M, int K> struct TmaCfg {
+template <class M, int K, int DIM> struct TmaCfg {
     static constexpr int NSR = tma_popc(M::READ_MASK);
     static constexpr int NARR = K + NSR;
     static constexpr int NSTAGE = 2;
-    // blocks per SM the launch bounds ask for: as many as the ring allows (227 KB / SM)
-    static constexpr size_t STAGE = (size_t)NARR * TMA_SEG * sizeof(double) + TMA_REC_BYTES;
+    // one ring stage: the tile's u brick (tensor TMA; first, 128-byte aligned), its weight and
+    // state rows, its 8 work records -- rounded up to a multiple of 128 bytes
+    static constexpr size_t BRICK = ((size_t)Brick<DIM>::N * sizeof(double) + 127) / 128 * 128;
+    static constexpr size_t ROWS = (size_t)NARR * TMA_SEG * sizeof(double);
+    static constexpr size_t STAGE = (BRICK + ROWS + TMA_REC_BYTES + 127) / 128 * 128;
+    static constexpr size_t STAGE_NB = (ROWS + TMA_REC_BYTES + 127) / 128 * 128;   // no brick
     static constexpr size_t SMEM = NSTAGE * STAGE + 64;
+    static constexpr size_t SMEM_NB = NSTAGE * STAGE_NB + 64;
+    // blocks per SM the launch bounds ask for: as many as the ring allows (227 KB / SM)
     static constexpr int BLOCKS = SMEM * 4 <= 224 * 1024 ? 4 : (SMEM * 3 <= 224 * 1024 ? 3 : 2);
 };
 
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
-__global__ void __launch_bounds__(BLOCK_THREADS, (TmaCfg<M, Stencil<DIM, ST>::K>::BLOCKS))
-step_kernel_tma(const __grid_constant__ StepArgs<M> A)
+__global__ void __launch_bounds__(BLOCK_THREADS, (TmaCfg<M, Stencil<DIM, ST>::K, DIM>::BLOCKS))
+step_kernel_tma(const __grid_constant__ StepArgs<M> A, const __grid_constant__ CUtensorMap tmap)
 {
     using S = Stencil<DIM, ST>;
+    using B = Brick<DIM>;
     constexpr int K = S::K;
-    using C = TmaCfg<M, K>;
+    using C = TmaCfg<M, K, DIM>;
     constexpr int NARR = C::NARR, NSTAGE = C::NSTAGE;
-    constexpr int STAGE_D = (int)(C::STAGE / sizeof(double));   // doubles per ring stage
+
     const StepCommon &P = A.k;
     const Grid &g = P.g;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // a ring stage holds the tile's rows and records, preceded -- only when bricks are on, so
+    // that the L1 keeps the shared memory it would take otherwise -- by the tile's u brick
+    const bool bricks = P.brick != 0 && P.tile_rec != nullptr;
+    const int BRICK_D = bricks ? (int)(C::BRICK / sizeof(double)) : 0;
+    const int STAGE_D = (int)((bricks ? C::STAGE : C::STAGE_NB) / sizeof(double));
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);     // [NSTAGE]{[NARR][SEG] rows, 8 records}
@@ -880,21 +892,39 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
 
     // producer (warp 0): start the bulk copies of tile t (compact range [c0, c1)) into
     // ring stage s
+    // tiles of a tiled grid that are not slab-boundary tiles get their u neighbourhood as a
+    // brick by tensor TMA (tile_rec: origin chunk + boundary flag); the others use plain loads
     auto issue = [&](int64_t t, int s, uint32_t c0, uint32_t c1) {
         const uint32_t c0a = c0 & ~1u;
         const unsigned bytes = c1 > c0 ? (((c1 - c0a) + 1u) & ~1u) * 8u : 0u;
-        if (lane == 0) mbar_arrive_expect_tx(full + s, bytes * NARR + TMA_REC_BYTES);
+        uint4 trec = make_uint4(0u, 0u, 0u, 1u);
+        if (bricks && lane == 0) trec = __ldg(P.tile_rec + t);
+        const bool brick_t = bricks && trec.w == 0u;        // (meaningful in lane 0 only)
+        if (lane == 0)
+            mbar_arrive_expect_tx(full + s, bytes * NARR + TMA_REC_BYTES +
+                                                (brick_t ? (unsigned)(B::N * 8) : 0u));
         __syncwarp();
         double *stage = ring + (size_t)s * STAGE_D;
+        if (lane == 0 && brick_t) {
+            const int64_t cpl = g.line >> 5;
+            const int64_t o = trec.z;
+            const int col0 = (int)(o % cpl) * 32;
+            if (DIM == 3) {
+                const int row0 = (int)((o / cpl) % g.rows), pl0 = (int)(o / (cpl * g.rows));
+                tma_load_brick3(stage, &tmap, col0 - B::X0, row0 - 1, pl0 - 1, full + s);
+            } else {
+                tma_load_brick2(stage, &tmap, col0 - B::X0, (int)(o / cpl) - 1, full + s);
+            }
+        }
         if (lane == 31)
-            tma_load_1d(stage + NARR * TMA_SEG, P.records + t * WARPS_PER_BLOCK, TMA_REC_BYTES,
-                        full + s);
+            tma_load_1d(stage + BRICK_D + NARR * TMA_SEG, P.records + t * WARPS_PER_BLOCK,
+                        TMA_REC_BYTES, full + s);
         if (bytes) {
             for (int a = lane; a < NARR; a += 32) {
                 const double *src = a < K
                     ? P.w + (int64_t)a * g.ld + c0a
                     : P.state + (int64_t)tma_nth(M::READ_MASK, a - K) * g.ld + c0a;
-                tma_load_1d(stage + a * TMA_SEG, src, bytes, full + s);
+                tma_load_1d(stage + BRICK_D + a * TMA_SEG, src, bytes, full + s);
             }
         }
     };
@@ -938,7 +968,8 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
         // everything this tile needs from HBM (work records, weight rows, state rows) was
         // requested one iteration ago; normally the wait returns at once
         mbar_wait(full + s, phase);
-        const double *stage = ring + (size_t)s * STAGE_D;
+        const double *stage = ring + (size_t)s * STAGE_D + BRICK_D;    // the tile's rows
+        const double *brick = ring + (size_t)s * STAGE_D;
         const uint4 rec = reinterpret_cast<const uint4 *>(stage + NARR * TMA_SEG)[warp];
         const int64_t chunk = (int64_t)(int32_t)rec.x;
         const uint32_t bits = chunk >= 0 ? rec.y : 0u;
@@ -953,13 +984,20 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A)
 
         double un[K];
         if (myo) {
-            const double *__restrict__ u = P.u + n;
+            if (bricks && !(HALO && side)) {
+                // warp = tile slot, lane = column: the brick's compile-time offsets
+                const double *bc = brick + B::centre(warp, lane);
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const Off o = S::at(k);
-                const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
-                                    (int64_t)o.r * g.s_row + o.l;
-                un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
+                for (int k = 0; k < K; ++k) un[k] = bc[B::off(S::at(k))];
+            } else {
+                const double *__restrict__ u = P.u + n;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const Off o = S::at(k);
+                    const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
+                                        (int64_t)o.r * g.s_row + o.l;
+                    un[k] = (HALO && side) ? __ldcg(u + off) : __ldg(u + off);
+                }
             }
         }
 
@@ -1119,7 +1157,7 @@ step_kernel_small(const __grid_constant__ StepArgs<M> A, const __grid_constant__
     constexpr int NS = M::NS > 0 ? M::NS : 1;
     const StepCommon &P = A.k;
     const Grid &g = P.g;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     double *const st_sm = reinterpret_cast<double *>(dyn_smem);      // [npt][NS][SMALL_THREADS]
     const int tid = threadIdx.x;
     const int64_t T = (int64_t)gridDim.x * SMALL_THREADS;
@@ -1242,29 +1280,38 @@ static int launch_small_model(int dim, int stencil, const StepCommon &k, const v
 template <class M, int DIM, int ST, bool TRACK, bool HALO>
 static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
 {
-    using C = TmaCfg<M, Stencil<DIM, ST>::K>;
+    using C = TmaCfg<M, Stencil<DIM, ST>::K, DIM>;
     auto kern = step_kernel_tma<M, DIM, ST, TRACK, HALO>;
-    // blocks of this instantiation each device holds at once (per device: a process may
-    // drive several GPUs, from several threads)
+    // u bricks in the ring: on for 3D tiled grids, off in 2D (A/B on a B200, profiles/:
+    // C3 +2 %, C2 -7 %); FWB_RING_BRICK=0/1 overrides
+    bool brick = k.brick && k.tmap_host && k.tile_rec && (k.g.line & 31) == 0 && DIM == 3;
+    {
+        const char *e = getenv("FWB_RING_BRICK");
+        if (e && e[0] == '0') brick = false;
+        if (e && e[0] == '1') brick = k.brick && k.tmap_host && k.tile_rec && (k.g.line & 31) == 0;
+    }
+    const size_t smem = brick ? C::SMEM : C::SMEM_NB;
+    // blocks of this instantiation each device holds at once (per device and per mode: a
+    // process may drive several GPUs, from several threads)
     static std::mutex mu;
-    static int resident_of[64] = {0};
+    static int resident_of[64][2] = {{0, 0}};
     int dev = 0;
     FWB_CUDA(cudaGetDevice(&dev));
     int resident = 0;
     {
         std::lock_guard<std::mutex> lock(mu);
-        if (dev >= 64 || resident_of[dev] == 0) {
+        if (dev >= 64 || resident_of[dev][brick] == 0) {
             FWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)C::SMEM));
             int sms = 0, per_sm = 0;
             FWB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             FWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK_THREADS,
-                                                                   C::SMEM));
+                                                                   smem));
             if (per_sm < 1) { set_error("step_kernel_tma does not fit on an SM"); return FWB_E_UNSUPPORTED; }
             resident = sms * per_sm;
-            if (dev < 64) resident_of[dev] = resident;
+            if (dev < 64) resident_of[dev][brick] = resident;
         } else {
-            resident = resident_of[dev];
+            resident = resident_of[dev][brick];
         }
     }
     StepArgs<M> a;
@@ -1278,8 +1325,12 @@ static int launch_tma(const StepCommon &k, const void *consts, cudaStream_t s)
         const int64_t nb = (int64_t)k.halo.lo.n_blocks + k.halo.hi.n_blocks;
         if (nb > blocks) { set_error("slab boundary does not fit the resident grid"); return FWB_E_UNSUPPORTED; }
     }
-    kern<<<(unsigned)blocks, BLOCK_THREADS, C::SMEM, s>>>(a);
-    note_step_variant(3);
+    CUtensorMap map;
+    if (brick) map = *reinterpret_cast<const CUtensorMap *>(k.tmap_host);
+    else memset(&map, 0, sizeof(map));
+    a.k.brick = brick ? 1 : 0;
+    kern<<<(unsigned)blocks, BLOCK_THREADS, smem, s>>>(a, map);
+    note_step_variant(brick ? 7 : 3);
     FWB_KERNEL_CHECK("step_kernel_tma");
     return 0;
 }

@@ -196,7 +196,7 @@ def test_public_api_runs_the_tma_kernels(monkeypatch):
         case["t_max"] = 0.2
         model, _ = build_model(fw, case)
         model.run()
-        assert L.fwb_last_step_variant() == 3, (name, L.fwb_last_step_variant())
+        assert L.fwb_last_step_variant() in (3, 7), (name, L.fwb_last_step_variant())
     # a tiled grid (line length 64): TP06 with the u brick by tensor TMA
     monkeypatch.setenv("FWB_PACKED", "0")
     tissue = fw.CardiacTissue3D([6, 12, 64])
