@@ -548,8 +548,10 @@ def run_b200(args):
                     continue
                 try:
                     s2, i2 = workloads.build(w, device, scale=args.scale)
-                    k = max(10, args.steps // 2)
-                    ms2, l2 = time_device(s2, k, 5, None, args.propagate)
+                    # a timed region of >= ~150 ms whatever the step costs (C2: 0.25 ms)
+                    ms_probe, _ = time_device(s2, 10, 5, None, args.propagate)
+                    k = int(max(10, min(1000, 150.0 / max(ms_probe / 10, 1e-3))))
+                    ms2, l2 = time_device(s2, k, 5, None, 0)
                     ach = i2["bytes_per_node"] * i2["n_myo"] * k / (ms2 * 1e-3) / 1e9
                     extras.append({"workload": i2["workload"], "value": i2["n_myo"] * k / (ms2 * 1e-3),
                                    "unit": UNIT, "ms_per_step": ms2 / k, "steps": k,

@@ -340,9 +340,11 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         double E_Na, E_K, G_K, E_K1, G_K1;   // parameter-only (:478, :337-338, :496, :404)
         // fast path only (ionic_fast): exp(offset * slope) of the shared-slope exponentials
         double k47, k32, kd, kf1, kf2, kf3, kx1, kx2, kxa, kxb;
+        double ec[8];      // fexp's reduction / polynomial constants (fexp_fill_consts)
     };
     static bool derive(const double *p, double dt, Consts &c)
     {
+        fexp_fill_consts(c.ec);
         const double gk = p[2], gk1 = p[3], ko = p[6], ki = p[7], nai = p[8], nao = p[9],
                      R = p[11], T = p[12], F = p[13], PR_NaK = p[14];
         c.dt = dt; c.gna = p[0]; c.gsi = p[1]; c.gkp = p[4]; c.gb = p[5];
@@ -409,31 +411,39 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
     FWB_HD static void ionic_fast(double u, double &un, IO &io, const Consts &c, double cai)
     {
         const double dt = c.dt;
-        const double g01 = fexp_fast(-0.1 * u);
-        const double g02 = fexp_fast(-0.02 * u), g04 = g02 * g02, g06 = g04 * g02;
+        const double *ec = c.ec;       // kernel-parameter bank -> uniform registers
+        auto EX = [ec](double x) { return fexp_fast_p(x, ec); };
+        auto EXN = [ec](double x) { return fexp_fast_p(x < -700.0 ? -700.0 : x, ec); };
+        auto EXC = [ec](double x) {
+            x = x < -700.0 ? -700.0 : x;
+            return fexp_fast_p(x > 700.0 ? 700.0 : x, ec);
+        };
+        (void)EXN; (void)EXC;
+        const double g01 = EX(-0.1 * u);
+        const double g02 = EX(-0.02 * u), g04 = g02 * g02, g06 = g04 * g02;
         const double g08 = g04 * g04, g20 = g08 * g08 * g04;          // exp(-0.2 u)
-        const double g05 = fexp_fast(0.05 * u), g15 = g05 * g05 * g05;
+        const double g05 = EX(0.05 * u), g15 = g05 * g05 * g05;
         // ---- I_Na (calc_ina :185-241)
         double ah, sh, aj, sj;                                          // alpha, alpha + beta
         if (u >= -40.) {
             ah = 0.;
-            sh = frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
+            sh = frcp3(0.13 * (1. + EX((u + 10.66) * (-1. / 11.1))));
             aj = 0.;
-            sj = 0.3 * fexp_fast(-2.535e-07 * u) * frcp3(fma(c.k32, g01, 1.));
+            sj = 0.3 * EX(-2.535e-07 * u) * frcp3(fma(c.k32, g01, 1.));
         } else {
-            ah = 0.135 * fexp_fast((80. + u) * (-1. / 6.8));
-            sh = ah + (3.56 * fexp_fast(0.079 * u) + 3.1e5 * fexp_fast(0.35 * u));
-            const double a = 1. + fexp_fast(0.311 * (u + 79.23));
-            const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
-            const double na = (-1.2714e5 * fexp_fast(0.2444 * u) -
-                               3.474e-5 * fexp_fast(-0.04391 * u)) * (u + 37.78);
-            const double nb = 0.1212 * fexp_fast(-0.01052 * u);
+            ah = 0.135 * EX((80. + u) * (-1. / 6.8));
+            sh = ah + (3.56 * EX(0.079 * u) + 3.1e5 * EX(0.35 * u));
+            const double a = 1. + EX(0.311 * (u + 79.23));
+            const double b = 1. + EX(-0.1378 * (u + 40.14));
+            const double na = (-1.2714e5 * EX(0.2444 * u) -
+                               3.474e-5 * EX(-0.04391 * u)) * (u + 37.78);
+            const double nb = 0.1212 * EX(-0.01052 * u);
             const double r = frcp3(a * b);
             aj = na * b * r;
             sj = fma(na, b, nb * a) * r;
         }
         const double am = 0.32 * (u + 47.13) * frcp3(fma(-c.k47, g01, 1.));
-        const double sm = am + 0.08 * fexp_fast(u * (-1. / 11.));
+        const double sm = am + 0.08 * EX(u * (-1. / 11.));
         const double m = gatef(io.ld(0), dt, am, sm);
         const double h = gatef(io.ld(1), dt, ah, sh);
         const double j = gatef(io.ld(2), dt, aj, sj);
@@ -444,15 +454,15 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         const double E_Si = fma(-13.0287, flog(cai), 7.7);
         const double I_Si = c.gsi * d * f * (u - E_Si);
         {
-            const double n1 = 0.095 * fexp_fast(-0.01 * (u - 5.));
-            const double a = 1. + fexp_fast(-0.072 * (u - 5.));
-            const double n2 = 0.07 * fexp_fast(-0.017 * (u + 44.));
+            const double n1 = 0.095 * EX(-0.01 * (u - 5.));
+            const double a = 1. + EX(-0.072 * (u - 5.));
+            const double n2 = 0.07 * EX(-0.017 * (u + 44.));
             const double b = fma(c.kd, g05, 1.);
             const double r = frcp3(a * b);
             d = gatef(d, dt, n1 * b * r, fma(n1, b, n2 * a) * r);
         }
         {
-            const double n1 = 0.012 * fexp_fast(-0.008 * (u + 28.));
+            const double n1 = 0.012 * EX(-0.008 * (u + 28.));
             const double a = fma(c.kf3, g15, 1.);
             const double n2 = 0.0065 * c.kf1 * g02;
             const double b = fma(c.kf2, g20, 1.);
@@ -466,8 +476,8 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         double x = io.ld(5);
         const double I_K = c.G_K * x * Xi * (u - c.E_K);
         {
-            const double n1 = 0.0005 * fexp_fast(0.083 * (u + 50.));
-            const double a = 1. + fexp_fast(0.057 * (u + 50.));
+            const double n1 = 0.0005 * EX(0.083 * (u + 50.));
+            const double a = 1. + EX(0.057 * (u + 50.));
             const double n2 = 0.0013 * c.kx1 * g06;
             const double b = fma(c.kx2, g04, 1.);
             const double r = frcp3(a * b);
@@ -476,12 +486,12 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         io.st(5, x);
         // ---- I_K1, I_Kp, I_b (calc_ik1 :359-408, calc_ikp :411-427, calc_ib :430-443)
         const double y = u - c.E_K1;
-        const double a1 = 1. + fexp_fast_clamped(0.2385 * (y - 59.215));
-        const double n1 = fma(0.49124, fexp_fast_clamped(0.08032 * (y + 5.476)),
-                              fexp_fast_clamped(0.06175 * (y - 594.31)));
-        const double b1 = 1.02 * (1. + fexp_fast_clamped(-0.5143 * (y + 4.753)));
+        const double a1 = 1. + EXC(0.2385 * (y - 59.215));
+        const double n1 = fma(0.49124, EXC(0.08032 * (y + 5.476)),
+                              EXC(0.06175 * (y - 594.31)));
+        const double b1 = 1.02 * (1. + EXC(-0.5143 * (y + 4.753)));
         const double ik1 = c.G_K1 * (b1 * frcp3(fma(n1, a1, b1))) * y;
-        const double ikp = c.gkp * frcp3(1. + fexp_fast((7.488 - u) * (1. / 5.98))) * y;
+        const double ikp = c.gkp * frcp3(1. + EX((7.488 - u) * (1. / 5.98))) * y;
         const double ib = c.gb * (u + 59.87);
         un -= dt * (ina + I_Si + (ik1 + ikp + ib) + I_K);
     }
@@ -1139,9 +1149,11 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         double l_nao, l_ko, l_cao, F_RT, e_fca, e_urel;
         double k47, k32, k5a, k5b, k17a, k17b, k17c, k85;
         int fast_ok;
+        double ec[8];      // fexp's reduction / polynomial constants (fexp_fill_consts)
     };
     static bool derive(const double *p, double dt, Consts &c)
     {
+        fexp_fill_consts(c.ec);
         const double F = p[9], T = p[10], R = p[11], Vj = p[13], Vup = p[14], Vrel = p[15],
                      nao = p[18], ko = p[19], kmko = p[23], kmnancx = p[24], kmcancx = p[25];
         c.dt = dt; c.gna = p[0]; c.gnab = p[1]; c.gk1 = p[2]; c.gks = p[4]; c.gto = p[5];
@@ -1219,66 +1231,74 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
                                   double ki, double cai)
     {
         const double dt = c.dt;
+        const double *ec = c.ec;       // kernel-parameter bank -> uniform registers
+        auto EX = [ec](double x) { return fexp_fast_p(x, ec); };
+        auto EXN = [ec](double x) { return fexp_fast_p(x < -700.0 ? -700.0 : x, ec); };
+        auto EXC = [ec](double x) {
+            x = x < -700.0 ? -700.0 : x;
+            return fexp_fast_p(x > 700.0 ? 700.0 : x, ec);
+        };
+        (void)EXN; (void)EXC;
         const double ena = c.RT_F * (c.l_nao - flog(nai));
         const double ek = c.RT_F * (c.l_ko - flog(ki));
         const double eca = c.RT_2F * (c.l_cao - flog(cai));
-        const double g01 = fexp_fast(-0.1 * u);
-        const double g5 = fexp_fast(-0.2 * u);                    // exp(-u / 5)
-        const double g17 = fexp_fast(u * (1. / 17.)), i17 = frcp3(g17);
+        const double g01 = EX(-0.1 * u);
+        const double g5 = EX(-0.2 * u);                    // exp(-u / 5)
+        const double g17 = EX(u * (1. / 17.)), i17 = frcp3(g17);
         // ---- I_Na
         double ina;
         {
             const double am = u == -47.13 ? 3.2 : 0.32 * (u + 47.13) * frcp3(fma(-c.k47, g01, 1.));
-            const double sm = am + 0.08 * fexp_fast(u * (-1. / 11.));
-            const double m = rlf(am * frcp3(sm), io.ld(5), fexp_fast_neg(-dt * sm));
+            const double sm = am + 0.08 * EX(u * (-1. / 11.));
+            const double m = rlf(am * frcp3(sm), io.ld(5), EXN(-dt * sm));
             double h_inf, sh, j_inf, sj;
             if (u >= -40) {
                 h_inf = 0.;
-                sh = frcp3(0.13 * (1. + fexp_fast((u + 10.66) * (-1. / 11.1))));
+                sh = frcp3(0.13 * (1. + EX((u + 10.66) * (-1. / 11.1))));
                 j_inf = 0.;
-                sj = 0.3 * fexp_fast(-0.0000002535 * u) * frcp3(fma(c.k32, g01, 1.));
+                sj = 0.3 * EX(-0.0000002535 * u) * frcp3(fma(c.k32, g01, 1.));
             } else {
-                const double ah = 0.135 * fexp_fast((80. + u) * (-1. / 6.8));
-                sh = ah + (3.56 * fexp_fast(0.079 * u) + 310000. * fexp_fast(0.35 * u));
+                const double ah = 0.135 * EX((80. + u) * (-1. / 6.8));
+                sh = ah + (3.56 * EX(0.079 * u) + 310000. * EX(0.35 * u));
                 h_inf = ah * frcp3(sh);
-                const double a = 1. + fexp_fast(0.311 * (u + 79.23));
-                const double b = 1. + fexp_fast(-0.1378 * (u + 40.14));
-                const double nab = (-127140. * fexp_fast(0.2444 * u) -
-                                    0.00003474 * fexp_fast(-0.04391 * u)) * (u + 37.78) * b;
-                const double tot = fma(0.1212 * fexp_fast(-0.01052 * u), a, nab);   // na b + nb a
+                const double a = 1. + EX(0.311 * (u + 79.23));
+                const double b = 1. + EX(-0.1378 * (u + 40.14));
+                const double nab = (-127140. * EX(0.2444 * u) -
+                                    0.00003474 * EX(-0.04391 * u)) * (u + 37.78) * b;
+                const double tot = fma(0.1212 * EX(-0.01052 * u), a, nab);   // na b + nb a
                 sj = tot * frcp3(a * b);
                 j_inf = nab * frcp3(tot);
             }
-            const double h = rlf(h_inf, io.ld(6), fexp_fast_neg(-dt * sh));
-            const double j = rlf(j_inf, io.ld(7), fexp_fast_neg(-dt * sj));
+            const double h = rlf(h_inf, io.ld(6), EXN(-dt * sh));
+            const double j = rlf(j_inf, io.ld(7), EXN(-dt * sj));
             io.st(5, m); io.st(6, h); io.st(7, j);
             ina = c.gna * (m * (m * m)) * h * j * (u - ena);
         }
-        const double ik1 = c.gk1 * (u - ek) * frcp3(1. + fexp_fast(0.07 * (u + 80.)));
+        const double ik1 = c.gk1 * (u - ek) * frcp3(1. + EX(0.07 * (u + 80.)));
         // ---- I_to, I_Kur (share tau_o)
         double ito, ikur;
         {
-            const double A = fma(c.k85, i17 * i17, fexp_fast((u - 30.) * (-1. / 59.0)));
+            const double A = fma(c.k85, i17 * i17, EX((u - 30.) * (-1. / 59.0)));
             const double B = fma(c.k17c, g17, 2.5);
             const double rtau_o = c.kq10 * 0.65 * (A + B) * frcp3(A * B);
-            const double o_inf = frcp3(1. + fexp_fast((u + 20.47) * (-1. / 17.54)));
-            const double C = 18.53 + fexp_fast((u + 113.7) * (1. / 10.95));
-            const double D = 35.56 + fexp_fast((u + 1.26) * (-1. / 7.44));
+            const double o_inf = frcp3(1. + EX((u + 20.47) * (-1. / 17.54)));
+            const double C = 18.53 + EX((u + 113.7) * (1. / 10.95));
+            const double D = 35.56 + EX((u + 1.26) * (-1. / 7.44));
             const double rtau_oi = c.kq10 * (C + D) * frcp3(C * D);
-            const double oi_inf = frcp3(1. + fexp_fast((u + 43.1) * (1. / 5.3)));
-            const double e_o = fexp_fast_neg(-dt * rtau_o);
+            const double oi_inf = frcp3(1. + EX((u + 43.1) * (1. / 5.3)));
+            const double e_o = EXN(-dt * rtau_o);
             const double oa = rlf(o_inf, io.ld(10), e_o);
-            const double oi = rlf(oi_inf, io.ld(11), fexp_fast_neg(-dt * rtau_oi));
+            const double oi = rlf(oi_inf, io.ld(11), EXN(-dt * rtau_oi));
             io.st(10, oa); io.st(11, oi);
             ito = c.gto * (oa * (oa * oa)) * oi * (u - ek);
 
-            const double gkur = fma(0.05, frcp3(1. + fexp_fast((u - 15.) * (-1. / 13.0))), 0.005);
-            const double ua_inf = frcp3(1. + fexp_fast((u + 30.3) * (-1. / 9.6)));
-            const double rtau_ui = c.kq10 * (frcp3(21. + fexp_fast((u - 185.) * (-1. / 28.0))) +
-                                             fexp_fast((u - 158.) * (1. / 16.0)));
-            const double ui_inf = frcp3(1. + fexp_fast((u - 99.45) * (1. / 27.48)));
+            const double gkur = fma(0.05, frcp3(1. + EX((u - 15.) * (-1. / 13.0))), 0.005);
+            const double ua_inf = frcp3(1. + EX((u + 30.3) * (-1. / 9.6)));
+            const double rtau_ui = c.kq10 * (frcp3(21. + EX((u - 185.) * (-1. / 28.0))) +
+                                             EX((u - 158.) * (1. / 16.0)));
+            const double ui_inf = frcp3(1. + EX((u - 99.45) * (1. / 27.48)));
             const double ua = rlf(ua_inf, io.ld(12), e_o);          // tau_ua == tau_o
-            const double ui = rlf(ui_inf, io.ld(13), fexp_fast_neg(-dt * rtau_ui));
+            const double ui = rlf(ui_inf, io.ld(13), EXN(-dt * rtau_ui));
             io.st(12, ua); io.st(13, ui);
             ikur = c.gkur_coeff * gkur * (ua * (ua * ua)) * ui * (u - ek);
         }
@@ -1286,51 +1306,51 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         double ikr;
         {
             const double d1 = fma(-c.k5a, g5, 1.);                                   // 1 - exp(-(u+14.1)/5)
-            const double d2 = fexp_fast((u - 3.3328) * (1. / 5.1237)) - 1.;
+            const double d2 = EX((u - 3.3328) * (1. / 5.1237)) - 1.;
             const double rtau_xr = fma(0.0003 * (u + 14.1), d2, 0.000073898 * (u - 3.3328) * d1) *
                                    frcp3(d1 * d2);
-            const double xr_inf = frcp3(1. + fexp_fast((u + 14.1) * (-1. / 6.5)));
-            const double xr = rlf(xr_inf, io.ld(15), fexp_fast_neg(-dt * rtau_xr));
+            const double xr_inf = frcp3(1. + EX((u + 14.1) * (-1. / 6.5)));
+            const double xr = rlf(xr_inf, io.ld(15), EXN(-dt * rtau_xr));
             io.st(15, xr);
-            ikr = 0.0294 * xr * (u - ek) * frcp3(1. + fexp_fast((u + 15.) * (1. / 22.4)));
+            ikr = 0.0294 * xr * (u - ek) * frcp3(1. + EX((u + 15.) * (1. / 22.4)));
         }
         // ---- I_Ks (gate in slot 14)
         double iks;
         {
             const double d1 = fma(-c.k17a, i17, 1.);                                 // 1 - exp(-(u-19.9)/17)
-            const double d2 = fexp_fast((u - 19.9) * (1. / 9.)) - 1.;
+            const double d2 = EX((u - 19.9) * (1. / 9.)) - 1.;
             const double rtau_xs = 2. * (u - 19.9) * fma(0.00004, d2, 0.000035 * d1) * frcp3(d1 * d2);
-            const double xs_inf = frcp3(fsqrt(1. + fexp_fast((u - 19.9) * (-1. / 12.7))));
-            const double xs = rlf(xs_inf, io.ld(14), fexp_fast_neg(-dt * rtau_xs));
+            const double xs_inf = frcp3(fsqrt(1. + EX((u - 19.9) * (-1. / 12.7))));
+            const double xs = rlf(xs_inf, io.ld(14), EXN(-dt * rtau_xs));
             io.st(14, xs);
             iks = c.gks * (xs * xs) * (u - ek);
         }
         // ---- I_CaL
         double ical;
         {
-            const double e10 = fexp_fast((u + 10.) * (-1. / 6.24));
+            const double e10 = EX((u + 10.) * (-1. / 6.24));
             const double rtau_d = 0.035 * (u + 10.) * (1. + e10) * frcp3(1. - e10);
-            const double d_inf = frcp3(1. + fexp_fast((u + 10.) * (-1. / 8.0)));
-            const double rtau_f = fma(0.0197, fexp_fast(-(0.0337 * 0.0337) * ((u + 10.) * (u + 10.))),
+            const double d_inf = frcp3(1. + EX((u + 10.) * (-1. / 8.0)));
+            const double rtau_f = fma(0.0197, EX(-(0.0337 * 0.0337) * ((u + 10.) * (u + 10.))),
                                       0.02) * (1. / 9.);
-            const double f_inf = frcp3(1. + fexp_fast((u + 28.) * (1. / 6.9)));
+            const double f_inf = frcp3(1. + EX((u + 28.) * (1. / 6.9)));
             const double fca_inf = frcp3(fma(cai, 1. / 0.00035, 1.));
-            const double d = rlf(d_inf, io.ld(8), fexp_fast_neg(-dt * rtau_d));
-            const double f = rlf(f_inf, io.ld(9), fexp_fast_neg(-dt * rtau_f));
+            const double d = rlf(d_inf, io.ld(8), EXN(-dt * rtau_d));
+            const double f = rlf(f_inf, io.ld(9), EXN(-dt * rtau_f));
             const double fca = rlf(fca_inf, io.ld(16), c.e_fca);
             io.st(8, d); io.st(9, f); io.st(16, fca);
             ical = c.gcal * d * f * fca * (u - 65.);
         }
         // ---- I_NaK, I_NaCa
         const double x = u * c.F_RT;
-        const double en01 = fexp_fast(-0.1 * x);
+        const double en01 = EX(-0.1 * x);
         const double en02 = en01 * en01, en04 = en02 * en02, en08 = en04 * en04;
         const double en_x = en08 * en02;                                             // exp(-x)
         const double qn = c.kmnai * frcp3(nai);
         const double inak = c.inakmax * c.ko_kmko *
                             frcp3(fma(0.0365 * c.nak_s, en_x, fma(0.1245, en01, 1.)) *
                                   fma(qn, fsqrt(qn), 1.));
-        const double e_rev = fexp_fast(-0.65 * x);
+        const double e_rev = EX(-0.65 * x);
         const double inaca = c.inacamax * e_rev * fma(-c.nao3 * cai, en_x, (nai * (nai * nai)) * c.cao) *
                              frcp3(en_x * c.ncx_t12 * fma(c.ksatncx, e_rev, 1.));
         const double ibca = c.gcab * (u - eca);
@@ -1344,15 +1364,15 @@ template <> struct Model<FWB_MODEL_COURTEMANCHE> {
         double irel;
         {
             const double Fn = c.Fn_a * io.ld(17) - c.Fn_b * (0.5 * ical - 0.2 * inaca);
-            const double u_inf = frcp3(1. + fexp_fast_clamped((Fn - 3.4175e-13) * (-1. / 13.67e-16)));
+            const double u_inf = frcp3(1. + EXC((Fn - 3.4175e-13) * (-1. / 13.67e-16)));
             const double rtau_v = frcp3(fma(2.09, u_inf, 1.91));
-            const double v_inf = 1. - frcp3(1. + fexp_fast_clamped((Fn - 6.835e-14) * (-1. / 13.67e-16)));
+            const double v_inf = 1. - frcp3(1. + EXC((Fn - 6.835e-14) * (-1. / 13.67e-16)));
             const double e79 = c.k5b * g5;                                           // exp(-(u-7.9)/5)
             const double rtau_w = fma(0.3, e79, 1.) * (u - 7.9) * frcp3(6. * (1. - e79));
             const double w_inf = 1. - frcp3(fma(c.k17b, i17, 1.));
             const double urel = rlf(u_inf, io.ld(19), c.e_urel);
-            const double vrel = rlf(v_inf, io.ld(18), fexp_fast_neg(-dt * rtau_v));
-            const double wrel = rlf(w_inf, io.ld(20), fexp_fast_neg(-dt * rtau_w));
+            const double vrel = rlf(v_inf, io.ld(18), EXN(-dt * rtau_v));
+            const double wrel = rlf(w_inf, io.ld(20), EXN(-dt * rtau_w));
             irel = c.krel * (urel * urel) * vrel * wrel * (carel - cai);
             io.st(17, irel); io.st(19, urel); io.st(18, vrel); io.st(20, wrel);
         }
