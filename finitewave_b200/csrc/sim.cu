@@ -128,6 +128,7 @@ struct FwbSim {
     int32_t *node_of;                // [n_myo] compact index -> flat node (multi-step kernel,
                                      // packed mode of the tile kernel)
     bool packed;                     // tile kernel in packed mode (sparse tissue, no halo)
+    bool small_off;                  // the multi-step cluster kernel does not fit this tissue
     bool brick_ok;
     alignas(64) CUtensorMap tmap[2]; // of buf[0] / buf[1]
     // slab halo
@@ -214,7 +215,7 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
     s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0; s->device_steps = 0;
     s->tile_base = nullptr; s->records = nullptr;
     s->tile_rec = nullptr; s->pos_of = nullptr; s->defer = nullptr; s->brick_ok = false;
-    s->node_of = nullptr; s->packed = false;
+    s->node_of = nullptr; s->packed = false; s->small_off = false;
     s->halo_on = false; s->epoch = 0; s->flags = nullptr;
     memset(s->peer_u, 0, sizeof(s->peer_u));
     memset(s->peer_flags, 0, sizeof(s->peer_flags));
@@ -580,9 +581,9 @@ __global__ void node_of_kernel(const int32_t *wl, int64_t n_work, const uint32_t
 static int64_t small_run_length(FwbSim *s, int64_t max_steps, Tracker **fused, int64_t *samples)
 {
     *fused = nullptr; *samples = 0;
-    if (!s->entry->launch_small || s->entry->n_state > 4 || s->halo_on) return 0;
-    if (s->n_myo < 1 || s->n_myo > (int64_t)SMALL_MAX_CTAS * SMALL_THREADS * SMALL_MAX_NPT) return 0;
-    if (s->g.n_nodes >= ((int64_t)1 << 31)) return 0;
+    if (!s->entry->launch_small || s->entry->n_state > 4 || s->halo_on || s->small_off) return 0;
+    if (s->n_myo < 1) return 0;
+    if (s->g.n_nodes > (int64_t)8 * SMALL_MAX_CHUNK) return 0;   // dense grid in DSMEM (8 CTAs always fit)
     const char *off = getenv("FWB_NO_SMALL_KERNEL");
     if (off && off[0] == '1') return 0;
     Tracker *act = nullptr;
@@ -625,21 +626,13 @@ static int ensure_node_of(FwbSim *s)
 static int run_small(FwbSim *s, int64_t m, Tracker *act, int64_t samples)
 {
     cudaStream_t st = s->stream;
-    {
-        int rc = ensure_node_of(s);
-        if (rc) return rc;
-    }
     StepCommon k;
     memset(&k, 0, sizeof(k));
     k.g = s->g; k.w = s->weights; k.state = s->state;
     SmallArgs sa;
     memset(&sa, 0, sizeof(sa));
-    sa.node_of = s->node_of;
     sa.buf[0] = s->buf[0]; sa.buf[1] = s->buf[1];
     sa.cur = s->cur; sa.n_steps = (int)m; sa.n_myo = s->n_myo;
-    const int64_t per = (int64_t)SMALL_MAX_CTAS * SMALL_THREADS;
-    sa.npt = (int)((s->n_myo + per - 1) / per);
-    if (s->n_myo <= SMALL_THREADS) sa.npt = 1;
     sa.step0 = s->step; sa.t0 = s->t;
     if (act) {
         sa.act_t = act->act_t; sa.act_thr = act->thr;
@@ -671,9 +664,13 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
                                                &act, &samples);
             if (m >= 4) {
                 int rc = run_small(s, m, act, samples);
-                if (rc) return rc;
-                it += m - 1;
-                continue;
+                if (rc == FWB_E_UNSUPPORTED) {
+                    s->small_off = true;         // too large for one cluster: per-step kernels
+                } else {
+                    if (rc) return rc;
+                    it += m - 1;
+                    continue;
+                }
             }
         }
         double *u = s->buf[s->cur];

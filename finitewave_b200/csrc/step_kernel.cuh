@@ -1109,22 +1109,24 @@ static int launch_one(const StepCommon &k, const void *consts, cudaStream_t s)
 // step_kernel_small: tissues of a few thousand nodes (the README quick start is 100 x 100)
 //
 // At this size one time step is ~2 us of launch latency around ~0.2 us of work.  This kernel
-// runs MANY steps in one launch: a single thread-block cluster (<= 8 CTAs x 1024 threads,
-// distributed over 8 SMs) owns the whole tissue, every thread keeps the state of its (<= 4)
-// nodes in shared memory for the whole run, reads the stencil's u operands from the L2-
-// resident ping-pong buffers (ld.global.cg: another CTA of the cluster wrote them), and the
-// steps are separated by a hardware cluster barrier (release / acquire at cluster scope)
-// instead of a kernel boundary.  The arithmetic is the per-step kernels' own (same slot
-// order, same Model::ionic), so the result is bit-identical; the host (fwb_sim_run) only
-// uses it for runs of steps in which no stimulus fires and only the activation-time tracker
-// samples.  t advances by the same repeated fp64 addition as on the host.
+// runs MANY steps in one launch: a single thread-block cluster (<= 8 CTAs x 1024 threads on 8
+// SMs) owns the whole tissue.  The two potential buffers live in DISTRIBUTED SHARED MEMORY for
+// the whole run -- CTA k holds the dense nodes [k * chunk, (k + 1) * chunk), chunk a power of
+// two -- every thread keeps the state of its (<= 4) nodes in its CTA's shared memory, the
+// stencil operands are `ld.shared::cluster` reads (mapa: node -> owning CTA), u_new is a
+// `st.shared::cluster` store, and the steps are separated by a hardware cluster barrier
+// (release / acquire at cluster scope) instead of a kernel boundary or an L2 round trip.
+// The arithmetic is the per-step kernels' own (same slot order, same Model::ionic), so the
+// result is bit-identical; the host (fwb_sim_run) only uses it for runs of steps in which no
+// stimulus fires and only the activation-time tracker samples.  t advances by the same
+// repeated fp64 addition as on the host.
 // ---------------------------------------------------------------------------
 struct SmallArgs {
-    const int32_t *node_of;    // [n_myo] flat node of each compact index
     double *buf[2];            // the two u buffers; buf[cur] is u at the first step
     int cur;
     int n_steps;
     int npt;                   // nodes per thread
+    int chunk;                 // dense nodes per CTA (a multiple of 32, <= 4096)
     int64_t n_myo;
     int64_t step0;
     double t0;
@@ -1133,7 +1135,8 @@ struct SmallArgs {
     double act_thr, act_start, act_end;
     int64_t act_every;
 };
-constexpr int SMALL_THREADS = 1024, SMALL_MAX_CTAS = 8, SMALL_MAX_NPT = 4;
+constexpr int SMALL_THREADS = 1024, SMALL_MAX_CTAS = 16, SMALL_MAX_NPT = 4, SMALL_MAX_CHUNK = 4096;
+constexpr size_t SMALL_SMEM_MAX = 220 * 1024;     // dynamic shared memory of one CTA
 
 // state of one node in shared memory: slot q of node-slot j of thread tid
 struct StateIOSmem {
@@ -1147,6 +1150,21 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n"
                  "barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// distributed shared memory: the word at local shared address `laddr` of CTA `rank`
+__device__ __forceinline__ double dsmem_ld(uint32_t laddr, uint32_t rank)
+{
+    uint32_t ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(laddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t laddr, uint32_t rank, double v)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
 
 template <class M, int DIM, int ST>
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
@@ -1158,44 +1176,78 @@ step_kernel_small(const __grid_constant__ StepArgs<M> A, const __grid_constant__
     const StepCommon &P = A.k;
     const Grid &g = P.g;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    double *const st_sm = reinterpret_cast<double *>(dyn_smem);      // [npt][NS][SMALL_THREADS]
+    const int chunk = sa.chunk;                                       // <= npt * SMALL_THREADS
+    double *const ub = reinterpret_cast<double *>(dyn_smem);          // [2][chunk] this CTA's nodes
+    double *const st_sm = ub + 2 * chunk;                             // [npt][NS][SMALL_THREADS]
+    // (the cluster barrier invalidates L1, so everything a step needs lives in shared memory)
+    double *const w_sm = st_sm + (size_t)sa.npt * NS * SMALL_THREADS;  // [npt][K][SMALL_THREADS]
     const int tid = threadIdx.x;
-    const int64_t T = (int64_t)gridDim.x * SMALL_THREADS;
-    const int64_t gt = (int64_t)blockIdx.x * SMALL_THREADS + tid;
+    const uint32_t rank = blockIdx.x;                                 // one cluster: rank = block
+    const uint32_t ub_addr = smem_u32(ub);
+    const int64_t base = (int64_t)rank * chunk;
     exp_table_to_smem();
-    __syncthreads();
 
-    // state -> shared memory
-    for (int j = 0; j < sa.npt; ++j) {
-        const int64_t c = gt + j * T;
-        if (c < sa.n_myo) {
-#pragma unroll
-            for (int q = 0; q < M::NS; ++q)
-                st_sm[(j * NS + q) * SMALL_THREADS + tid] = P.state[(int64_t)q * g.ld + c];
-        }
+    // CTA `rank` owns the dense nodes [base, base + chunk): both potential buffers go to its
+    // shared memory, thread tid owns the nodes base + tid + j * 1024 (the updated ones among
+    // them: their state and weight rows go to shared memory too)
+    for (int i = tid; i < chunk; i += SMALL_THREADS) {
+        const int64_t m = base + i;
+        ub[i] = m < g.n_nodes ? sa.buf[0][m] : 0.0;
+        ub[chunk + i] = m < g.n_nodes ? sa.buf[1][m] : 0.0;
     }
+    uint32_t live = 0;                 // bit j: node-slot j is an updated node
+    for (int j = 0; j < sa.npt; ++j) {
+        const int loc0 = tid + j * SMALL_THREADS;
+        const int64_t m = base + loc0;
+        if (loc0 >= chunk || m >= g.n_nodes) continue;
+        const uint32_t bits = g.chunk_bits[m >> 5];
+        const int ln = (int)(m & 31);
+        if (!((bits >> ln) & 1u)) continue;
+        const int64_t c = (int64_t)g.chunk_base[m >> 5] + __popc(bits & ((1u << ln) - 1u));
+        live |= 1u << j;
+#pragma unroll
+        for (int q = 0; q < M::NS; ++q)
+            st_sm[(j * NS + q) * SMALL_THREADS + tid] = P.state[(int64_t)q * g.ld + c];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            w_sm[(j * K + k) * SMALL_THREADS + tid] = P.w[(int64_t)k * g.ld + c];
+    }
+    cluster_sync_all();
 
     double t = sa.t0;
     int cur = sa.cur;
+    int64_t act_rem = sa.act_every > 0 ? sa.step0 % sa.act_every : 0;
     for (int it = 0; it < sa.n_steps; ++it) {
-        const double *__restrict__ u = sa.buf[cur];
-        double *__restrict__ u_new = sa.buf[cur ^ 1];
-        const bool do_act = sa.act_t && !(sa.act_start > t || t > sa.act_end) &&
-                            (sa.step0 + it) % sa.act_every == 0;
+        const double *usrc = ub + (size_t)cur * chunk;
+        double *udst = ub + (size_t)(cur ^ 1) * chunk;
+        const uint32_t src = ub_addr + (uint32_t)cur * (uint32_t)chunk * 8u;
+        const bool do_act = sa.act_t && !(sa.act_start > t || t > sa.act_end) && act_rem == 0;
+        act_rem = act_rem + 1 == sa.act_every ? 0 : act_rem + 1;
+#ifdef FWB_SMALL_NOWORK          // (timing experiments only)
+        for (int j = 0; j < 0; ++j) {
+#else
         for (int j = 0; j < sa.npt; ++j) {
-            const int64_t c = gt + j * T;
-            if (c >= sa.n_myo) break;
-            const int64_t n = __ldg(sa.node_of + c);
-            const double *__restrict__ up = u + n;
-            const double *__restrict__ w = P.w + c;
+#endif
+            if (!((live >> j) & 1u)) continue;
+            const int32_t loc = tid + j * SMALL_THREADS;              // node inside this CTA's range
+            const double *w = w_sm + (j * K) * SMALL_THREADS + tid;
             double un[K], wn[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const Off o = S::at(k);
-                const int64_t off = (DIM == 3 ? (int64_t)o.p * g.s_plane : 0) +
-                                    (int64_t)o.r * g.s_row + o.l;
-                un[k] = __ldcg(up + off);
-                wn[k] = __ldg(w + (int64_t)k * g.ld);
+                const int32_t off = (DIM == 3 ? o.p * (int32_t)g.s_plane : 0) +
+                                    o.r * (int32_t)g.s_row + o.l;
+                const int32_t nb = loc + off;
+                // most neighbours are this CTA's own: plain shared memory; the others (near
+                // the ends of the range) come from the neighbour CTA's shared memory
+                if ((uint32_t)nb < (uint32_t)chunk) {
+                    un[k] = usrc[nb];
+                } else {
+                    const uint32_t m = (uint32_t)((int32_t)base + nb);
+                    const uint32_t owner = m / (uint32_t)chunk;
+                    un[k] = dsmem_ld(src + (m - owner * (uint32_t)chunk) * 8u, owner);
+                }
+                wn[k] = w[k * SMALL_THREADS];
             }
             double acc = mul(un[0], wn[0]);
 #pragma unroll
@@ -1205,46 +1257,99 @@ step_kernel_small(const __grid_constant__ StepArgs<M> A, const __grid_constant__
             for (int k = 0; k < K; ++k)
                 if (S::at(k).p == 0 && S::at(k).r == 0 && S::at(k).l == 0) uc = un[k];
             if (do_act) {
+                const int64_t n = base + loc;
                 const double a = sa.act_t[n];
                 if (a < 0 && uc > sa.act_thr) sa.act_t[n] = t;
             }
             StateIOSmem io{st_sm + (j * NS) * SMALL_THREADS + tid};
             M::ionic(uc, acc, io, A.c);
-            __stcg(u_new + n, acc);
+            udst[loc] = acc;
         }
         t += A.c.dt;
         cur ^= 1;
+#ifndef FWB_SMALL_NOBAR          // (timing experiments only)
         cluster_sync_all();
+#endif
     }
 
-    // state back to the compact rows
-    for (int j = 0; j < sa.npt; ++j) {
-        const int64_t c = gt + j * T;
-        if (c < sa.n_myo) {
-#pragma unroll
-            for (int q = 0; q < M::NS; ++q)
-                if ((M::WRITE_MASK >> q) & 1u)
-                    P.state[(int64_t)q * g.ld + c] = st_sm[(j * NS + q) * SMALL_THREADS + tid];
+    // both buffers and the state back to global memory
+    for (int i = tid; i < chunk; i += SMALL_THREADS) {
+        const int64_t m = base + i;
+        if (m < g.n_nodes) {
+            sa.buf[0][m] = ub[i];
+            sa.buf[1][m] = ub[chunk + i];
         }
+    }
+    for (int j = 0; j < sa.npt; ++j) {
+        if (!((live >> j) & 1u)) continue;
+        const int64_t m = base + tid + j * SMALL_THREADS;
+        const uint32_t bits = g.chunk_bits[m >> 5];
+        const int64_t c = (int64_t)g.chunk_base[m >> 5] + __popc(bits & ((1u << (int)(m & 31)) - 1u));
+#pragma unroll
+        for (int q = 0; q < M::NS; ++q)
+            if ((M::WRITE_MASK >> q) & 1u)
+                P.state[(int64_t)q * g.ld + c] = st_sm[(j * NS + q) * SMALL_THREADS + tid];
     }
 }
 
 template <class M, int DIM, int ST>
-static int launch_small_one(const StepCommon &k, const void *consts, const SmallArgs &sa,
+static int launch_small_one(const StepCommon &k, const void *consts, const SmallArgs &sa_in,
                             cudaStream_t s)
 {
     StepArgs<M> a;
     a.k = k;
     a.c = *reinterpret_cast<const typename M::Consts *>(consts);
-    const int64_t per_cta = (int64_t)SMALL_THREADS * sa.npt;
-    int ctas = (int)((sa.n_myo + per_cta - 1) / per_cta);
-    if (ctas < 1) ctas = 1;
-    if (ctas > SMALL_MAX_CTAS) { set_error("step_kernel_small: tissue too large"); return FWB_E_UNSUPPORTED; }
-    constexpr int NS = M::NS > 0 ? M::NS : 1;
-    const size_t smem = (size_t)sa.npt * NS * SMALL_THREADS * sizeof(double);
+    SmallArgs sa = sa_in;
+    // CTA r owns the dense nodes [r * chunk, (r + 1) * chunk).  As many CTAs (= SMs: the step
+    // is FP64-throughput-bound inside each of them) as one cluster may have -- 16 where the
+    // device schedules a non-portable cluster of this kernel, else 8 -- but not more than one
+    // per 256 nodes
     auto kern = step_kernel_small<M, DIM, ST>;
     int rc;
-    if ((rc = ensure_dyn_smem(kern, (size_t)SMALL_MAX_NPT * NS * SMALL_THREADS * sizeof(double)))) return rc;
+    if ((rc = ensure_dyn_smem(kern, SMALL_SMEM_MAX))) return rc;
+    static std::mutex mu;
+    static int max_ctas_of[64] = {0};
+    int dev = 0;
+    FWB_CUDA(cudaGetDevice(&dev));
+    int max_ctas = 8;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 64 && max_ctas_of[dev]) {
+            max_ctas = max_ctas_of[dev];
+        } else {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t q;
+                memset(&q, 0, sizeof(q));
+                q.gridDim = dim3(SMALL_MAX_CTAS); q.blockDim = dim3(SMALL_THREADS);
+                q.dynamicSmemBytes = SMALL_SMEM_MAX;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = SMALL_MAX_CTAS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                q.attrs = qa; q.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q) == cudaSuccess && n_clusters >= 1)
+                    max_ctas = SMALL_MAX_CTAS;
+            }
+            cudaGetLastError();
+            if (dev < 64) max_ctas_of[dev] = max_ctas;
+        }
+    }
+    int ctas = (int)((k.g.n_nodes + 255) / 256);
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    int chunk = (int)(((k.g.n_nodes + ctas - 1) / ctas + 31) / 32 * 32);
+    if (chunk > SMALL_MAX_CHUNK) { set_error("step_kernel_small: tissue too large"); return FWB_E_UNSUPPORTED; }
+    ctas = (int)((k.g.n_nodes + chunk - 1) / chunk);
+    sa.chunk = chunk;
+    sa.npt = (chunk + SMALL_THREADS - 1) / SMALL_THREADS;
+    constexpr int NS = M::NS > 0 ? M::NS : 1;
+    constexpr int K = Stencil<DIM, ST>::K;
+    const size_t smem = (size_t)2 * chunk * sizeof(double) +
+                        (size_t)sa.npt * (NS + K) * SMALL_THREADS * sizeof(double);
+    if (smem > SMALL_SMEM_MAX) {
+        set_error("step_kernel_small: tissue too large for shared memory");
+        return FWB_E_UNSUPPORTED;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);
