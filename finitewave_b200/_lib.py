@@ -49,6 +49,7 @@ def _sig(L):
     L.fwb_sim_set_tile_base.argtypes = [p, p, p]
     L.fwb_sim_set_tiles.argtypes = [p, p, p]
     L.fwb_sim_set_packed.argtypes = [p, c_int]
+    L.fwb_sim_set_copy_idle.argtypes = [p, c_int]
     L.fwb_order_tiles.argtypes = [c_int, POINTER(c_int64), c_int, c_int, c_int64, c_int64, p, p, p,
                                   c_int64, p, p, p, p]
     L.fwb_gather_compact.argtypes = [p, p, c_int64, p, p, p]

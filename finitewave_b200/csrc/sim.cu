@@ -129,6 +129,7 @@ struct FwbSim {
                                      // packed mode of the tile kernel)
     bool packed;                     // tile kernel in packed mode (sparse tissue, no halo)
     bool small_off;                  // the multi-step cluster kernel does not fit this tissue
+    bool copy_idle;                  // see StepCommon::copy_idle (fwb_sim_set_copy_idle)
     bool brick_ok;
     alignas(64) CUtensorMap tmap[2]; // of buf[0] / buf[1]
     // slab halo
@@ -215,7 +216,7 @@ extern "C" int fwb_sim_create(FwbSim **out, int dim, const int64_t *shape, int m
     s->ecg_partial = nullptr; s->ecg_partial_cap = 0; s->launches = 0; s->device_steps = 0;
     s->tile_base = nullptr; s->records = nullptr;
     s->tile_rec = nullptr; s->pos_of = nullptr; s->defer = nullptr; s->brick_ok = false;
-    s->node_of = nullptr; s->packed = false; s->small_off = false;
+    s->node_of = nullptr; s->packed = false; s->small_off = false; s->copy_idle = false;
     s->halo_on = false; s->epoch = 0; s->flags = nullptr;
     memset(s->peer_u, 0, sizeof(s->peer_u));
     memset(s->peer_flags, 0, sizeof(s->peer_flags));
@@ -345,6 +346,13 @@ static int64_t ecg_blocks(const FwbSim *s)
     const bool tile_kernel = s->entry->n_state > 4 && s->tile_rec && s->pos_of && s->defer;
     if (tile_kernel && s->packed && !s->halo_on) return (s->n_myo + BLOCK_THREADS - 1) / BLOCK_THREADS;
     return step_blocks(s->g);
+}
+
+extern "C" int fwb_sim_set_copy_idle(FwbSim *s, int on)
+{
+    if (!s) return FWB_E_ARG;
+    s->copy_idle = on != 0;
+    return 0;
 }
 
 extern "C" int fwb_sim_set_packed(FwbSim *s, int on)
@@ -732,6 +740,7 @@ extern "C" int fwb_sim_run(FwbSim *s, int64_t n_steps)
         }
         if (s->packed && !s->halo_on) { k.node_of = s->node_of; k.n_packed = s->n_myo; }
         k.brick = s->brick_ok ? 1 : 0;
+        k.copy_idle = s->copy_idle ? 1 : 0;
         k.tmap_host = &s->tmap[s->cur];
         if (s->halo_on) {
             Halo &h = k.halo;

@@ -90,6 +90,9 @@ struct StepCommon {
     uint32_t *defer_ctr;        // [0] entries in defer_list, [1] finished blocks of that kernel
     const int32_t *node_of;     // PACKED mode (sparse tissue): flat node of each compact index;
     int64_t n_packed;           // block t owns compact nodes [256 t, 256 t + 256) of n_packed
+    int copy_idle;              // ring kernel: lanes of listed chunks that own no updated node
+                                // store u -> u_new (the value that is there already), so that
+                                // every 32-byte sector of u_new is written whole
     int brick;                  // the launch carries a tensor map of u (interior tiles use it)
     const void *tmap_host;      // HOST pointer to that CUtensorMap (read by the launcher only)
 };
@@ -981,6 +984,11 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A, const __grid_constant__ C
             const double uu = P.u[n];
             if (a < 0 && uu > P.act_thr) P.act_t[n] = P.t;
         }
+        // Whole sectors: a partially written 32-byte sector makes L2 fetch the rest from DRAM
+        // before it can write it back (30 % fibrosis: three sectors in four).  Where the host
+        // has checked that both potential buffers agree on the nodes the solver does not
+        // update, the idle lanes of a listed chunk store the value that is there already.
+        if (P.copy_idle && !myo && chunk >= 0 && n < g.n_nodes) P.u_new[n] = __ldg(P.u + n);
 
         double un[K];
         if (myo) {

@@ -83,6 +83,7 @@ class DeviceSimulation:
         eng.create_sim(_lib.MODEL_IDS[model._MODEL], model._param_vector(), self.dt)
         if self.slow_offset:
             _lib.check(eng.L.fwb_sim_set_slow_offset(eng.sim, self.slow_offset))
+        eng.update_copy_idle()
         self.t, self.step = 0.0, 0
         self.stims, self.trackers = [], []
         self._shim = _Shim(self)
@@ -219,6 +220,7 @@ class DeviceSimulation:
         eng.ubuf[cur ^ 1].copy_(bufs["u_new"], non_blocking=True)
         for slot, name in enumerate(self.state_names):
             eng.upload_state(slot, bufs[name])
+        eng.update_copy_idle()
         eng.synchronize()
 
     def collect(self):

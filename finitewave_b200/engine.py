@@ -104,6 +104,9 @@ class Engine:
         rank (its tissue feeds weights and stimuli, its nodes are never updated here)."""
         dev = self.device
         self._halo = (bool(halo[0]), bool(halo[1]))
+        self._has_special = special_boundaries is not None and bool(np.any(
+            special_boundaries.cpu().numpy() if isinstance(special_boundaries, torch.Tensor)
+            else np.asarray(special_boundaries)))
         self.destroy_sim()      # it borrows the index structures replaced below
         if isinstance(mesh, torch.Tensor):
             m = mesh.to(dev)
@@ -269,6 +272,23 @@ class Engine:
         """rows = (r0, r1): only those slices of axis 0 (host_out has that many)."""
         src = self.ubuf[which] if rows is None else self.ubuf[which][rows[0]:rows[1]]
         _as_tensor(host_out).copy_(src, non_blocking=True)
+
+    def update_copy_idle(self):
+        """Whole-sector stores of u_new in the ring kernel (fwb_sim_set_copy_idle): allowed
+        when no stimulus can touch a node the solver does not update (no special boundaries)
+        and both potential buffers agree on all such nodes right now -- then storing
+        u -> u_new there changes nothing.  Call after every upload of u / u_new."""
+        if not self.sim:
+            return
+        # (opt-in, FWB_COPY_IDLE=1: measured on a B200 it costs C2 3 % instead of saving the
+        # partial-sector fills -- 43.8 vs 45.4 G upd/s in one call, profiles/r2_history.md)
+        ok = not getattr(self, "_has_special", False) and os.environ.get("FWB_COPY_IDLE") == "1"
+        if ok:
+            halo = getattr(self, "_halo", (False, False))
+            own = slice(1 if halo[0] else 0, -1 if halo[1] else None)   # ghost slices are never listed
+            differ = (self.ubuf[0][own] != self.ubuf[1][own]) & (self.update[own] == 0)
+            ok = not bool(differ.any().item())
+        check(self.L.fwb_sim_set_copy_idle(self.sim, int(ok)), "fwb_sim_set_copy_idle")
 
     def needs_allocation(self, n_state):
         return (self.state is None or self.ubuf[0] is None

@@ -228,6 +228,7 @@ class CardiacModel:
         # state rows only exist for updated nodes; where the host arrays hold something
         # else than init_* on the other nodes, downloads must preserve it
         self._keep_offnodes = [c != 0 for c in eng.off_fill()]
+        eng.update_copy_idle()
 
     def _partition(self):
         """Who handles what, from the sequences as they are NOW (the reference re-reads them
@@ -389,6 +390,7 @@ class CardiacModel:
                     self._download()
                 self.stim_sequence.stimulate_next()
                 eng.upload_dense(eng.current(), self._host_array("u"))
+                eng.update_copy_idle()
                 host_view_valid = False
 
             # ---- the device steps ---------------------------------------------------

@@ -195,6 +195,9 @@ class MultiEngine:
             e.upload_state(slot, host[a:b], fill=fill, rows=loc)
         self._each(one)
 
+    def update_copy_idle(self):
+        self._each(lambda r, e: e.update_copy_idle())
+
     def off_fill(self):
         per = [e.off_fill() for e in self.engines]
         return [sum(p[i] for p in per if i < len(p)) for i in range(max(len(p) for p in per))] \

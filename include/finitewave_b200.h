@@ -297,6 +297,12 @@ FWB_API int fwb_sim_set_tiles(FwbSim *sim, const uint32_t *tile_rec, const uint8
  * a ventricle wall, heavy fibrosis): a block owns 256 consecutive compact nodes instead of
  * one spatial tile, so every warp is full; u operands by plain loads.  on = 0: tile mode. */
 FWB_API int fwb_sim_set_packed(FwbSim *sim, int on);
+/* Ring kernel (HBM-bound models): let the lanes of a listed chunk that own no updated node
+ * store u -> u_new, so that u_new is written in whole 32-byte sectors (a partially written
+ * sector costs a DRAM read of the rest).  The CALLER asserts that both u buffers hold the
+ * same value on every node the solver does not update (then the stores change nothing) and
+ * that no stimulus can touch such a node (no special boundaries). */
+FWB_API int fwb_sim_set_copy_idle(FwbSim *sim, int on);
 /* rebind after the caller re-uploaded / recomputed arrays (same sizes) */
 FWB_API int fwb_sim_set_weights(FwbSim *sim, const double *weights);
 FWB_API int fwb_sim_set_params(FwbSim *sim, const double *params, int n_params, double dt);

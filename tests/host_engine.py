@@ -94,6 +94,9 @@ class OracleEngine:
         self.state = np.zeros((max(n_state, 1), self.ld))     # only its shape is looked at
         self._off = [0] * n_state
 
+    def update_copy_idle(self):
+        pass
+
     def needs_allocation(self, n_state):
         return (self.state is None or self.ubuf[0] is None
                 or self.state.shape != (max(n_state, 1), self.ld))
