@@ -331,32 +331,6 @@ def e2e_host_api(workload, steps_per_call, calls, scale=1.0, slices=None, device
             "launches": launches, "initialize_seconds": init_s}
 
 
-def e2e_slabs(sim, info, steps_per_call, calls, dist, device):
-    """N > 1: every rank round-trips its slab (u, u_new, all state arrays) through pinned
-    host memory around each run of `steps_per_call` steps; max over ranks."""
-    import torch
-    bufs = sim.host_buffers()
-    sim.download_host(bufs)
-    per_call = sum(b.numel() * 8 for b in bufs.values())
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(calls):
-        sim.upload_host(bufs)
-        sim.run(steps_per_call)
-        sim.download_host(bufs)
-    torch.cuda.synchronize()
-    sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-    nm = torch.tensor([info["n_myo"]], dtype=torch.float64, device=device)
-    dist.all_reduce(nm, op=dist.ReduceOp.SUM)
-    return {"value": float(nm.item()) * steps_per_call * calls / float(sec.item()), "unit": UNIT,
-            "h2d_bytes_per_step": per_call, "d2h_bytes_per_step": per_call,
-            "steps_per_call": steps_per_call, "calls": calls,
-            "api": "finitewave_b200.devrun.DeviceSimulation upload_host -> run -> download_host "
-                   "per rank (bytes are per rank and call); one e2e step = one call"}
-
-
 def e2e_multi_gpu(args, world):
     """N > 1, rank 0 only, after the other ranks have exited: the C5 family through
     `TP063D.run()` on `world` GPUs of this one process.  The slab thickness per GPU is the

@@ -55,7 +55,6 @@ def requested_devices(model):
 
 def supported(model, shape, devices):
     """(ok, reason): can this model / tissue run slab-decomposed in one process?"""
-    from .stimulation import StimSequence  # noqa: F401
     if min(devices) < 0 or max(devices) >= torch.cuda.device_count():
         return False, "a requested device is not visible"
     if shape[-1] % 32 != 0:
