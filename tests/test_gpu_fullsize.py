@@ -139,6 +139,47 @@ def test_c5_tp06_slab_invariance_and_oracle_line():
     assert np.ptp(got) > 20
 
 
+def test_c4_ventricle_window_equals_small_oracle_run():
+    """C4: TP06 on the ventricle-shaped shell in a 512^3 box (helix fibres, 19-point stencil;
+    the tissue fills its tiles poorly, so the tile kernel runs in PACKED mode).  A window at
+    the apex -- where the stimulus sits -- equals the same window of an oracle run on a 72^3
+    sub-box cut out of the same mesh and fibre field (locality: 24 steps, 26 nodes of margin)."""
+    import torch
+    import finitewave_b200 as fw
+    from finitewave_b200 import workloads
+    from finitewave_b200.devrun import DeviceSimulation
+    from oracle import oracle
+
+    n, steps, m, marg = 512, 24, 72, 26
+    dev = torch.device("cuda")
+    mesh, fib = workloads.ventricle_shell((n, n, n), dev)
+    sim = DeviceSimulation(_cfg(fw.TP063D()), mesh, fibers=fib)
+    sim.add_stim(fw.StimVoltageCoord3D(0, -20, 0, n, 0, n, 0, 40))   # its edge crosses the window
+    assert sim.n_myo / (sim.engine.n_work * 32) < 0.85          # -> packed mode
+    sim.run(steps)
+    o = (220, 220, 8)
+    box = tuple(slice(a, a + m) for a in o)
+    sub_mesh = mesh[box].cpu().numpy().copy()
+    sub_fib = fib[box].cpu().numpy().copy()
+    del fib
+    case = dict(model="tp06", shape=[m, m, m], dt=0.01, dr=0.25, t_max=steps * 0.01 - 0.005,
+                mesh=sub_mesh, fibers=sub_fib,
+                stims=[dict(kind="voltage_coord", t=0, value=-20, box=[0, m, 0, m, 0, 40 - o[2]])])
+    ref = oracle.simulate(case)
+    assert int(ref["step"]) == steps
+    win = (slice(marg, m - marg),) * 3
+    big = tuple(slice(a + marg, a + m - marg) for a in o)
+    tissue = sub_mesh[win] == 1
+    assert tissue.sum() > 1000
+    u = sim.u_device()[big].cpu().numpy()
+    assert np.max(np.abs(u - ref["u"][win])) <= 1e-9 * np.max(np.abs(ref["u"]))
+    for name in ("m", "h", "cass", "xs", "Ki"):
+        got = sim.state_host(name)[big]
+        want = ref[name][win]
+        assert np.max(np.abs(got - want)) <= 1e-9 * max(np.max(np.abs(want)), 1e-300), name
+    assert np.ptp(u[tissue]) > 10                                # the wave is inside the window
+
+
 def test_full_size_run_is_deterministic():
     import torch
     from finitewave_b200 import workloads
