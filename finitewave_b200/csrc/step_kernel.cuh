@@ -608,8 +608,8 @@ __device__ __forceinline__ void tile_body(const StepArgs<M> &A, const CUtensorMa
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (packed) {
         rec.x = t * (uint32_t)BLOCK_THREADS;
-        const int64_t left = P.n_packed - (int64_t)rec.x;
-        rec.y = left >= BLOCK_THREADS ? (uint32_t)BLOCK_THREADS : (uint32_t)(left > 0 ? left : 0);
+        const uint32_t np = (uint32_t)P.n_packed;                 // (< 2^31: node ids are int32)
+        rec.y = np > rec.x ? min(np - rec.x, (uint32_t)BLOCK_THREADS) : 0u;
     } else {
         rec = __ldg(P.tile_rec + t);
     }
