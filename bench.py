@@ -164,6 +164,9 @@ def port_time(workload, budget_s, steps=None, warmup=3):
 
 def reference_time(workload, steps, warmup):
     """The reference itself (numba) on its bounded sample -> cpu_baseline dict, sec, steps."""
+    # torchrun sets OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every core
+    if os.environ.get("OMP_NUM_THREADS") in ("1", ""):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import ref_numba
     r = ref_numba.time_reference("c5" if workload == "c5t" else workload, steps, warmup=warmup)
     return dict(value=r["n_myo"] * r["steps"] / r["seconds"], unit=UNIT, cores=r["threads"],
