@@ -16,4 +16,4 @@ for w in d["other_workloads"]:
     print("  ", w.get("workload","")[:70], "|", round(w.get("value",0)/1e9,3), round(w.get("hbm_frac",0),4), w.get("device_ms_per_1000_steps"), w.get("error"))
 print(d["cpu_baseline"])
 PY
-bash scripts/gpu_profile_r2.sh r2c
+# (ncu captures: scripts/gpu_profile_r2.sh TAG)
