@@ -250,6 +250,38 @@ def time_device(sim, steps, warmup, dist=None, propagate=0):
     return ms, sim.launch_count() - l0
 
 
+def halo_check(sim, rank, world, dist, device):
+    """N > 1, after the timed steps: every slab's ghost slice must be, bit for bit, the owned
+    boundary slice of the neighbour that stored it (the last in-kernel halo exchange has
+    landed: DeviceSimulation.run ends with fwb_sim_halo_sync).  Each rank contributes an
+    order-dependent fingerprint (sum and sum of squares of the slice, taken in the same
+    element order on both sides) of its two ghost slices and its two owned boundary slices."""
+    import torch
+    u = sim.u_device()
+    dist.barrier()
+
+    def fp(x):
+        x = x.reshape(-1)
+        return [float(x.sum().item()), float((x * x).sum().item())]
+    lo, hi = sim.halo
+    mine = torch.tensor(
+        (fp(u[0]) if lo else [0.0, 0.0]) + (fp(u[1 if lo else 0])) +
+        (fp(u[-2 if hi else -1])) + (fp(u[-1]) if hi else [0.0, 0.0]),
+        dtype=torch.float64, device=device)          # [ghost_lo, own_first, own_last, ghost_hi]
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    bad = 0
+    for r in range(world - 1):
+        a, b = allv[r].tolist(), allv[r + 1].tolist()
+        if a[6:8] != b[2:4]:      # r's ghost_hi  vs  (r+1)'s first owned slice
+            bad += 1
+        if b[0:2] != a[4:6]:      # (r+1)'s ghost_lo  vs  r's last owned slice
+            bad += 1
+    return {"ok": bad == 0, "interfaces": world - 1, "mismatches": bad,
+            "what": "ghost slice == neighbour's owned boundary slice after the timed steps "
+                    "(bitwise fingerprints, all-gathered)"}
+
+
 def host_model(workload, scale=1.0, slices=None, devices=None):
     """The workload through the PUBLIC host API (numpy tissue, model classes).  `slices`:
     thickness along axis 0 (C5 family: 128 per GPU); `devices`: model.devices."""
@@ -454,6 +486,12 @@ def run_b200(args):
         n_total = float(nm.item())
     else:
         ms_max, n_total = ms, float(info["n_myo"])
+    halo = None
+    if dist is not None:
+        try:
+            halo = halo_check(sim, rank, world, dist, device)
+        except Exception as e:
+            halo = {"ok": False, "error": repr(e)}
     value = n_total * args.steps / (ms_max * 1e-3)
     kernel_ms = ms / args.steps
     achieved = info["bytes_per_node"] * info["n_myo"] / (kernel_ms * 1e-3) / 1e9
@@ -471,6 +509,7 @@ def run_b200(args):
             "state": f"after {args.propagate} propagation steps + {args.warmup} warm-up steps "
                      "from the stimulus at t = 0", "scale": args.scale},
         "gpu_launches": launches,
+        "halo_check": halo,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
