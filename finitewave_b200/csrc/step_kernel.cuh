@@ -985,10 +985,13 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A, const __grid_constant__ C
             if (a < 0 && uu > P.act_thr) P.act_t[n] = P.t;
         }
         // Whole sectors: a partially written 32-byte sector makes L2 fetch the rest from DRAM
-        // before it can write it back (30 % fibrosis: three sectors in four).  Where the host
-        // has checked that both potential buffers agree on the nodes the solver does not
-        // update, the idle lanes of a listed chunk store the value that is there already.
-        if (P.copy_idle && !myo && chunk >= 0 && n < g.n_nodes) P.u_new[n] = __ldg(P.u + n);
+        // (30 % fibrosis: three sectors in four).  Where the host has checked that both
+        // potential buffers agree on the nodes the solver does not update, the idle lanes of a
+        // listed chunk carry the value that is there already and the warp stores its 256 bytes
+        // with ONE instruction below (two partial stores per sector would still fill).
+        const bool idle = P.copy_idle && !myo && chunk >= 0 && n < g.n_nodes;
+        double out = 0.0;
+        if (idle) out = __ldg(P.u + n);
 
         double un[K];
         if (myo) {
@@ -1024,9 +1027,10 @@ step_kernel_tma(const __grid_constant__ StepArgs<M> A, const __grid_constant__ C
             StateIOTma<M> io{row + K * TMA_SEG, P.state + c, g.ld};
             M::ionic(uc, acc, io, A.c);
 
-            P.u_new[n] = acc;
+            out = acc;
             if (HALO && side) side->peer_dst[n - side->first] = acc;
         }
+        if (myo || idle) P.u_new[n] = out;
 
         if (HALO && side) {
             __threadfence_system();

@@ -280,9 +280,10 @@ class Engine:
         u -> u_new there changes nothing.  Call after every upload of u / u_new."""
         if not self.sim:
             return
-        # (opt-in, FWB_COPY_IDLE=1: measured on a B200 it costs C2 3 % instead of saving the
-        # partial-sector fills -- 43.8 vs 45.4 G upd/s in one call, profiles/r2_history.md)
-        ok = not getattr(self, "_has_special", False) and os.environ.get("FWB_COPY_IDLE") == "1"
+        # (FWB_COPY_IDLE=0 turns it off.  C2 on a B200: DRAM reads 1.268 -> 1.175 GB per step,
+        # total traffic 1.10 x -> 1.04 x the algorithmic bytes, 46.1 -> 46.9 G upd/s in one call,
+        # profiles/r2_history.md)
+        ok = not getattr(self, "_has_special", False) and os.environ.get("FWB_COPY_IDLE") != "0"
         if ok:
             halo = getattr(self, "_halo", (False, False))
             own = slice(1 if halo[0] else 0, -1 if halo[1] else None)   # ghost slices are never listed
