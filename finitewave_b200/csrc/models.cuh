@@ -339,7 +339,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         double dt, gna, gsi, gkp, gb;
         double E_Na, E_K, G_K, E_K1, G_K1;   // parameter-only (:478, :337-338, :496, :404)
         // fast path only (ionic_fast): exp(offset * slope) of the shared-slope exponentials
-        double k47, k32, kd, kf1, kf2, kf3, kx1, kx2, kxa, kxb;
+        double k47, k32, kd, kf1, kf2, kf3, kx1, kx2, kxa, kxb, kdn, kfn;
         double ec[8];      // fexp's reduction / polynomial constants (fexp_fill_consts)
     };
     static bool derive(const double *p, double dt, Consts &c)
@@ -357,6 +357,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         c.kf1 = exp(-0.02 * 30.); c.kf2 = exp(-0.2 * 30.); c.kf3 = exp(0.15 * 28.);
         c.kx1 = exp(-0.06 * 20.); c.kx2 = exp(-0.04 * 20.);
         c.kxa = exp(0.04 * (77. - 35.)); c.kxb = exp(-0.04 * 35.);
+        c.kdn = 0.095 * exp(0.01 * 5.); c.kfn = 0.012 * exp(-0.008 * 28.);
         return true;
     }
     FWB_HD static double gate(double var, double dt, double alpha, double beta)
@@ -401,9 +402,12 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
     //    dt (inf - x) / tau is dt (a - x (a + b)): no division at all
     //  * a = n1 / A, b = n2 / B are put over the common denominator A B: one reciprocal
     //    (frcp3) per gate; K_1x = a / (a + b) likewise
-    //  * exponentials with commensurable slopes share one evaluation (-0.1, -0.02 / -0.04 /
-    //    -0.06 / -0.2, 0.05 / 0.15); Xi needs none: (exp(.04 (u + 77)) - 1) / exp(.04 (u + 35))
-    //    = exp(1.68) - exp(-1.4) exp(-.04 u)
+    //  * exponentials with commensurable slopes share one evaluation: exp(-0.002 u) is the
+    //    common root of -0.008 / -0.01 / -0.02 / -0.04 / -0.06 (six multiplications replace
+    //    four evaluations; the 30th power carries 30 x the root's half-ulp error), -0.1 / -0.2
+    //    share another, 0.05 / 0.15 a third; Xi needs none:
+    //    (exp(.04 (u + 77)) - 1) / exp(.04 (u + 35)) = exp(1.68) - exp(-1.4) exp(-.04 u)
+    //  * exp(-2.535e-7 u), |u| < 300: four Taylor terms (remainder < 2e-18)
     //  * log(cai) by flog
     // ------------------------------------------------------------------------------------
     FWB_HD static double gatef(double x, double dt, double a, double ab) { return fma(dt, fma(-x, ab, a), x); }
@@ -419,9 +423,12 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
             return fexp_fast_p(x > 700.0 ? 700.0 : x, ec);
         };
         (void)EXN; (void)EXC;
-        const double g01 = EX(-0.1 * u);
-        const double g02 = EX(-0.02 * u), g04 = g02 * g02, g06 = g04 * g02;
-        const double g08 = g04 * g04, g20 = g08 * g08 * g04;          // exp(-0.2 u)
+        const double r1 = EX(-0.002 * u), r2 = r1 * r1, r4 = r2 * r2;  // exp(-0.008 u)
+        const double g001 = r4 * r1;                                   // exp(-0.01 u)
+        const double g02 = g001 * g001, g04 = g02 * g02, g06 = g04 * g02;
+        // exp(-0.1 u) keeps its own evaluation: 1 - k47 g01 cancels around u = -47.13, where a
+        // 50th power's 5e-15 would show as 3e-11 in alpha_m
+        const double g01 = EX(-0.1 * u), g20 = g01 * g01;               // exp(-0.2 u)
         const double g05 = EX(0.05 * u), g15 = g05 * g05 * g05;
         // ---- I_Na (calc_ina :185-241)
         double ah, sh, aj, sj;                                          // alpha, alpha + beta
@@ -429,7 +436,9 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
             ah = 0.;
             sh = frcp3(0.13 * (1. + EX((u + 10.66) * (-1. / 11.1))));
             aj = 0.;
-            sj = 0.3 * EX(-2.535e-07 * u) * frcp3(fma(c.k32, g01, 1.));
+            const double z = -2.535e-07 * u;          // |z| < 7.7e-5 (fast_ok: |u| < 300)
+            const double ez = fma(z, fma(z, fma(z, 1. / 6., 0.5), 1.), 1.);
+            sj = 0.3 * ez * frcp3(fma(c.k32, g01, 1.));
         } else {
             ah = 0.135 * EX((80. + u) * (-1. / 6.8));
             sh = ah + (3.56 * EX(0.079 * u) + 3.1e5 * EX(0.35 * u));
@@ -454,7 +463,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
         const double E_Si = fma(-13.0287, flog(cai), 7.7);
         const double I_Si = c.gsi * d * f * (u - E_Si);
         {
-            const double n1 = 0.095 * EX(-0.01 * (u - 5.));
+            const double n1 = c.kdn * g001;
             const double a = 1. + EX(-0.072 * (u - 5.));
             const double n2 = 0.07 * EX(-0.017 * (u + 44.));
             const double b = fma(c.kd, g05, 1.);
@@ -462,7 +471,7 @@ template <> struct Model<FWB_MODEL_LUO_RUDY91> {
             d = gatef(d, dt, n1 * b * r, fma(n1, b, n2 * a) * r);
         }
         {
-            const double n1 = 0.012 * EX(-0.008 * (u + 28.));
+            const double n1 = c.kfn * r4;
             const double a = fma(c.kf3, g15, 1.);
             const double n2 = 0.0065 * c.kf1 * g02;
             const double b = fma(c.kf2, g20, 1.);
