@@ -99,3 +99,55 @@ def test_slab_rows_of_the_multi_engine_cover_the_tissue():
             assert lo == a - int(halo[0]) and hi == b + int(halo[1])
             seen[a:b] += 1
         assert (seen == 1).all()
+
+
+# ---------------------------------------------------------------------------
+# bench.py's halo_check (N > 1): over gloo, world size 3, with CPU tensors standing in for the
+# slabs' device buffers -- consistent slabs pass, one stale ghost slice is reported.
+# ---------------------------------------------------------------------------
+class _FakeSlab:
+    def __init__(self, u, halo):
+        self._u, self.halo = u, halo
+
+    def u_device(self):
+        return self._u
+
+
+def _halo_worker(rank, world, port, corrupt, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from finitewave_b200 import slab
+    n0 = 17
+    g = torch.from_numpy(np.random.default_rng(3).normal(size=(n0, 5, 6)))      # the whole tissue
+    lo, hi, halo = slab.stored_range(slab.partition(n0, world)[rank], n0)
+    u = g[lo:hi].clone()
+    if corrupt and rank == 1:
+        u[0, 2, 3] += 1e-13                     # rank 1's lower ghost slice is stale by one ulp-ish
+    res = _bench().halo_check(_FakeSlab(u, halo), rank, world, dist, torch.device("cpu"))
+    out.put((rank, res["ok"], res["interfaces"], res["mismatches"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("corrupt", [False, True])
+def test_halo_check_over_gloo_world3(corrupt):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, 3, port, corrupt, out)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (not corrupt, 2, 1 if corrupt else 0)
+    assert [r[1:] for r in res] == [want] * 3, res
