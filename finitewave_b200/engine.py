@@ -313,7 +313,10 @@ class Engine:
             if self._offfill is None or len(self._offfill) <= slot:
                 self._offfill = torch.zeros(max(self.n_state, slot + 1), dtype=torch.int64,
                                             device=self.device)
-            self._offfill[slot] = 0
+            # (not `self._offfill[slot] = 0`: indexed assignment of a Python scalar goes through
+            # a host -> device copy that waits for the stream, i.e. for the upload just queued --
+            # measured: it serialised the slabs' uploads of a multi-GPU run)
+            self._offfill.narrow(0, slot, 1).zero_()
             check(self.L.fwb_count_offfill(_ptr(self.staging), float(fill), self.n_nodes,
                                            _ptr(self.chunk_bits), _ptr(self._offfill[slot:]),
                                            _stream()), "fwb_count_offfill")
